@@ -1,0 +1,257 @@
+/*
+ * seqlib_b200.h -- C ABI of the B200-native seed-and-extend engine.
+ *
+ * This is the drop-in boundary: plain pointers and
+ * sizes, no C++/torch types.  Every entry point names the reference
+ * interface it replaces (paths relative to the SeqLib tree).  The library
+ * behind it is CUDA only: there is no CPU fallback, every call that needs
+ * the device fails with B200_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Conventions
+ *   - return value: 0 on success, a negative B200_ERR_* code otherwise;
+ *     b200_last_error() returns a thread-local message.
+ *   - every buffer handed back through an out-parameter of
+ *     b200_mem_align_batch() is owned by the b200_results_t handle and is
+ *     released by b200_results_free().
+ */
+#ifndef SEQLIB_B200_H
+#define SEQLIB_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK            0
+#define B200_ERR_ARG      -1
+#define B200_ERR_CUDA     -2
+#define B200_ERR_NOMEM    -3
+#define B200_ERR_IO       -4
+#define B200_ERR_LIMIT    -5   /* input outside the supported envelope */
+
+const char *b200_last_error(void);
+
+/* ------------------------------------------------------------------ */
+/* Options: field-for-field the layout of bwa's mem_opt_t             */
+/* (bwa/bwamem.h:52-84) so a binding can pass its own struct through. */
+/* ------------------------------------------------------------------ */
+typedef struct b200_mem_opt {
+    int a, b;
+    int o_del, e_del;
+    int o_ins, e_ins;
+    int pen_unpaired;
+    int pen_clip5, pen_clip3;
+    int w;
+    int zdrop;
+    uint64_t max_mem_intv;
+    int T;
+    int flag;
+    int min_seed_len;
+    int min_chain_weight;
+    int max_chain_extend;
+    float split_factor;
+    int split_width;
+    int max_occ;
+    int max_chain_gap;
+    int n_threads;
+    int chunk_size;
+    float mask_level;
+    float drop_ratio;
+    float XA_drop_ratio;
+    float mask_level_redun;
+    float mapQ_coef_len;
+    int mapQ_coef_fac;
+    int max_ins;
+    int max_matesw;
+    int max_XA_hits, max_XA_hits_alt;
+    int8_t mat[25];
+} b200_mem_opt_t;
+
+/* replaces mem_opt_init() (bwa/bwamem.c:74-110) + bwa_fill_scmat()
+ * (bwa/bwa.c:136-145); fills *opt in place. */
+void b200_mem_opt_init(b200_mem_opt_t *opt);
+void b200_fill_scmat(int a, int b, int8_t mat[25]);
+
+/* ------------------------------------------------------------------ */
+/* Index                                                              */
+/* ------------------------------------------------------------------ */
+typedef struct b200_index b200_index_t;
+
+/* One reference contig as the host sees it (bntann1_t, bwa/bntseq.h:41-48). */
+typedef struct b200_contig {
+    int64_t offset;
+    int32_t len;
+    int32_t n_ambs;
+    uint32_t gi;
+    int32_t is_alt;
+    const char *name;
+    const char *anno;
+} b200_contig_t;
+
+/* Host view of an index in bwa's own layout; all pointers owned by the
+ * index handle.  bwt is the Occ-interleaved array of bwt_bwtupdate_core()
+ * (bwa/bwtindex.c:149-171), sa is sampled every sa_intv ranks with
+ * sa[0] = -1 (bwa/bwt.c:62-84), pac is the forward strand, 4 bases/byte. */
+typedef struct b200_index_view {
+    uint64_t primary, L2[5], seq_len, bwt_size;
+    const uint32_t *bwt;
+    int sa_intv;
+    uint64_t n_sa;
+    const uint64_t *sa;
+    int64_t l_pac;
+    const uint8_t *pac;
+    int32_t n_seqs;
+    const b200_contig_t *contigs;
+} b200_index_view_t;
+
+/* replaces BWAIndex::ConstructIndex (src/BWAIndex.cpp:83-180): names/seqs
+ * are n NUL-terminated strings.  Ambiguous bases become lrand48()&3, drawn
+ * in the reference's order (two passes, src/BWAIndex.cpp:107-113,217).
+ * The suffix sort, BWT, Occ interleave and SA sampling run on the GPU.
+ * flags: bit0 = keep a host copy in bwa layout (needed for WriteIndex). */
+int b200_index_construct(int n, const char *const *names, const char *const *seqs,
+                         int flags, b200_index_t **out);
+
+/* Builds an index over a 2-bit forward pac that is already on the host
+ * (4 bases/byte, bwa order).  Same engine as b200_index_construct without
+ * the ASCII pass; used for the 3 Gb synthetic reference. */
+int b200_index_construct_pac(int64_t l_pac, const uint8_t *pac, int n_seqs,
+                             const b200_contig_t *contigs, int flags, b200_index_t **out);
+
+/* replaces BWAIndex::LoadIndex -> bwa_idx_load (bwa/bwa.c:289-316). */
+int b200_index_load(const char *prefix, b200_index_t **out);
+/* replaces BWAIndex::WriteIndex (src/BWAIndex.cpp:382-406): .bwt .sa .pac .ann .amb */
+int b200_index_write(const b200_index_t *idx, const char *prefix);
+
+/* replaces bwa_idx_destroy (bwa/bwa.c:323-335). */
+void b200_index_destroy(b200_index_t *idx);
+
+/* Host view (valid when the host copy was kept / loaded). */
+int b200_index_view(const b200_index_t *idx, b200_index_view_t *view);
+
+/* Device image: one contiguous blob (like bwa_idx2mem, bwa/bwa.c:362-401) so
+ * a single ncclBroadcast ships it.  export copies device->device into a
+ * caller-provided device buffer of b200_index_blob_bytes(); attach builds
+ * an index handle over such a buffer (the buffer must outlive the handle). */
+int64_t b200_index_blob_bytes(const b200_index_t *idx);
+int b200_index_export_blob(const b200_index_t *idx, void *dev_dst);
+int b200_index_attach_blob(void *dev_blob, int64_t nbytes, b200_index_t **out);
+/* contig table of an attached blob is read back from the blob itself. */
+
+int b200_index_n_seqs(const b200_index_t *idx);
+const char *b200_index_seq_name(const b200_index_t *idx, int rid);
+int64_t b200_index_seq_len(const b200_index_t *idx, int rid);
+int64_t b200_index_l_pac(const b200_index_t *idx);
+
+/* ------------------------------------------------------------------ */
+/* Alignment                                                          */
+/* ------------------------------------------------------------------ */
+
+/* One alignment region + its finished alignment: the union of
+ * mem_alnreg_t (bwa/bwamem.h:86-105) and mem_aln_t (bwa/bwamem.h:115-126)
+ * as produced by mem_align1() followed by mem_reg2aln(). */
+typedef struct b200_hit {
+    int64_t rb, re;
+    int64_t pos;
+    uint64_t hash;
+    int32_t qb, qe;
+    int32_t rid;
+    int32_t score, truesc, sub, alt_sc, csub, sub_n, w, seedcov;
+    int32_t secondary, secondary_all, seedlen0, n_comp, is_alt;
+    float frac_rep;
+    int32_t flag;       /* mem_aln_t.flag (0x100 for secondary) */
+    int32_t is_rev;
+    int32_t mapq;
+    int32_t NM;
+    int32_t aln_sub;    /* mem_aln_t.sub = max(sub, csub) */
+    int32_t n_cigar;
+    int32_t md_len;     /* strlen(MD) */
+    int64_t cigar_off;  /* index of the first CIGAR word in the cigar pool */
+    int64_t md_off;     /* byte offset of the MD string in the md pool */
+} b200_hit_t;
+
+typedef struct b200_results b200_results_t;
+
+typedef struct b200_results_view {
+    int64_t n_reads;
+    const int64_t *hit_off;   /* n_reads+1 entries; hits of read i are [hit_off[i], hit_off[i+1]) */
+    const b200_hit_t *hits;
+    const uint32_t *cigar;    /* BAM encoding len<<4|op, op 3 = clip (rewritten to S/H by the caller) */
+    const char *md;           /* NUL-terminated MD strings */
+    int64_t n_hits, n_cigar, n_md;
+} b200_results_view_t;
+
+/* Batch form of BWAAligner::alignSequence's compute
+ * (src/BWAAligner.cpp:104-128): per read mem_align1()
+ * (bwa/bwamem_extra.c:103-115) then mem_reg2aln() (bwa/bwamem.c:1119-1189)
+ * for every region, in region order.
+ *   seqs/seq_off : concatenated ASCII reads; read i = seqs[seq_off[i], seq_off[i+1])
+ *   hash_ids     : the per-read tie-break id, i.e. the caller's lrand48()
+ *                  draw (bwa/bwamem_extra.c:112); NULL = draw lrand48()
+ *                  here, one per read in order.
+ * Host buffers in, host buffers out; H2D/D2H copies are inside the call. */
+int b200_mem_align_batch(const b200_index_t *idx, const b200_mem_opt_t *opt,
+                         int64_t n_reads, const char *seqs, const int64_t *seq_off,
+                         const int64_t *hash_ids, b200_results_t **out);
+int b200_results_view(const b200_results_t *res, b200_results_view_t *view);
+void b200_results_free(b200_results_t *res);
+
+/* Device-resident form used by bench.py's "value" leg: the reads are
+ * uploaded once, each call runs all kernels and leaves results on the
+ * device.  n_launches (optional) receives the number of kernel launches. */
+typedef struct b200_batch b200_batch_t;
+int b200_batch_create(const b200_index_t *idx, const b200_mem_opt_t *opt,
+                      int64_t n_reads, const char *seqs, const int64_t *seq_off,
+                      const int64_t *hash_ids, b200_batch_t **out);
+int b200_batch_run(b200_batch_t *b, int *n_launches);
+int b200_batch_fetch(b200_batch_t *b, b200_results_t **out);
+void b200_batch_destroy(b200_batch_t *b);
+
+/* Per-stage device timings (ms, CUDA events on the launching stream) and
+ * work counters of the last b200_batch_run / b200_mem_align_batch. */
+typedef struct b200_stage_stats {
+    float ms_seed, ms_chain, ms_extend, ms_finalize, ms_total;
+    uint64_t occ_blocks;      /* Occ blocks fetched (32 B each)            */
+    uint64_t sa_reads;        /* suffix-array entries fetched (8 B each)   */
+    uint64_t ref_bytes;       /* packed reference bytes fetched            */
+    uint64_t sw_cells;        /* DP cells inside the adaptive band         */
+    uint64_t n_ext, n_global; /* ksw_extend2 / ksw_global2 calls           */
+    uint64_t n_overflow;      /* reads re-run with spill buffers           */
+    int n_launches;
+} b200_stage_stats_t;
+int b200_last_stats(b200_stage_stats_t *out);
+
+/* Stage dumps for parity tests (each mirrors one reference intermediate). */
+typedef struct b200_intv { uint64_t x0, x1, x2, info; } b200_intv_t; /* bwtintv_t, bwa/bwt.h:62-64 */
+int b200_debug_collect_intv(const b200_index_t *idx, const b200_mem_opt_t *opt,
+                            int64_t n_reads, const char *seqs, const int64_t *seq_off,
+                            int64_t **intv_off, b200_intv_t **intv);   /* free() both */
+
+/* ------------------------------------------------------------------ */
+/* ksw_extend2 batch (config 3 microbench + unit parity)              */
+/* replaces ksw_extend2 (bwa/ksw.c:416-515)                           */
+/* ------------------------------------------------------------------ */
+typedef struct b200_ext_job {
+    int32_t qlen, tlen;
+    int64_t q_off, t_off;    /* offsets into the query / target byte pools (nt4 codes 0..4) */
+    int32_t w, end_bonus, zdrop, h0;
+} b200_ext_job_t;
+typedef struct b200_ext_out {
+    int32_t score, qle, tle, gtle, gscore, max_off;
+} b200_ext_out_t;
+int b200_ksw_extend2_batch(int64_t n, const b200_ext_job_t *jobs,
+                           const uint8_t *qpool, int64_t qpool_len,
+                           const uint8_t *tpool, int64_t tpool_len,
+                           const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
+                           b200_ext_out_t *out, uint64_t *cells, float *kernel_ms);
+
+/* Device selection for multi-GPU processes (one process per GPU). */
+int b200_set_device(int ordinal);
+int b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
