@@ -1,0 +1,177 @@
+// fmindex.cuh -- FM-index primitives over the 32-byte Occ block layout.
+// Semantics follow bwa (bwa/bwt.c:53-275): rank k counts BWT symbols in
+// B0[0..k'] with k' = k - (k >= primary) because '$' is not stored.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct OccLoad { u32 c0, c1, c2, c3; u64 s0, s1; };
+
+HD OccLoad load_block(const DevIndex &ix, u64 blk)
+{
+    OccLoad r;
+#if defined(__CUDA_ARCH__)
+    const uint4 *p = reinterpret_cast<const uint4 *>(ix.occ + blk);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    r.c0 = a.x; r.c1 = a.y; r.c2 = a.z; r.c3 = a.w;
+    r.s0 = (u64)b.x | (u64)b.y << 32; r.s1 = (u64)b.z | (u64)b.w << 32;
+#else
+    const OccBlock &b = ix.occ[blk];
+    r.c0 = b.cnt[0]; r.c1 = b.cnt[1]; r.c2 = b.cnt[2]; r.c3 = b.cnt[3];
+    r.s0 = b.sym[0]; r.s1 = b.sym[1];
+#endif
+    return r;
+}
+
+// number of symbols equal to c among the lowest n (0..32) symbols of w
+HD int cnt_word(u64 w, int c, int n)
+{
+    u64 t = w ^ (0x5555555555555555ull * (u64)c);       // matching symbols become 00
+    u64 z = ~(t | (t >> 1)) & 0x5555555555555555ull;
+    u64 m = n >= 32 ? ~0ull : ((1ull << (2 * n)) - 1);
+    return popc64(z & m);
+}
+
+// counts of A,C,G,T in the first r (1..64) symbols of a loaded block, added to the block base
+HD void block_rank4(const OccLoad &b, int r, u64 cnt[4])
+{
+    int n0 = r < 32 ? r : 32, n1 = r - n0;
+    int a = cnt_word(b.s0, 0, n0) + cnt_word(b.s1, 0, n1);
+    int c = cnt_word(b.s0, 1, n0) + cnt_word(b.s1, 1, n1);
+    int g = cnt_word(b.s0, 2, n0) + cnt_word(b.s1, 2, n1);
+    cnt[0] = b.c0 + a; cnt[1] = b.c1 + c; cnt[2] = b.c2 + g; cnt[3] = b.c3 + (r - a - c - g);
+}
+
+// bwt_2occ4 (bwa/bwt.c:189-220) on ranks k <= l; k or l may be (u64)-1.
+template <class Ctr>
+HD void occ4_pair(const DevIndex &ix, u64 k, u64 l, u64 ck[4], u64 cl[4], Ctr &ctr)
+{
+    const u64 NEG1 = ~0ull;
+    u64 kk = k, ll = l;
+    if (k != NEG1) kk = k - (k >= ix.primary);
+    if (l != NEG1) ll = l - (l >= ix.primary);
+    if (k == NEG1) { ck[0] = ck[1] = ck[2] = ck[3] = 0; }
+    if (l == NEG1) { cl[0] = cl[1] = cl[2] = cl[3] = 0; }
+    u64 bk = kk >> 6, bl = ll >> 6;
+    if (k != NEG1) {
+        OccLoad b = load_block(ix, bk);
+        ctr.occ_blocks++;
+        block_rank4(b, (int)(kk & 63) + 1, ck);
+        if (l != NEG1 && bl == bk) { block_rank4(b, (int)(ll & 63) + 1, cl); return; }
+    }
+    if (l != NEG1) {
+        OccLoad b = load_block(ix, bl);
+        ctr.occ_blocks++;
+        block_rank4(b, (int)(ll & 63) + 1, cl);
+    }
+}
+
+// bwt_extend (bwa/bwt.c:262-275): all four children of a bi-interval.
+template <class Ctr>
+HD void extend4(const DevIndex &ix, const Intv &ik, Intv ok[4], int is_back, Ctr &ctr)
+{
+    u64 tk[4], tl[4];
+    u64 a = is_back ? ik.x0 : ik.x1;      // x[!is_back]
+    u64 o = is_back ? ik.x1 : ik.x0;      // x[is_back]
+    occ4_pair(ix, a - 1, a - 1 + ik.x2, tk, tl, ctr);
+    u64 na[4], ns[4], no[4];
+    for (int i = 0; i < 4; ++i) { na[i] = ix.L2[i] + 1 + tk[i]; ns[i] = tl[i] - tk[i]; }
+    no[3] = o + (a <= ix.primary && a + ik.x2 - 1 >= ix.primary);
+    no[2] = no[3] + ns[3];
+    no[1] = no[2] + ns[2];
+    no[0] = no[1] + ns[1];
+    for (int i = 0; i < 4; ++i) {
+        ok[i].x2 = ns[i];
+        if (is_back) { ok[i].x0 = na[i]; ok[i].x1 = no[i]; }
+        else { ok[i].x1 = na[i]; ok[i].x0 = no[i]; }
+    }
+}
+
+// bwt_set_intv (bwa/bwt.h:82)
+HD void set_intv(const DevIndex &ix, int c, Intv &ik)
+{
+    ik.x0 = ix.L2[c] + 1; ik.x2 = ix.L2[c + 1] - ix.L2[c]; ik.x1 = ix.L2[3 - c] + 1; ik.info = 0;
+}
+
+// bwt_B0 (bwa/bwt.h:80): symbol x of the $-less BWT
+HD int bwt_sym(const OccLoad &b, int j) { return (int)(((j < 32 ? b.s0 : b.s1) >> (2 * (j & 31))) & 3); }
+
+// bwt_invPsi (bwa/bwt.c:53-59) with bwt_occ (bwa/bwt.c:107-129)
+template <class Ctr>
+HD u64 inv_psi(const DevIndex &ix, u64 k, Ctr &ctr)
+{
+    if (k == ix.primary) return 0;
+    u64 x = k - (k > ix.primary);
+    OccLoad b = load_block(ix, x >> 6);
+    ctr.occ_blocks++;
+    int c = bwt_sym(b, (int)(x & 63));
+    // bwt_occ(k, c): k == seq_len cannot reach here with k <= seq_len handled below
+    u64 n;
+    if (k == ix.seq_len) n = ix.L2[c + 1] - ix.L2[c];
+    else {
+        u64 kk = k - (k >= ix.primary);     // same block as x (kk == x unless k == primary, excluded above)
+        u64 cnt[4];
+        if ((kk >> 6) != (x >> 6)) { b = load_block(ix, kk >> 6); ctr.occ_blocks++; }
+        block_rank4(b, (int)(kk & 63) + 1, cnt);
+        n = cnt[c];
+    }
+    return ix.L2[c] + n;
+}
+
+// bwt_sa (bwa/bwt.c:86-96)
+template <class Ctr>
+HD u64 sa_lookup(const DevIndex &ix, u64 k, Ctr &ctr)
+{
+    u64 steps = 0, mask = (1ull << ix.sa_shift) - 1;
+    while (k & mask) { ++steps; k = inv_psi(ix, k, ctr); }
+    ctr.sa_reads++;
+#if defined(__CUDA_ARCH__)
+    return steps + __ldg(ix.sa + (k >> ix.sa_shift));
+#else
+    return steps + ix.sa[k >> ix.sa_shift];
+#endif
+}
+
+// base at position p (0 <= p < 2*l_pac) of the forward+reverse text: what
+// bns_get_seq (bwa/bntseq.c:403-424) unpacks from pac.
+HD int text_base(const DevIndex &ix, i64 p)
+{
+#if defined(__CUDA_ARCH__)
+    u64 w = __ldg(ix.text + (p >> 5));
+#else
+    u64 w = ix.text[p >> 5];
+#endif
+    return (int)((w >> (2 * (p & 31))) & 3);
+}
+
+// bns_pos2rid (bwa/bntseq.c:354-368) on a forward-strand position
+HD int pos2rid(const DevIndex &ix, i64 pos_f)
+{
+    if (pos_f >= ix.l_pac) return -1;
+    int lo = 0, hi = ix.n_seqs;      // contig_off[lo] <= pos_f < contig_off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (pos_f >= ix.contig_off[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// bns_depos (bwa/bntseq.h:87-90)
+HD i64 depos(const DevIndex &ix, i64 pos, int *is_rev)
+{
+    *is_rev = pos >= ix.l_pac;
+    return *is_rev ? (ix.l_pac << 1) - 1 - pos : pos;
+}
+
+// bns_intv2rid (bwa/bntseq.c:370-378)
+HD int intv2rid(const DevIndex &ix, i64 rb, i64 re)
+{
+    int is_rev;
+    if (rb < ix.l_pac && re > ix.l_pac) return -2;
+    int rid_b = pos2rid(ix, depos(ix, rb, &is_rev));
+    int rid_e = rb < re ? pos2rid(ix, depos(ix, re - 1, &is_rev)) : rid_b;
+    return rid_b == rid_e ? rid_b : -1;
+}
+
+} // namespace b200

@@ -1,0 +1,65 @@
+// hostutil.h -- small host-side helpers shared by the engine and the test harness.
+#pragma once
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include "pipeline.cuh"
+
+namespace b200 {
+
+inline Opt opt_from_abi(const b200_mem_opt_t &o)
+{
+    Opt p;
+    p.a = o.a; p.b = o.b; p.o_del = o.o_del; p.e_del = o.e_del; p.o_ins = o.o_ins; p.e_ins = o.e_ins;
+    p.pen_clip5 = o.pen_clip5; p.pen_clip3 = o.pen_clip3; p.w = o.w; p.zdrop = o.zdrop;
+    p.max_mem_intv = o.max_mem_intv; p.T = o.T; p.flag = o.flag; p.min_seed_len = o.min_seed_len;
+    p.min_chain_weight = o.min_chain_weight; p.max_chain_extend = o.max_chain_extend; p.split_factor = o.split_factor;
+    p.split_width = o.split_width; p.max_occ = o.max_occ; p.max_chain_gap = o.max_chain_gap;
+    p.mask_level = o.mask_level; p.drop_ratio = o.drop_ratio; p.mask_level_redun = o.mask_level_redun;
+    p.mapQ_coef_len = o.mapQ_coef_len; p.mapQ_coef_fac = o.mapQ_coef_fac;
+    for (int i = 0; i < 25; ++i) p.mat[i] = o.mat[i];
+    return p;
+}
+
+// log(i) from the host libm for every integer the MAPQ formula can see
+// (mem_approx_mapq_se, bwa/bwamem.c:982-1006): alignment span, seed coverage, sub_n + 1.
+inline std::vector<double> make_log_table(int maxlen, const Opt &opt)
+{
+    int n = 2 * maxlen + 8 * opt.w + 4096;
+    std::vector<double> t(n);
+    t[0] = 0.0;
+    for (int i = 1; i < n; ++i) t[i] = std::log((double)i);
+    return t;
+}
+
+// Fast-path capacities (typical 150-bp reads) and the spill capacities for reads that overflow them.
+inline Caps default_caps(int maxlen, bool tiny = false)
+{
+    Caps c;
+    c.maxlen = maxlen;
+    if (tiny) { c.intv = 6; c.wchains = 3; c.wseeds = 6; c.chains = 2; c.seeds = 4; c.regs = 2; c.hits = 1; c.cigar = 3; c.md = 6; c.z = 1024; }
+    else { c.intv = 48; c.wchains = 64; c.wseeds = 128; c.chains = 16; c.seeds = 48; c.regs = 16; c.hits = 4; c.cigar = 10; c.md = 48; c.z = (i64)maxlen * 64; }
+    return c;
+}
+
+inline Caps big_caps(int maxlen, const Opt &opt)
+{
+    Caps c;
+    c.maxlen = maxlen;
+    c.intv = 4 * maxlen + 64;
+    i64 ws = (i64)c.intv * std::min(opt.max_occ, 64) + 1024;
+    c.wseeds = (int)std::min<i64>(ws, 1 << 20);
+    c.wchains = c.wseeds;
+    c.chains = std::min(c.wchains, 4096);
+    c.seeds = std::min(c.wseeds, 1 << 16);
+    c.regs = std::min(c.seeds, 4096);
+    c.hits = c.regs;
+    c.cigar = 2 * maxlen + 8;
+    c.md = 4 * maxlen + 64;
+    int w4 = opt.w << 2;
+    i64 ncol = std::min<i64>(maxlen, 2 * (i64)w4 + 1);
+    c.z = ncol * ((i64)maxlen + 2 * w4 + 64);
+    return c;
+}
+
+} // namespace b200
