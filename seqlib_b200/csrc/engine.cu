@@ -1,0 +1,525 @@
+// engine.cu -- read-batched seed-and-extend on the GPU: kernels, chunk driver, C ABI.
+//
+//   b200_mem_align_batch  <- the compute of BWAAligner::alignSequence (src/BWAAligner.cpp:104-128):
+//                            mem_align1 (bwa/bwamem_extra.c:103-115) + mem_reg2aln (bwa/bwamem.c:1119-1189) per region
+//   b200_ksw_extend2_batch<- ksw_extend2 (bwa/ksw.c:416-515)
+//
+// Per chunk of reads four kernels run back to back on one stream, each thread
+// taking reads from a shared work counter (a warp claims 32 reads at a time):
+//   k_seed -> k_chain -> k_extend -> k_finalize, then k_gather compacts the hits
+// of the chunk in read order (cub scan of the per-read counts).  There is no
+// CPU path: without a usable CUDA device every entry point returns B200_ERR_CUDA.
+#include <cub/cub.cuh>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <string>
+#include <algorithm>
+#include "engine.cuh"
+
+using namespace b200;
+
+namespace b200 {
+
+struct DevCounters { unsigned long long v[8]; };   // occ_blocks, sa_reads, ref_bytes, sw_cells, n_ext, n_global, n_ovf, pool_fail
+
+__device__ __forceinline__ void flush_counters(const CtrLocal &c, DevCounters *g)
+{
+    // warp-aggregate, one atomic per warp and counter
+    unsigned long long v[6] = {c.occ_blocks, c.sa_reads, c.ref_bytes, c.sw_cells, c.n_ext, c.n_global};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&g->v[k], x);
+    }
+}
+
+// a warp claims 32 consecutive work items
+__device__ __forceinline__ i64 claim(unsigned long long *counter)
+{
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return (i64)base + (threadIdx.x & 31);
+}
+
+struct KArgs {
+    DevIndex ix; Opt opt; Caps caps; Batch B;
+    const i32 *order; i64 n_work;           // work item i processes read order[i] (NULL: i)
+    u8 *scratch; size_t scratch_stride;
+    unsigned long long *work_ctr; DevCounters *ctrs;
+    const double *log_tab; int n_log;
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
+{
+    u8 *scr = A.scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.scratch_stride;
+    CtrLocal ctr;
+    for (;;) {
+        i64 w = claim(A.work_ctr);
+        if (w - (threadIdx.x & 31) >= A.n_work) break;
+        if (w < A.n_work) {
+            i64 rid = A.order ? A.order[w] : w;
+            if (STAGE == 0) stage_seed(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
+            else if (STAGE == 1) stage_chain(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
+            else if (STAGE == 2) stage_extend(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
+            else stage_finalize(A.ix, A.opt, A.caps, A.B, rid, scr, A.log_tab, A.n_log, ctr);
+        }
+    }
+    flush_counters(ctr, A.ctrs);
+}
+
+// ASCII -> nt4 codes (nst_nt4_table, bwa/bntseq.c:46-63; mem_align1_core keeps codes < 4 as they are, bwa/bwamem.c:1087-1088)
+__global__ void k_encode(const u8 *__restrict__ in, u8 *__restrict__ out, i64 n)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (i64)gridDim.x * blockDim.x) {
+        u8 c = in[i], v;
+        switch (c) {
+        case 'A': case 'a': v = 0; break; case 'C': case 'c': v = 1; break;
+        case 'G': case 'g': v = 2; break; case 'T': case 't': v = 3; break;
+        case '-': v = 5; break;
+        default: v = c < 4 ? c : 4;
+        }
+        out[i] = v;
+    }
+}
+
+__global__ void k_clear_u32(u32 *a, i64 n) { i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = 0; }
+__global__ void k_clear_list(u32 *a, const i32 *list, i64 n) { i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[list[i]] = 0; }
+
+// list the reads of [0,n) whose ovf bits intersect mask
+__global__ void k_list_ovf(const u32 *__restrict__ ovf, i64 n, u32 mask, i32 *__restrict__ list, unsigned long long *cnt)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (ovf[i] & mask) { unsigned long long o = atomicAdd(cnt, 1ull); list[o] = (i32)i; }
+}
+
+__global__ void k_counts(const ReadRec *__restrict__ rec, i64 n, i64 *__restrict__ nh, i64 *__restrict__ nc, i64 *__restrict__ nm)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    nh[i] = rec[i].n_hits; nc[i] = rec[i].n_cigar; nm[i] = rec[i].n_md;
+}
+
+// compact the chunk's hits in read order; one warp per read
+__global__ void k_gather(const ReadRec *__restrict__ rec, i64 n, Pools P, const i64 *__restrict__ oh, const i64 *__restrict__ oc,
+                         const i64 *__restrict__ om, i64 base_h, i64 base_c, i64 base_m,
+                         i64 *__restrict__ hit_off, b200_hit_t *__restrict__ hits, u32 *__restrict__ cigar, char *__restrict__ md)
+{
+    i64 r = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const ReadRec R = rec[r];
+    if (lane == 0) hit_off[r] = base_h + oh[r];
+    i64 c = oc[r], m = om[r];
+    for (int i = 0; i < R.n_hits; ++i) {
+        const b200_hit_t *src = P.hits + R.hit_off + i;
+        b200_hit_t *dst = hits + oh[r] + i;
+        const u32 *s32 = (const u32 *)src; u32 *d32 = (u32 *)dst;
+        for (int k = lane; k < (int)(sizeof(b200_hit_t) / 4); k += 32) d32[k] = s32[k];
+        __syncwarp();
+        int ncg = src->n_cigar, nmd = src->md_len + 1;
+        for (int k = lane; k < ncg; k += 32) cigar[c + k] = P.cigar[src->cigar_off + k];
+        for (int k = lane; k < nmd; k += 32) md[m + k] = P.md[src->md_off + k];
+        __syncwarp();
+        if (lane == 0) { dst->cigar_off = base_c + c; dst->md_off = base_m + m; }
+        c += ncg; m += nmd;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+struct HostResults {
+    std::vector<i64> hit_off; std::vector<b200_hit_t> hits; std::vector<u32> cigar; std::vector<char> md;
+};
+
+struct Engine {
+    int device = -1, sms = 148;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8];
+    // chunk buffers
+    DevBuf seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, small;
+    DevBuf p_intv, p_chain, p_seed, p_reg, p_hit, p_cigar, p_md;
+    DevBuf nh, nc, nm, oh, oc, om, cubtmp, o_hit_off, o_hits, o_cigar, o_md;
+    double pool_scale = 1.0;
+    b200_stage_stats_t stats;
+
+    void init()
+    {
+        int d = 0;
+        CU_CHECK(cudaGetDevice(&d));
+        if (st && d == device) return;
+        device = d;
+        CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
+        CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; ++i) CU_CHECK(cudaEventCreate(&ev[i]));
+        memset(&stats, 0, sizeof(stats));
+    }
+};
+
+static Engine &engine() { static thread_local Engine e; e.init(); return e; }
+
+template <int STAGE>
+static int stage_grid(int sms)
+{
+    int per = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage<STAGE>, 128, 0));
+    if (per < 1) per = 1;
+    return sms * per;
+}
+
+struct ChunkCtx {
+    Engine *E; const b200_index *idx; Opt opt; Caps caps, big; int maxlen;
+    i64 n; // reads in this chunk
+    Batch B; std::vector<double> logtab;
+};
+
+static size_t max4(size_t a, size_t b, size_t c, size_t d) { return std::max(std::max(a, b), std::max(c, d)); }
+
+template <int STAGE>
+static void launch_stage(Engine &E, KArgs &A, int grid)
+{
+    CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
+    k_stage<STAGE><<<grid, 128, 0, E.st>>>(A);
+    CU_CHECK(cudaGetLastError());
+}
+
+// Runs the four stages over `n_work` reads (all reads of the chunk, or the spill list).
+static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
+{
+    int g[4];
+    if (!spill) { g[0] = stage_grid<0>(E.sms); g[1] = stage_grid<1>(E.sms); g[2] = stage_grid<2>(E.sms); g[3] = stage_grid<3>(E.sms); }
+    else g[0] = g[1] = g[2] = g[3] = std::max<int>(1, (int)std::min<i64>((A.n_work + 127) / 128, 8));
+    size_t stride = max4(seed_scratch_bytes(A.caps), chain_scratch_bytes(A.caps), extend_scratch_bytes(A.caps), finalize_scratch_bytes(A.caps));
+    stride = (stride + 63) & ~(size_t)63;
+    int gmax = std::max(std::max(g[0], g[1]), std::max(g[2], g[3]));
+    DevBuf &S = spill ? E.spill_scratch : E.scratch;
+    S.reserve(stride * (size_t)gmax * 128);
+    A.scratch = S.as<u8>(); A.scratch_stride = stride;
+    cudaEvent_t *ev = E.ev;
+    CU_CHECK(cudaEventRecord(ev[0], E.st));
+    launch_stage<0>(E, A, g[0]); CU_CHECK(cudaEventRecord(ev[1], E.st));
+    launch_stage<1>(E, A, g[1]); CU_CHECK(cudaEventRecord(ev[2], E.st));
+    launch_stage<2>(E, A, g[2]); CU_CHECK(cudaEventRecord(ev[3], E.st));
+    launch_stage<3>(E, A, g[3]); CU_CHECK(cudaEventRecord(ev[4], E.st));
+    E.stats.n_launches += 4;
+    if (ms4) {
+        CU_CHECK(cudaEventSynchronize(ev[4]));
+        for (int i = 0; i < 4; ++i) { float t = 0; cudaEventElapsedTime(&t, ev[i], ev[i + 1]); ms4[i] += t; }
+    }
+}
+
+// Device-side result of one chunk (compact, read order).
+struct ChunkOut { i64 n_hits, n_cigar, n_md; };
+
+// Processes reads [r0, r0+n) whose encoded bases / offsets / ids are already on the device
+// (d_seq nt4, d_off relative to the batch start, d_ids).  Leaves compact results in E.o_* and returns their sizes.
+static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, int maxlen, const u8 *d_seq, const i64 *d_off,
+                              const i64 *d_ids, i64 n, i64 base_h, i64 base_c, i64 base_m, const double *d_log, int n_log)
+{
+    Caps caps = default_caps(maxlen), big = big_caps(maxlen, opt);
+    E.ovf.reserve(n * 4 + 64); E.rec.reserve(n * sizeof(ReadRec) + 64); E.list.reserve(n * 4 + 64); E.small.reserve(4096);
+    unsigned long long *d_small = E.small.as<unsigned long long>();   // [0]=work ctr, [1]=list count, [8..15]=pool used, [16..]=DevCounters
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        double sc = E.pool_scale;
+        i64 cap[N_POOLS] = {(i64)(n * 24 * sc) + 65536, (i64)(n * 6 * sc) + 65536, (i64)(n * 24 * sc) + 65536, (i64)(n * 6 * sc) + 65536,
+                            (i64)(n * 3 * sc) + 65536, (i64)(n * 12 * sc) + 65536, (i64)(n * 48 * sc) + 65536};
+        E.p_intv.reserve(cap[POOL_INTV] * sizeof(Intv)); E.p_chain.reserve(cap[POOL_CHAIN] * sizeof(Chain)); E.p_seed.reserve(cap[POOL_SEED] * sizeof(Seed));
+        E.p_reg.reserve(cap[POOL_REG] * sizeof(Reg)); E.p_hit.reserve(cap[POOL_HIT] * sizeof(b200_hit_t)); E.p_cigar.reserve(cap[POOL_CIGAR] * 4);
+        E.p_md.reserve(cap[POOL_MD]);
+        CU_CHECK(cudaMemsetAsync(E.small.p, 0, 4096, E.st));
+        k_clear_u32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n);
+        KArgs A; memset(&A, 0, sizeof(A));
+        A.ix = idx->dev; A.opt = opt; A.caps = caps;
+        A.B.n_reads = n; A.B.seq = d_seq; A.B.seq_off = d_off; A.B.hash_id = d_ids; A.B.ovf = E.ovf.as<u32>(); A.B.rec = E.rec.as<ReadRec>();
+        Pools &P = A.B.pool;
+        P.intv = E.p_intv.as<Intv>(); P.chains = E.p_chain.as<Chain>(); P.seeds = E.p_seed.as<Seed>(); P.regs = E.p_reg.as<Reg>();
+        P.hits = E.p_hit.as<b200_hit_t>(); P.cigar = E.p_cigar.as<u32>(); P.md = E.p_md.as<char>();
+        for (int k = 0; k < N_POOLS; ++k) P.cap[k] = cap[k];
+        P.used = d_small + 8;
+        A.order = nullptr; A.n_work = n; A.work_ctr = d_small; A.ctrs = (DevCounters *)(d_small + 16);
+        A.log_tab = d_log; A.n_log = n_log;
+        float ms4[4] = {0, 0, 0, 0};
+        run_stages(E, A, false, ms4);
+        // spill pass for reads that overflowed their scratch slot
+        const u32 SCR = OVF_INTV | OVF_SEED | OVF_CHAIN | OVF_REG | OVF_OUT | OVF_SCRATCH;
+        k_list_ovf<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n, SCR, E.list.as<i32>(), d_small + 1);
+        unsigned long long h_small[24];
+        CU_CHECK(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaStreamSynchronize(E.st));
+        i64 n_sp = (i64)h_small[1];
+        if (n_sp) {
+            E.stats.n_overflow += (u64)n_sp;
+            k_clear_list<<<(unsigned)((n_sp + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), E.list.as<i32>(), n_sp);
+            KArgs S = A; S.caps = big; S.order = E.list.as<i32>(); S.n_work = n_sp;
+            run_stages(E, S, true, ms4);
+            E.stats.n_launches += 1;
+        }
+        // any read still flagged?  pool exhaustion => retry the chunk with larger pools; anything else is a hard limit
+        CU_CHECK(cudaMemsetAsync(d_small + 1, 0, 8, E.st));
+        k_list_ovf<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n, 0xffffffffu, E.list.as<i32>(), d_small + 1);
+        CU_CHECK(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaStreamSynchronize(E.st));
+        E.stats.n_launches += 4;
+        if (h_small[1]) {
+            bool pool_full = false;
+            for (int k = 0; k < N_POOLS; ++k) if ((i64)h_small[8 + k] > cap[k]) pool_full = true;
+            if (pool_full) { E.pool_scale *= 2.0; continue; }
+            throw std::runtime_error("a read exceeds the supported working-set limits (seeds/chains/regions)");
+        }
+        E.stats.ms_seed += ms4[0]; E.stats.ms_chain += ms4[1]; E.stats.ms_extend += ms4[2]; E.stats.ms_finalize += ms4[3];
+        const unsigned long long *c = h_small + 16;
+        E.stats.occ_blocks += c[0]; E.stats.sa_reads += c[1]; E.stats.ref_bytes += c[2]; E.stats.sw_cells += c[3]; E.stats.n_ext += c[4]; E.stats.n_global += c[5];
+        // compact in read order
+        E.nh.reserve(n * 8 + 8); E.nc.reserve(n * 8 + 8); E.nm.reserve(n * 8 + 8); E.oh.reserve(n * 8 + 16); E.oc.reserve(n * 8 + 16); E.om.reserve(n * 8 + 16);
+        k_counts<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.rec.as<ReadRec>(), n, E.nh.as<i64>(), E.nc.as<i64>(), E.nm.as<i64>());
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, E.nh.as<i64>(), E.oh.as<i64>(), (int)n, E.st);
+        E.cubtmp.reserve(tb);
+        CU_CHECK(cub::DeviceScan::ExclusiveSum(E.cubtmp.p, tb, E.nh.as<i64>(), E.oh.as<i64>(), (int)n, E.st));
+        CU_CHECK(cub::DeviceScan::ExclusiveSum(E.cubtmp.p, tb, E.nc.as<i64>(), E.oc.as<i64>(), (int)n, E.st));
+        CU_CHECK(cub::DeviceScan::ExclusiveSum(E.cubtmp.p, tb, E.nm.as<i64>(), E.om.as<i64>(), (int)n, E.st));
+        ChunkOut out;
+        out.n_hits = (i64)h_small[8 + POOL_HIT]; out.n_cigar = (i64)h_small[8 + POOL_CIGAR]; out.n_md = (i64)h_small[8 + POOL_MD];
+        // pools may hold abandoned allocations of spilled reads: exact totals come from the scans
+        i64 last[3], lastn[3];
+        CU_CHECK(cudaMemcpyAsync(&last[0], E.oh.as<i64>() + (n - 1), 8, cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaMemcpyAsync(&last[1], E.oc.as<i64>() + (n - 1), 8, cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaMemcpyAsync(&last[2], E.om.as<i64>() + (n - 1), 8, cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaMemcpyAsync(&lastn[0], E.nh.as<i64>() + (n - 1), 8, cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaMemcpyAsync(&lastn[1], E.nc.as<i64>() + (n - 1), 8, cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaMemcpyAsync(&lastn[2], E.nm.as<i64>() + (n - 1), 8, cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaStreamSynchronize(E.st));
+        out.n_hits = last[0] + lastn[0]; out.n_cigar = last[1] + lastn[1]; out.n_md = last[2] + lastn[2];
+        E.o_hit_off.reserve(n * 8 + 8); E.o_hits.reserve(out.n_hits * sizeof(b200_hit_t) + 64); E.o_cigar.reserve(out.n_cigar * 4 + 64); E.o_md.reserve(out.n_md + 64);
+        k_gather<<<(unsigned)((n * 32 + 255) / 256), 256, 0, E.st>>>(E.rec.as<ReadRec>(), n, P, E.oh.as<i64>(), E.oc.as<i64>(), E.om.as<i64>(), base_h, base_c, base_m,
+                                                                    E.o_hit_off.as<i64>(), E.o_hits.as<b200_hit_t>(), E.o_cigar.as<u32>(), E.o_md.as<char>());
+        CU_CHECK(cudaGetLastError());
+        E.stats.n_launches += 5;
+        return out;
+    }
+    throw std::runtime_error("pool growth did not converge");
+}
+
+static i64 chunk_reads()
+{
+    const char *e = getenv("B200_CHUNK");
+    i64 v = e ? atoll(e) : (1 << 20);
+    return v < 1024 ? 1024 : v;
+}
+
+} // namespace b200
+
+struct b200_results { HostResults r; };
+
+struct b200_batch {
+    const b200_index *idx; Opt opt; i64 n; int maxlen;
+    std::vector<i64> h_off;
+    DevBuf d_seq, d_off, d_ids, d_log; int n_log;
+    // device-resident compact results of the last run, per chunk
+    struct Chunk { i64 r0, n; ChunkOut out; DevBuf hit_off, hits, cigar, md; };
+    std::vector<Chunk *> chunks;
+    ~b200_batch() { for (auto c : chunks) delete c; }
+};
+
+extern "C" {
+
+static int check_reads(const b200_mem_opt_t *opt, i64 n, const int64_t *off, int *maxlen_out)
+{
+    int maxlen = 1;
+    for (i64 i = 0; i < n; ++i) {
+        i64 l = off[i + 1] - off[i];
+        if (l < 0 || l > (1 << 20)) return fail(B200_ERR_ARG, "bad read length");
+        if (l > maxlen) maxlen = (int)l;
+    }
+    // mem_flt_chained_seeds (bwa/bwamem.c:624-628) starts to act once 5.5*ln(l) <= 0.05*l (l >~ 730 bp with min_chain_weight 0);
+    // that seed-SW filter is not part of this engine yet, so such reads are refused instead of silently diverging.
+    double lim = opt->min_chain_weight ? 1.1 * opt->min_chain_weight : 5.5 * log((double)maxlen);
+    if (!(lim > 0.05 * maxlen)) return fail(B200_ERR_LIMIT, "reads long enough to trigger mem_flt_chained_seeds (> ~730 bp) are not supported yet");
+    *maxlen_out = maxlen;
+    return B200_OK;
+}
+
+int b200_batch_create(const b200_index_t *idx, const b200_mem_opt_t *opt, int64_t n, const char *seqs, const int64_t *off,
+                      const int64_t *ids, b200_batch_t **out)
+{
+    if (!idx || !opt || !out || n < 0 || (n && (!seqs || !off))) return fail(B200_ERR_ARG, "bad argument");
+    *out = nullptr;
+    int maxlen = 1, rc;
+    if ((rc = check_reads(opt, n, off, &maxlen)) != B200_OK) return rc;
+    b200_batch *b = new b200_batch;
+    try {
+        Engine &E = engine();
+        b->idx = idx; b->opt = opt_from_abi(*opt); b->n = n; b->maxlen = maxlen;
+        b->h_off.assign(off, off + n + 1);
+        i64 base = off[0], total = off[n] - base;
+        std::vector<i64> rel(n + 1);
+        for (i64 i = 0; i <= n; ++i) rel[i] = off[i] - base;
+        std::vector<i64> myids;
+        if (!ids) { myids.resize(n); for (i64 i = 0; i < n; ++i) myids[i] = lrand48(); ids = myids.data(); }
+        b->d_seq.reserve(total + 64); b->d_off.reserve((n + 1) * 8); b->d_ids.reserve(n * 8 + 8);
+        E.seq_ascii.reserve(total + 64);
+        CU_CHECK(cudaMemcpyAsync(E.seq_ascii.p, seqs + base, total, cudaMemcpyHostToDevice, E.st));
+        CU_CHECK(cudaMemcpyAsync(b->d_off.p, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, E.st));
+        CU_CHECK(cudaMemcpyAsync(b->d_ids.p, ids, n * 8, cudaMemcpyHostToDevice, E.st));
+        if (total) k_encode<<<E.sms * 8, 256, 0, E.st>>>(E.seq_ascii.as<u8>(), b->d_seq.as<u8>(), total);
+        std::vector<double> lt = make_log_table(maxlen, b->opt);
+        b->n_log = (int)lt.size();
+        b->d_log.reserve(lt.size() * 8);
+        CU_CHECK(cudaMemcpyAsync(b->d_log.p, lt.data(), lt.size() * 8, cudaMemcpyHostToDevice, E.st));
+        CU_CHECK(cudaStreamSynchronize(E.st));
+    } catch (const std::exception &e) { delete b; return fail(B200_ERR_CUDA, e.what()); }
+    *out = b;
+    return B200_OK;
+}
+
+int b200_batch_run(b200_batch_t *b, int *n_launches)
+{
+    if (!b) return fail(B200_ERR_ARG, "bad argument");
+    try {
+        Engine &E = engine();
+        memset(&E.stats, 0, sizeof(E.stats));
+        CU_CHECK(cudaEventRecord(E.ev[6], E.st));
+        for (auto c : b->chunks) delete c;
+        b->chunks.clear();
+        i64 CH = chunk_reads(), bh = 0, bc = 0, bm = 0;
+        for (i64 r0 = 0; r0 < b->n; r0 += CH) {
+            i64 n = std::min(CH, b->n - r0);
+            ChunkOut o = process_chunk(E, b->idx, b->opt, b->maxlen, b->d_seq.as<u8>(), b->d_off.as<i64>() + r0, b->d_ids.as<i64>() + r0, n, bh, bc, bm,
+                                       b->d_log.as<double>(), b->n_log);
+            b200_batch::Chunk *c = new b200_batch::Chunk;
+            c->r0 = r0; c->n = n; c->out = o;
+            // keep the compact result on the device (swap buffers with the engine's output buffers)
+            std::swap(c->hit_off.p, E.o_hit_off.p); std::swap(c->hit_off.cap, E.o_hit_off.cap);
+            std::swap(c->hits.p, E.o_hits.p); std::swap(c->hits.cap, E.o_hits.cap);
+            std::swap(c->cigar.p, E.o_cigar.p); std::swap(c->cigar.cap, E.o_cigar.cap);
+            std::swap(c->md.p, E.o_md.p); std::swap(c->md.cap, E.o_md.cap);
+            b->chunks.push_back(c);
+            bh += o.n_hits; bc += o.n_cigar; bm += o.n_md;
+        }
+        CU_CHECK(cudaEventRecord(E.ev[7], E.st));
+        CU_CHECK(cudaEventSynchronize(E.ev[7]));
+        cudaEventElapsedTime(&E.stats.ms_total, E.ev[6], E.ev[7]);
+        if (n_launches) *n_launches = E.stats.n_launches;
+    } catch (const std::exception &e) { return fail(B200_ERR_CUDA, e.what()); }
+    return B200_OK;
+}
+
+int b200_batch_fetch(b200_batch_t *b, b200_results_t **out)
+{
+    if (!b || !out) return fail(B200_ERR_ARG, "bad argument");
+    *out = nullptr;
+    b200_results *R = new b200_results;
+    try {
+        Engine &E = engine();
+        i64 th = 0, tc = 0, tm = 0;
+        for (auto c : b->chunks) { th += c->out.n_hits; tc += c->out.n_cigar; tm += c->out.n_md; }
+        HostResults &H = R->r;
+        H.hit_off.resize(b->n + 1); H.hits.resize(th); H.cigar.resize(tc); H.md.resize(tm);
+        i64 ph = 0, pc = 0, pm = 0;
+        for (auto c : b->chunks) {
+            CU_CHECK(cudaMemcpyAsync(H.hit_off.data() + c->r0, c->hit_off.p, c->n * 8, cudaMemcpyDeviceToHost, E.st));
+            if (c->out.n_hits) CU_CHECK(cudaMemcpyAsync(H.hits.data() + ph, c->hits.p, c->out.n_hits * sizeof(b200_hit_t), cudaMemcpyDeviceToHost, E.st));
+            if (c->out.n_cigar) CU_CHECK(cudaMemcpyAsync(H.cigar.data() + pc, c->cigar.p, c->out.n_cigar * 4, cudaMemcpyDeviceToHost, E.st));
+            if (c->out.n_md) CU_CHECK(cudaMemcpyAsync(H.md.data() + pm, c->md.p, c->out.n_md, cudaMemcpyDeviceToHost, E.st));
+            ph += c->out.n_hits; pc += c->out.n_cigar; pm += c->out.n_md;
+        }
+        CU_CHECK(cudaStreamSynchronize(E.st));
+        H.hit_off[b->n] = th;
+    } catch (const std::exception &e) { delete R; return fail(B200_ERR_CUDA, e.what()); }
+    *out = R;
+    return B200_OK;
+}
+
+void b200_batch_destroy(b200_batch_t *b) { delete b; }
+
+int b200_mem_align_batch(const b200_index_t *idx, const b200_mem_opt_t *opt, int64_t n, const char *seqs, const int64_t *off,
+                         const int64_t *ids, b200_results_t **out)
+{
+    if (!out) return fail(B200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    b200_batch_t *b = nullptr;
+    int rc = b200_batch_create(idx, opt, n, seqs, off, ids, &b);
+    if (rc != B200_OK) return rc;
+    rc = b200_batch_run(b, nullptr);
+    if (rc == B200_OK) rc = b200_batch_fetch(b, out);
+    b200_batch_destroy(b);
+    return rc;
+}
+
+int b200_results_view(const b200_results_t *res, b200_results_view_t *v)
+{
+    if (!res || !v) return fail(B200_ERR_ARG, "bad argument");
+    const HostResults &H = res->r;
+    v->n_reads = (int64_t)H.hit_off.size() - 1; v->hit_off = H.hit_off.data(); v->hits = H.hits.data();
+    v->cigar = H.cigar.data(); v->md = H.md.data();
+    v->n_hits = (int64_t)H.hits.size(); v->n_cigar = (int64_t)H.cigar.size(); v->n_md = (int64_t)H.md.size();
+    return B200_OK;
+}
+
+void b200_results_free(b200_results_t *res) { delete res; }
+
+int b200_last_stats(b200_stage_stats_t *out)
+{
+    if (!out) return fail(B200_ERR_ARG, "bad argument");
+    try { *out = engine().stats; } catch (const std::exception &e) { return fail(B200_ERR_CUDA, e.what()); }
+    return B200_OK;
+}
+
+// ---- stage dump for tests: intervals of every read (mem_collect_intv) -------------------
+int b200_debug_collect_intv(const b200_index_t *idx, const b200_mem_opt_t *opt, int64_t n, const char *seqs, const int64_t *off,
+                            int64_t **intv_off, b200_intv_t **intv)
+{
+    if (!idx || !opt || !intv_off || !intv) return fail(B200_ERR_ARG, "bad argument");
+    b200_batch_t *b = nullptr;
+    int rc = b200_batch_create(idx, opt, n, seqs, off, nullptr, &b);
+    if (rc != B200_OK) return rc;
+    try {
+        Engine &E = engine();
+        Caps big = big_caps(b->maxlen, b->opt);
+        E.ovf.reserve(n * 4 + 64); E.rec.reserve(n * sizeof(ReadRec) + 64); E.small.reserve(4096);
+        i64 cap = n * (i64)big.intv + 1024;
+        E.p_intv.reserve(cap * sizeof(Intv));
+        CU_CHECK(cudaMemsetAsync(E.small.p, 0, 4096, E.st));
+        k_clear_u32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n);
+        KArgs A; memset(&A, 0, sizeof(A));
+        unsigned long long *d_small = E.small.as<unsigned long long>();
+        A.ix = idx->dev; A.opt = b->opt; A.caps = big;
+        A.B.n_reads = n; A.B.seq = b->d_seq.as<u8>(); A.B.seq_off = b->d_off.as<i64>(); A.B.hash_id = b->d_ids.as<i64>();
+        A.B.ovf = E.ovf.as<u32>(); A.B.rec = E.rec.as<ReadRec>();
+        A.B.pool.intv = E.p_intv.as<Intv>(); A.B.pool.cap[POOL_INTV] = cap; A.B.pool.used = d_small + 8;
+        A.n_work = n; A.work_ctr = d_small; A.ctrs = (DevCounters *)(d_small + 16);
+        size_t stride = (seed_scratch_bytes(big) + 63) & ~(size_t)63;
+        int grid = 8;
+        E.spill_scratch.reserve(stride * grid * 128);
+        A.scratch = E.spill_scratch.as<u8>(); A.scratch_stride = stride;
+        launch_stage<0>(E, A, grid);
+        std::vector<ReadRec> rec(n);
+        CU_CHECK(cudaMemcpyAsync(rec.data(), E.rec.p, n * sizeof(ReadRec), cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaStreamSynchronize(E.st));
+        i64 tot = 0;
+        for (i64 i = 0; i < n; ++i) tot += rec[i].n_intv;
+        std::vector<Intv> pool(cap);
+        CU_CHECK(cudaMemcpy(pool.data(), E.p_intv.p, cap * sizeof(Intv), cudaMemcpyDeviceToHost));
+        int64_t *o = (int64_t *)malloc((n + 1) * 8);
+        b200_intv_t *iv = (b200_intv_t *)malloc((tot + 1) * sizeof(b200_intv_t));
+        i64 k = 0;
+        for (i64 i = 0; i < n; ++i) {
+            o[i] = k;
+            for (int j = 0; j < rec[i].n_intv; ++j, ++k) {
+                const Intv &p = pool[rec[i].intv_off + j];
+                iv[k].x0 = p.x0; iv[k].x1 = p.x1; iv[k].x2 = p.x2; iv[k].info = p.info;
+            }
+        }
+        o[n] = k;
+        *intv_off = o; *intv = iv;
+    } catch (const std::exception &e) { b200_batch_destroy(b); return fail(B200_ERR_CUDA, e.what()); }
+    b200_batch_destroy(b);
+    return B200_OK;
+}
+
+} // extern "C"

@@ -32,13 +32,13 @@ inline std::vector<double> make_log_table(int maxlen, const Opt &opt)
     return t;
 }
 
-// Fast-path capacities (typical 150-bp reads) and the spill capacities for reads that overflow them.
+// Scratch-slot capacities: the main pass (typical short reads) and the spill pass for reads that overflow it.
 inline Caps default_caps(int maxlen, bool tiny = false)
 {
     Caps c;
     c.maxlen = maxlen;
-    if (tiny) { c.intv = 6; c.wchains = 3; c.wseeds = 6; c.chains = 2; c.seeds = 4; c.regs = 2; c.hits = 1; c.cigar = 3; c.md = 6; c.z = 1024; }
-    else { c.intv = 48; c.wchains = 64; c.wseeds = 128; c.chains = 16; c.seeds = 48; c.regs = 16; c.hits = 4; c.cigar = 10; c.md = 48; c.z = (i64)maxlen * 64; }
+    if (tiny) { c.intv = 6; c.wchains = 3; c.wseeds = 6; c.seeds = 4; c.regs = 2; c.cigar = 3; c.md = 6; c.z = 1024; }
+    else { c.intv = 64; c.wchains = 64; c.wseeds = 160; c.seeds = 96; c.regs = 24; c.cigar = 24; c.md = 96; c.z = (i64)maxlen * 64; }
     return c;
 }
 
@@ -50,10 +50,8 @@ inline Caps big_caps(int maxlen, const Opt &opt)
     i64 ws = (i64)c.intv * std::min(opt.max_occ, 64) + 1024;
     c.wseeds = (int)std::min<i64>(ws, 1 << 20);
     c.wchains = c.wseeds;
-    c.chains = std::min(c.wchains, 4096);
-    c.seeds = std::min(c.wseeds, 1 << 16);
-    c.regs = std::min(c.seeds, 4096);
-    c.hits = c.regs;
+    c.seeds = c.wseeds;
+    c.regs = std::min(c.seeds, 8192);
     c.cigar = 2 * maxlen + 8;
     c.md = 4 * maxlen + 64;
     int w4 = opt.w << 2;

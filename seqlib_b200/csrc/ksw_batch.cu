@@ -1,0 +1,85 @@
+// ksw_batch.cu -- batched ksw_extend2 (bwa/ksw.c:416-515): config-3 microbenchmark and unit parity entry point.
+#include <vector>
+#include <cstring>
+#include "engine.cuh"
+
+using namespace b200;
+
+namespace b200 {
+
+struct ExtArgs {
+    const b200_ext_job_t *jobs; i64 n; const u8 *qp, *tp; i8 mat[25]; int o_del, e_del, o_ins, e_ins;
+    b200_ext_out_t *out; EH *eh; int eh_stride; unsigned long long *cells; unsigned long long *work;
+};
+
+struct CellCtr { unsigned long long sw_cells, n_ext; };
+
+// v1: one thread per job, persistent threads, the scalar recurrence of ksw.cuh
+__global__ void __launch_bounds__(128) k_ext_scalar(const __grid_constant__ ExtArgs A)
+{
+    EH *eh = A.eh + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.eh_stride;
+    CellCtr c; c.sw_cells = 0; c.n_ext = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(A.work, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((i64)base >= A.n) break;
+        i64 i = (i64)base + (threadIdx.x & 31);
+        if (i < A.n) {
+            const b200_ext_job_t j = A.jobs[i];
+            BytesSeq q; q.p = A.qp + j.q_off; q.step = 1;
+            BytesSeq t; t.p = A.tp + j.t_off; t.step = 1;
+            ExtResult r = extend2(j.qlen, q, j.tlen, t, A.mat, A.o_del, A.e_del, A.o_ins, A.e_ins, j.w, j.end_bonus, j.zdrop, j.h0, eh, c);
+            b200_ext_out_t o; o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off;
+            A.out[i] = o;
+        }
+    }
+    unsigned long long x = c.sw_cells;
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(A.cells, x);
+}
+
+} // namespace b200
+
+extern "C" int b200_ksw_extend2_batch(int64_t n, const b200_ext_job_t *jobs, const uint8_t *qpool, int64_t qpool_len,
+                                      const uint8_t *tpool, int64_t tpool_len, const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
+                                      b200_ext_out_t *out, uint64_t *cells, float *kernel_ms)
+{
+    if (n < 0 || (n && (!jobs || !qpool || !tpool || !out))) return fail(B200_ERR_ARG, "bad argument");
+    try {
+        int dev = 0, sms = 148;
+        CU_CHECK(cudaGetDevice(&dev));
+        CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int maxq = 1;
+        for (i64 i = 0; i < n; ++i) { if (jobs[i].qlen > maxq) maxq = jobs[i].qlen; if (jobs[i].h0 <= 0) return fail(B200_ERR_ARG, "h0 must be positive"); }
+        DevBuf dj, dq, dt, dout, deh, dsmall;
+        dj.reserve(n * sizeof(b200_ext_job_t) + 64); dq.reserve(qpool_len + 64); dt.reserve(tpool_len + 64); dout.reserve(n * sizeof(b200_ext_out_t) + 64); dsmall.reserve(64);
+        CU_CHECK(cudaMemcpy(dj.p, jobs, n * sizeof(b200_ext_job_t), cudaMemcpyHostToDevice));
+        CU_CHECK(cudaMemcpy(dq.p, qpool, qpool_len, cudaMemcpyHostToDevice));
+        CU_CHECK(cudaMemcpy(dt.p, tpool, tpool_len, cudaMemcpyHostToDevice));
+        CU_CHECK(cudaMemset(dsmall.p, 0, 64));
+        int per = 1;
+        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ext_scalar, 128, 0));
+        int grid = sms * (per < 1 ? 1 : per);
+        int stride = maxq + 2;
+        deh.reserve((size_t)grid * 128 * stride * sizeof(EH));
+        ExtArgs A; memset(&A, 0, sizeof(A));
+        A.jobs = dj.as<b200_ext_job_t>(); A.n = n; A.qp = dq.as<u8>(); A.tp = dt.as<u8>(); memcpy(A.mat, mat, 25);
+        A.o_del = o_del; A.e_del = e_del; A.o_ins = o_ins; A.e_ins = e_ins; A.out = dout.as<b200_ext_out_t>();
+        A.eh = deh.as<EH>(); A.eh_stride = stride; A.cells = dsmall.as<unsigned long long>(); A.work = dsmall.as<unsigned long long>() + 1;
+        cudaEvent_t e0, e1; CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1));
+        CU_CHECK(cudaEventRecord(e0));
+        k_ext_scalar<<<grid, 128>>>(A);
+        CU_CHECK(cudaEventRecord(e1));
+        CU_CHECK(cudaEventSynchronize(e1));
+        CU_CHECK(cudaGetLastError());
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        CU_CHECK(cudaMemcpy(out, dout.p, n * sizeof(b200_ext_out_t), cudaMemcpyDeviceToHost));
+        unsigned long long hc = 0;
+        CU_CHECK(cudaMemcpy(&hc, dsmall.p, 8, cudaMemcpyDeviceToHost));
+        if (cells) *cells = hc;
+        if (kernel_ms) *kernel_ms = ms;
+    } catch (const std::exception &e) { return fail(B200_ERR_CUDA, e.what()); }
+    return B200_OK;
+}

@@ -7,8 +7,12 @@
 //   stage_extend   chains -> raw regions        (mem_chain2aln per chain)
 //   stage_finalize regions -> hits              (mem_sort_dedup_patch, mem_mark_primary_se, mem_reg2aln)
 //
-// Per-read slots have fixed capacities (Caps).  A read that does not fit sets
-// its overflow bits and is re-run by the host driver with the large Caps.
+// A stage works inside its thread's scratch slot (capacities = Caps), then
+// bump-allocates exactly what it produced from the chunk-wide pools and copies
+// it there; ReadRec keeps (offset, count) per read.  A read that does not fit
+// the scratch slot sets OVF bits and is re-run by the host driver in a spill
+// pass with few threads and large slots; a full pool fails the chunk, which is
+// retried with larger pools.
 #pragma once
 #include "common.cuh"
 #include "seed.cuh"
@@ -19,33 +23,41 @@
 
 namespace b200 {
 
-struct Caps {
-    int intv;        // intervals per read
-    int wchains;     // chains while chaining (scratch)
-    int wseeds;      // seeds while chaining (scratch)
-    int chains;      // kept chains per read (output of stage_chain)
-    int seeds;       // seeds of kept chains per read
-    int regs;        // regions per read
-    int hits;        // hits per read
-    int cigar;       // cigar words per hit
-    int md;          // md bytes per hit (incl. NUL)
-    int maxlen;      // longest read in the batch
-    i64 z;           // direction bytes per scratch slot
+struct Caps {           // per-slot scratch capacities
+    int intv;           // intervals per read
+    int wchains;        // chains while chaining
+    int wseeds;         // seeds while chaining
+    int seeds;          // seeds of the kept chains (bounds the sort scratch of chain2aln)
+    int regs;           // regions per read (= hits per read)
+    int cigar;          // cigar words per hit
+    int md;             // md bytes per hit (incl. NUL)
+    int maxlen;         // longest read in the batch
+    i64 z;              // direction bytes
 };
 
-// Views of the per-batch HBM buffers.  Read i of the batch owns slot i of every array.
+enum { POOL_INTV = 0, POOL_CHAIN, POOL_SEED, POOL_REG, POOL_HIT, POOL_CIGAR, POOL_MD, N_POOLS };
+enum { OVF_POOL = 64 };
+
+struct Pools {
+    Intv *intv; Chain *chains; Seed *seeds; Reg *regs; b200_hit_t *hits; u32 *cigar; char *md;
+    i64 cap[N_POOLS];
+    unsigned long long *used;   // N_POOLS bump counters
+};
+
+struct ReadRec {
+    i64 intv_off, chain_off, seed_off, reg_off, hit_off;
+    i32 n_intv, n_chains, n_seeds, n_regs, n_hits, n_cigar, n_md;
+    float frac_rep;
+};
+
 struct Batch {
     i64 n_reads;
     const u8 *seq;           // nt4 codes, concatenated
     const i64 *seq_off;      // n_reads + 1
     const i64 *hash_id;      // n_reads
-    const i32 *order;        // optional indirection: slot i processes read order[i] (NULL = identity)
-    u32 *ovf;                // per read overflow bits (indexed by read id)
-    // stage outputs
-    Intv *intv; i32 *n_intv;
-    Chain *chains; Seed *seeds; i32 *n_chains; float *frac_rep;
-    Reg *regs; i32 *n_regs;
-    b200_hit_t *hits; u32 *cigar; char *md; i32 *n_hits;
+    u32 *ovf;                // per read overflow bits
+    ReadRec *rec;            // per read
+    Pools pool;
 };
 
 struct CtrLocal {
@@ -53,122 +65,153 @@ struct CtrLocal {
     HD CtrLocal() : occ_blocks(0), sa_reads(0), ref_bytes(0), sw_cells(0), n_ext(0), n_global(0) {}
 };
 
-// ------------------------------------------------------------------ seed
-// scratch per slot: 2 * (maxlen + 1) Intv
-HD size_t seed_scratch_bytes(const Caps &c) { return sizeof(Intv) * 2 * (size_t)(c.maxlen + 1); }
+HD i64 pool_alloc(const Pools &P, int which, i64 n)
+{
+    if (n == 0) return 0;
+#if defined(__CUDA_ARCH__)
+    i64 off = (i64)atomicAdd(P.used + which, (unsigned long long)n);
+#else
+    i64 off = (i64)P.used[which]; P.used[which] += (unsigned long long)n;
+#endif
+    return off + n <= P.cap[which] ? off : -1;
+}
 
-HD void stage_seed(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 slot, i64 rid, u8 *scratch, CtrLocal &ctr)
+HD u8 *align8(u8 *p) { return (u8 *)(((uintptr_t)p + 7) & ~(uintptr_t)7); }
+
+// ------------------------------------------------------------------ seed
+HD size_t seed_scratch_bytes(const Caps &c) { return sizeof(Intv) * (2 * (size_t)(c.maxlen + 1) + (size_t)c.intv); }
+
+HD void stage_seed(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
 {
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
     const u8 *seq = B.seq + B.seq_off[rid];
-    IntvSink out; out.a = B.intv + slot * caps.intv; out.n = 0; out.cap = caps.intv; out.overflow = false;
+    ReadRec &R = B.rec[rid];
+    R.n_intv = 0; R.intv_off = 0;
+    if (B.ovf[rid]) return;
     Intv *prev = (Intv *)scratch, *curr = prev + (caps.maxlen + 1);
+    IntvSink out; out.a = curr + (caps.maxlen + 1); out.n = 0; out.cap = caps.intv; out.overflow = false;
     if (len >= opt.min_seed_len) collect_intv(ix, opt, len, seq, out, prev, curr, ctr);
-    B.n_intv[slot] = out.overflow ? 0 : out.n;
-    if (out.overflow) B.ovf[rid] |= OVF_INTV;
+    if (out.overflow) { B.ovf[rid] |= OVF_INTV; return; }
+    i64 off = pool_alloc(B.pool, POOL_INTV, out.n);
+    if (off < 0) { B.ovf[rid] |= OVF_POOL; return; }
+    for (int i = 0; i < out.n; ++i) B.pool.intv[off + i] = out.a[i];
+    R.n_intv = out.n; R.intv_off = off;
 }
 
 // ------------------------------------------------------------------ chain
+HD size_t chain_nodes(const Caps &c) { return (size_t)c.wchains / 3 + 8; }
 HD size_t chain_scratch_bytes(const Caps &c)
 {
-    size_t nodes = (size_t)c.wchains / 4 + 8;
-    return sizeof(Chain) * c.wchains + sizeof(Seed) * c.wseeds + sizeof(BtNode) * nodes + sizeof(i32) * 2 * (size_t)c.wchains + 64;
+    return sizeof(Chain) * c.wchains + sizeof(Seed) * c.wseeds + sizeof(BtNode) * chain_nodes(c) + sizeof(i32) * 2 * (size_t)c.wchains + 64;
 }
 
-HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 slot, i64 rid, u8 *scratch, CtrLocal &ctr)
+HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
 {
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
-    B.n_chains[slot] = 0; B.frac_rep[slot] = 0.f;
+    ReadRec &R = B.rec[rid];
+    R.n_chains = 0; R.n_seeds = 0; R.chain_off = R.seed_off = 0; R.frac_rep = 0.f;
     if (B.ovf[rid]) return;
     ChainWork w;
-    size_t nodes = (size_t)caps.wchains / 4 + 8;
     u8 *p = scratch;
     w.chains = (Chain *)p; p += sizeof(Chain) * caps.wchains; w.cap_chains = caps.wchains;
     w.seeds = (Seed *)p; p += sizeof(Seed) * caps.wseeds; w.cap_seeds = caps.wseeds;
-    w.nodes = (BtNode *)p; p += sizeof(BtNode) * nodes; w.cap_nodes = (int)nodes;
+    w.nodes = (BtNode *)p; p += sizeof(BtNode) * chain_nodes(caps); w.cap_nodes = (int)chain_nodes(caps);
     i32 *order = (i32 *)p; p += sizeof(i32) * caps.wchains;
     i32 *kept = (i32 *)p;
     int n_order = 0;
-    int l_rep = build_chains(ix, opt, len, B.intv + slot * caps.intv, B.n_intv[slot], w, order, &n_order, ctr);
+    int l_rep = build_chains(ix, opt, len, B.pool.intv + R.intv_off, R.n_intv, w, order, &n_order, ctr);
     if (w.ovf) { B.ovf[rid] |= w.ovf; return; }
     int n = filter_chains(opt, w, order, n_order, kept);
-    // mem_flt_chained_seeds (bwa/bwamem.c:624-641) is a no-op below ~730 bp; longer reads are rejected by the host driver
-    // linearise kept chains into the read's output slot
-    Chain *oc = B.chains + slot * caps.chains;
-    Seed *os = B.seeds + slot * caps.seeds;
+    // mem_flt_chained_seeds (bwa/bwamem.c:624-641) only acts on reads longer than ~730 bp; the host driver rejects those
     int ns = 0;
-    if (n > caps.chains) { B.ovf[rid] |= OVF_CHAIN; return; }
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i) ns += w.chains[order[i]].n;
+    if (ns > caps.seeds) { B.ovf[rid] |= OVF_SEED; return; }
+    i64 coff = pool_alloc(B.pool, POOL_CHAIN, n), soff = pool_alloc(B.pool, POOL_SEED, ns);
+    if (coff < 0 || soff < 0) { B.ovf[rid] |= OVF_POOL; return; }
+    Chain *oc = B.pool.chains + coff;
+    Seed *os = B.pool.seeds + soff;
+    ns = 0;
+    for (int i = 0; i < n; ++i) {           // linearise the kept chains
         const Chain &c = w.chains[order[i]];
-        if (ns + c.n > caps.seeds) { B.ovf[rid] |= OVF_SEED; return; }
         oc[i] = c;
         oc[i].head = ns;
         for (int s = c.head; s >= 0; s = w.seeds[s].next) os[ns++] = w.seeds[s];
         oc[i].tail = ns - 1;
     }
-    B.n_chains[slot] = n;
-    B.frac_rep[slot] = (float)l_rep / len;
+    R.n_chains = n; R.n_seeds = ns; R.chain_off = coff; R.seed_off = soff;
+    R.frac_rep = (float)l_rep / len;
 }
 
 // ------------------------------------------------------------------ extend
-// scratch per slot: (maxlen+1) EH + caps.seeds u64
-HD size_t extend_scratch_bytes(const Caps &c) { return sizeof(EH) * (size_t)(c.maxlen + 2) + sizeof(u64) * (size_t)c.seeds; }
-
-HD void stage_extend(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 slot, i64 rid, u8 *scratch, CtrLocal &ctr)
+HD size_t extend_scratch_bytes(const Caps &c)
 {
-    B.n_regs[slot] = 0;
+    return sizeof(EH) * (size_t)(c.maxlen + 2) + sizeof(u64) * (size_t)c.seeds + sizeof(Reg) * (size_t)c.regs + 64;
+}
+
+HD void stage_extend(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
+{
+    ReadRec &R = B.rec[rid];
+    R.n_regs = 0; R.reg_off = 0;
     if (B.ovf[rid]) return;
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
     const u8 *seq = B.seq + B.seq_off[rid];
-    EH *eh = (EH *)scratch;
-    u64 *srt = (u64 *)(scratch + sizeof(EH) * (size_t)(caps.maxlen + 2));
-    RegSink av; av.a = B.regs + slot * caps.regs; av.n = 0; av.cap = caps.regs; av.overflow = false;
-    const Chain *oc = B.chains + slot * caps.chains;
-    const Seed *os = B.seeds + slot * caps.seeds;
-    int n = B.n_chains[slot];
-    float fr = B.frac_rep[slot];
-    for (int i = 0; i < n; ++i) {
-        chain2aln(ix, opt, len, seq, os + oc[i].head, oc[i].n, oc[i].rid, fr, av, srt, eh, ctr);
+    u8 *p = scratch;
+    EH *eh = (EH *)p; p += sizeof(EH) * (size_t)(caps.maxlen + 2);
+    u64 *srt = (u64 *)p; p += sizeof(u64) * (size_t)caps.seeds;
+    RegSink av; av.a = (Reg *)p; av.n = 0; av.cap = caps.regs; av.overflow = false;
+    const Chain *oc = B.pool.chains + R.chain_off;
+    const Seed *os = B.pool.seeds + R.seed_off;
+    for (int i = 0; i < R.n_chains; ++i) {
+        chain2aln(ix, opt, len, seq, os + oc[i].head, oc[i].n, oc[i].rid, R.frac_rep, av, srt, eh, ctr);
         if (av.overflow) { B.ovf[rid] |= OVF_REG; return; }
     }
-    B.n_regs[slot] = av.n;
+    i64 off = pool_alloc(B.pool, POOL_REG, av.n);
+    if (off < 0) { B.ovf[rid] |= OVF_POOL; return; }
+    for (int i = 0; i < av.n; ++i) B.pool.regs[off + i] = av.a[i];
+    R.n_regs = av.n; R.reg_off = off;
 }
 
 // ------------------------------------------------------------------ finalize
-// scratch per slot: (maxlen + 2 + extra) EH + z bytes + 2*regs i32
 HD size_t finalize_scratch_bytes(const Caps &c)
 {
-    return sizeof(EH) * (size_t)(c.maxlen + 2) + (size_t)c.z + sizeof(i32) * 2 * (size_t)c.regs + 64;
+    return sizeof(EH) * (size_t)(c.maxlen + 2) + (size_t)c.z + 8 + sizeof(i32) * 2 * (size_t)c.regs + sizeof(u32) * (size_t)c.cigar + (size_t)c.md + 64;
 }
 
-HD void stage_finalize(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 slot, i64 rid, u8 *scratch,
+HD void stage_finalize(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch,
                        const double *log_tab, int n_log, CtrLocal &ctr)
 {
-    B.n_hits[slot] = 0;
+    ReadRec &R = B.rec[rid];
+    R.n_hits = R.n_cigar = R.n_md = 0; R.hit_off = 0;
     if (B.ovf[rid]) return;
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
     const u8 *seq = B.seq + B.seq_off[rid];
     FinScratch fs;
     u8 *p = scratch;
     fs.eh = (EH *)p; p += sizeof(EH) * (size_t)(caps.maxlen + 2);
-    fs.z = p; fs.z_cap = caps.z; p += caps.z;
-    p = (u8 *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
-    fs.zidx = (i32 *)p;
+    fs.z = p; fs.z_cap = caps.z; p = align8(p + caps.z);
+    fs.zidx = (i32 *)p; p += sizeof(i32) * 2 * (size_t)caps.regs;
+    u32 *cg = (u32 *)p; p += sizeof(u32) * (size_t)caps.cigar;
+    char *md = (char *)p;
     fs.qbuf = 0;
     fs.log_tab = log_tab; fs.n_log = n_log;
-    Reg *a = B.regs + slot * caps.regs;
-    int n = B.n_regs[slot];
-    n = sort_dedup_patch(ix, opt, seq, n, a, fs, ctr);
+    Reg *a = B.pool.regs + R.reg_off;
+    int n = sort_dedup_patch(ix, opt, seq, R.n_regs, a, fs, ctr);
     for (int i = 0; i < n; ++i)                       // mem_align1_core tail (bwa/bwamem.c:1111-1115)
         if (a[i].rid >= 0 && ix.contig_alt[a[i].rid]) a[i].is_alt = 1;
     mark_primary_se(opt, n, a, B.hash_id[rid], fs.zidx);
-    if (n > caps.hits) { B.ovf[rid] |= OVF_OUT; return; }
-    b200_hit_t *H = B.hits + slot * caps.hits;
+    i64 hoff = pool_alloc(B.pool, POOL_HIT, n);
+    if (hoff < 0) { B.ovf[rid] |= OVF_POOL; return; }
+    b200_hit_t *H = B.pool.hits + hoff;
+    int tot_c = 0, tot_m = 0;
     for (int i = 0; i < n; ++i) {
-        u32 *cg = B.cigar + (slot * caps.hits + i) * (i64)caps.cigar;
-        char *md = B.md + (slot * caps.hits + i) * (i64)caps.md;
         AlnOut o = reg2aln(ix, opt, len, seq, &a[i], fs, cg, caps.cigar, md, caps.md, ctr);
-        if (o.overflow || o.need_host) { B.ovf[rid] |= o.need_host ? OVF_SCRATCH : OVF_OUT; return; }
+        if (o.overflow || o.need_host) { B.ovf[rid] |= OVF_OUT; return; }
+        i64 co = pool_alloc(B.pool, POOL_CIGAR, o.n_cigar), mo = pool_alloc(B.pool, POOL_MD, o.md_len + 1);
+        if (co < 0 || mo < 0) { B.ovf[rid] |= OVF_POOL; return; }
+        for (int k = 0; k < o.n_cigar; ++k) B.pool.cigar[co + k] = cg[k];
+        for (int k = 0; k < o.md_len; ++k) B.pool.md[mo + k] = md[k];
+        B.pool.md[mo + o.md_len] = 0;
+        tot_c += o.n_cigar; tot_m += o.md_len + 1;
         b200_hit_t &h = H[i];
         const Reg &r = a[i];
         h.rb = r.rb; h.re = r.re; h.pos = o.pos; h.hash = r.hash; h.qb = r.qb; h.qe = r.qe; h.rid = r.rid;
@@ -176,10 +219,10 @@ HD void stage_finalize(const DevIndex &ix, const Opt &opt, const Caps &caps, con
         h.w = r.w; h.seedcov = r.seedcov; h.secondary = r.secondary; h.secondary_all = r.secondary_all;
         h.seedlen0 = r.seedlen0; h.n_comp = r.n_comp; h.is_alt = r.is_alt; h.frac_rep = r.frac_rep;
         h.flag = o.flag; h.is_rev = o.is_rev; h.mapq = o.mapq; h.NM = o.NM; h.aln_sub = o.sub;
-        h.n_cigar = o.n_cigar; h.md_len = o.md_len; h.cigar_off = 0; h.md_off = 0;
+        h.n_cigar = o.n_cigar; h.md_len = o.md_len; h.cigar_off = co; h.md_off = mo;
         if (o.rid != r.rid) h.rid = -1000;   // the reference asserts equality (bwa/bwamem.c:1183)
     }
-    B.n_hits[slot] = n;
+    R.n_hits = n; R.n_cigar = tot_c; R.n_md = tot_m; R.hit_off = hoff;
 }
 
 } // namespace b200

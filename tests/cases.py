@@ -1,0 +1,91 @@
+"""Deterministic test inputs shared by the golden generator and the tests."""
+import numpy as np
+from seqlib_b200 import synth
+from seqlib_b200.abi import EXT_JOB_DTYPE
+
+KAT_NAMES = ["ref3", "ref4", "ref5", "ref6"]
+KAT_SEQS = ["ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCGATCGATCGATCGTAGC",
+            "CTACTTTATCATCTACACACTGCCTGACTGCGGCGACGAGCGAGCAGCTACTATCGACT",
+            "CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGCCATGT",
+            "TATCTACTGCGCGCGATCATCTAGCGCAGGACGAGCATC" + "N" * 100 + "CGATCGTTATTATCGAGCGACGATCTACTACGT"]
+KAT_QUERIES = ["ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCG", "CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGC"]
+KAT_SRAND = 0   # srand48(0) before ConstructIndex so the N -> lrand48()&3 draws are reproducible in one process
+
+
+def ids_for(n):
+    return np.arange(n, dtype=np.int64) * 7919 + 13
+
+
+def c1_reference():
+    l_pac = 10000
+    pac = synth.reference(l_pac)
+    ctg = synth.contigs_for(l_pac, 1, "ref10k")
+    return pac, ctg, synth.ascii_of(pac, 0, l_pac)
+
+
+def c1_reads(pac, ctg, n=1000):
+    a, off, _, _ = synth.reads(pac, 10000, ctg, n, 150, 0.01, 5e-4)
+    return a, off
+
+
+def read_lines(path):
+    with open(path) as f:
+        return [l.strip() for l in f if l.strip()]
+
+
+def c3_tuples(n, seed=0x5EED0003):
+    """Config-3 shaped ksw_extend2 jobs: target random 300, query = target[0:150] with 2 % subs + 0.2 % indels, h0 in [19,150]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tp = rng.integers(0, 4, size=n * 300, dtype=np.uint8)
+    qp = np.zeros(n * 150, dtype=np.uint8)
+    jobs = np.zeros(n, dtype=EXT_JOB_DTYPE)
+    for i in range(n):
+        t = tp[i * 300:(i + 1) * 300]
+        q = []
+        j = 0
+        while len(q) < 150 and j < 300:
+            x = rng.random()
+            if x < 0.001:
+                j += 1 + int(rng.integers(0, 3))
+                continue
+            if x < 0.002:
+                q.extend(rng.integers(0, 4, size=1 + int(rng.integers(0, 3))).tolist())
+                continue
+            b = int(t[j])
+            if rng.random() < 0.02:
+                b = (b + 1 + int(rng.integers(0, 3))) & 3
+            q.append(b)
+            j += 1
+        q = (q + [0] * 150)[:150]
+        qp[i * 150:(i + 1) * 150] = q
+        jobs[i] = (150, 300, i * 150, i * 300, 100, 5, 100, int(rng.integers(19, 151)))
+    return jobs, qp, tp
+
+
+def c3_tuples_fast(n, seed=0x5EED0003):
+    """Vectorised variant for the 1M-pair microbenchmark: substitutions only in the numpy path plus sparse indels."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tp = rng.integers(0, 4, size=(n, 300), dtype=np.uint8)
+    q = tp[:, :150].copy()
+    sub = rng.random((n, 150)) < 0.02
+    q[sub] = (q[sub] + rng.integers(1, 4, size=int(sub.sum()), dtype=np.uint8)) & 3
+    # one indel in ~26 % of the pairs (0.2 % per base): shift the tail by one base
+    has = rng.random(n) < 0.26
+    posn = rng.integers(10, 140, size=n)
+    idx = np.nonzero(has)[0]
+    for i in idx[: min(len(idx), 400000)]:
+        p = posn[i]
+        if i & 1:
+            q[i, p + 1:] = q[i, p:-1].copy()      # insertion in the query
+        else:
+            q[i, p:-1] = q[i, p + 1:].copy()      # deletion from the query
+    jobs = np.zeros(n, dtype=EXT_JOB_DTYPE)
+    jobs["qlen"] = 150
+    jobs["tlen"] = 300
+    jobs["q_off"] = np.arange(n, dtype=np.int64) * 150
+    jobs["t_off"] = np.arange(n, dtype=np.int64) * 300
+    jobs["w"] = 100
+    jobs["end_bonus"] = 5
+    jobs["zdrop"] = 100
+    jobs["h0"] = rng.integers(19, 151, size=n)
+    return jobs, q.reshape(-1), tp.reshape(-1)

@@ -56,58 +56,65 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
     R->ovf.assign(n, 0);
     R->intv_off.assign(n + 1, 0); R->chn_off.assign(n + 1, 0); R->reg_off.assign(n + 1, 0);
     R->seed_off.push_back(0);
+    // one set of pools for the whole call, like one chunk on the device
+    size_t pc[N_POOLS] = {(size_t)n * 64 + 4096, (size_t)n * 16 + 4096, (size_t)n * 64 + 4096, (size_t)n * 16 + 4096,
+                          (size_t)n * 8 + 4096, (size_t)n * 64 + 4096, (size_t)n * 256 + 4096};
+    std::vector<Intv> p_intv(pc[POOL_INTV] * 8); std::vector<Chain> p_chain(pc[POOL_CHAIN] * 8); std::vector<Seed> p_seed(pc[POOL_SEED] * 8);
+    std::vector<Reg> p_reg(pc[POOL_REG] * 8); std::vector<b200_hit_t> p_hit(pc[POOL_HIT] * 8); std::vector<u32> p_cig(pc[POOL_CIGAR] * 8);
+    std::vector<char> p_md(pc[POOL_MD] * 8);
+    unsigned long long used[N_POOLS] = {0};
+    std::vector<ReadRec> rec(n + 1); std::vector<u32> ovf(n + 1, 0);
+    Batch B; memset(&B, 0, sizeof(B));
+    B.n_reads = n; B.seq = seq.data(); B.seq_off = off; B.hash_id = ids; B.ovf = ovf.data(); B.rec = rec.data();
+    B.pool.intv = p_intv.data(); B.pool.chains = p_chain.data(); B.pool.seeds = p_seed.data(); B.pool.regs = p_reg.data();
+    B.pool.hits = p_hit.data(); B.pool.cigar = p_cig.data(); B.pool.md = p_md.data(); B.pool.used = used;
+    B.pool.cap[POOL_INTV] = p_intv.size(); B.pool.cap[POOL_CHAIN] = p_chain.size(); B.pool.cap[POOL_SEED] = p_seed.size();
+    B.pool.cap[POOL_REG] = p_reg.size(); B.pool.cap[POOL_HIT] = p_hit.size(); B.pool.cap[POOL_CIGAR] = p_cig.size(); B.pool.cap[POOL_MD] = p_md.size();
+    bool dbg = getenv("HOSTSIM_DEBUG") != 0;
+    std::vector<std::vector<Reg> > raws(n);
     for (int64_t r = 0; r < n; ++r) {
         for (int pass = 0; pass < 2; ++pass) {
             const Caps &c = caps[pass];
-            std::vector<Intv> intv(c.intv); std::vector<Chain> chains(c.chains); std::vector<Seed> sd(c.seeds); std::vector<Reg> regs(c.regs);
-            std::vector<b200_hit_t> hits(c.hits); std::vector<u32> cg((size_t)c.hits * c.cigar); std::vector<char> md((size_t)c.hits * c.md);
-            i32 n_intv = 0, n_chains = 0, n_regs = 0, n_hits = 0; float frac = 0; u32 ovf = 0;
-            Batch B; memset(&B, 0, sizeof(B));
-            int64_t one_off[2] = {0, off[r + 1] - off[r]};
-            B.n_reads = 1; B.seq = seq.data() + off[r]; B.seq_off = one_off; B.hash_id = &ids[r]; B.ovf = &ovf;
-            B.intv = intv.data(); B.n_intv = &n_intv; B.chains = chains.data(); B.seeds = sd.data(); B.n_chains = &n_chains; B.frac_rep = &frac;
-            B.regs = regs.data(); B.n_regs = &n_regs; B.hits = hits.data(); B.cigar = cg.data(); B.md = md.data(); B.n_hits = &n_hits;
             CtrLocal ctr;
             std::vector<u8> s1(seed_scratch_bytes(c) + 64), s2(chain_scratch_bytes(c) + 64), s3(extend_scratch_bytes(c) + 64), s4(finalize_scratch_bytes(c) + 64);
-            bool dbg = getenv("HOSTSIM_DEBUG") != 0;
-            if (dbg) fprintf(stderr, "read %ld pass %d seed\n", (long)r, pass);
-            stage_seed(ix, opt, c, B, 0, 0, s1.data(), ctr);
-            if (dbg) fprintf(stderr, " n_intv %d ovf %u; chain\n", n_intv, ovf);
-            stage_chain(ix, opt, c, B, 0, 0, s2.data(), ctr);
-            if (dbg) fprintf(stderr, " n_chains %d ovf %u; extend\n", n_chains, ovf);
-            std::vector<Reg> raw;
-            stage_extend(ix, opt, c, B, 0, 0, s3.data(), ctr);
-            raw.assign(regs.begin(), regs.begin() + n_regs);
-            if (dbg) fprintf(stderr, " n_regs %d ovf %u; finalize\n", n_regs, ovf);
-            stage_finalize(ix, opt, c, B, 0, 0, s4.data(), logtab.data(), (int)logtab.size(), ctr);
-            if (ovf && pass == 0) { R->ovf[r] = ovf; continue; }
-            if (ovf) { R->ovf[r] |= 0x80000000u | ovf; }
-            for (int i = 0; i < n_intv; ++i) R->intv.push_back(intv[i]);
-            for (int i = 0; i < n_chains; ++i) {
-                const Chain &ch = chains[i];
-                int64_t row[6] = {ch.pos, ch.rid, ch.w, ch.kept, ch.n, ch.first};
-                R->chn.insert(R->chn.end(), row, row + 6);
-                for (int s = 0; s < ch.n; ++s) {
-                    const Seed &q = sd[ch.head + s];
-                    int64_t srow[4] = {q.rbeg, q.qbeg, q.len, q.score};
-                    R->seeds.insert(R->seeds.end(), srow, srow + 4);
-                }
-                R->seed_off.push_back((int64_t)R->seeds.size() / 4);
-            }
-            for (size_t i = 0; i < raw.size(); ++i) {
-                b200_hit_t h; memset(&h, 0, sizeof(h));
-                h.rb = raw[i].rb; h.re = raw[i].re; h.qb = raw[i].qb; h.qe = raw[i].qe; h.rid = raw[i].rid; h.score = raw[i].score;
-                h.truesc = raw[i].truesc; h.w = raw[i].w; h.seedcov = raw[i].seedcov; h.seedlen0 = raw[i].seedlen0; h.frac_rep = raw[i].frac_rep;
-                R->regs.push_back(h);
-            }
-            for (int i = 0; i < n_hits; ++i) {
-                b200_hit_t h = hits[i];
-                h.cigar_off = (int64_t)R->cigar.size(); h.md_off = (int64_t)R->md.size();
-                for (int k = 0; k < h.n_cigar; ++k) R->cigar.push_back(cg[(size_t)i * c.cigar + k]);
-                for (int k = 0; k <= h.md_len; ++k) R->md.push_back(md[(size_t)i * c.md + k]);
-                R->hits.push_back(h);
-            }
+            ovf[r] = 0;
+            if (dbg) fprintf(stderr, "read %ld pass %d\n", (long)r, pass);
+            stage_seed(ix, opt, c, B, r, s1.data(), ctr);
+            stage_chain(ix, opt, c, B, r, s2.data(), ctr);
+            stage_extend(ix, opt, c, B, r, s3.data(), ctr);
+            raws[r].assign(B.pool.regs + rec[r].reg_off, B.pool.regs + rec[r].reg_off + rec[r].n_regs);
+            stage_finalize(ix, opt, c, B, r, s4.data(), logtab.data(), (int)logtab.size(), ctr);
+            if (ovf[r] && pass == 0) { R->ovf[r] = ovf[r]; continue; }
+            if (ovf[r]) R->ovf[r] |= 0x80000000u | ovf[r];
             break;
+        }
+        const ReadRec &rr = rec[r];
+        for (int i = 0; i < rr.n_intv; ++i) R->intv.push_back(B.pool.intv[rr.intv_off + i]);
+        for (int i = 0; i < rr.n_chains; ++i) {
+            const Chain &ch = B.pool.chains[rr.chain_off + i];
+            int64_t row[6] = {ch.pos, ch.rid, ch.w, ch.kept, ch.n, ch.first};
+            R->chn.insert(R->chn.end(), row, row + 6);
+            for (int s = 0; s < ch.n; ++s) {
+                const Seed &q = B.pool.seeds[rr.seed_off + ch.head + s];
+                int64_t srow[4] = {q.rbeg, q.qbeg, q.len, q.score};
+                R->seeds.insert(R->seeds.end(), srow, srow + 4);
+            }
+            R->seed_off.push_back((int64_t)R->seeds.size() / 4);
+        }
+        for (size_t i = 0; i < raws[r].size(); ++i) {
+            const Reg &q = raws[r][i];
+            b200_hit_t h; memset(&h, 0, sizeof(h));
+            h.rb = q.rb; h.re = q.re; h.qb = q.qb; h.qe = q.qe; h.rid = q.rid; h.score = q.score;
+            h.truesc = q.truesc; h.w = q.w; h.seedcov = q.seedcov; h.seedlen0 = q.seedlen0; h.frac_rep = q.frac_rep;
+            R->regs.push_back(h);
+        }
+        for (int i = 0; i < rr.n_hits; ++i) {
+            b200_hit_t h = B.pool.hits[rr.hit_off + i];
+            int64_t co = h.cigar_off, mo = h.md_off;
+            h.cigar_off = (int64_t)R->cigar.size(); h.md_off = (int64_t)R->md.size();
+            for (int k = 0; k < h.n_cigar; ++k) R->cigar.push_back(B.pool.cigar[co + k]);
+            for (int k = 0; k <= h.md_len; ++k) R->md.push_back(B.pool.md[mo + k]);
+            R->hits.push_back(h);
         }
         R->hit_off[r + 1] = (int64_t)R->hits.size();
         R->intv_off[r + 1] = (int64_t)R->intv.size();

@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the committed golden vectors
+produced by the reference's own bwa C and (b) the live reference library when oracle/_ref is present."""
+import ctypes
+import filecmp
+import os
+import numpy as np
+import pytest
+
+import cases
+import goldenlib
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from seqlib_b200 import capi as c
+    c.set_device(0)
+    return c
+
+
+def _libc():
+    return ctypes.CDLL(None)
+
+
+def test_kat_construct_and_align(capi):
+    """seq_test/seq_test.cpp:848-911: 4 inline contigs (one with 100 Ns), two queries."""
+    gold, z = goldenlib.load("kat")
+    _libc().srand48(cases.KAT_SRAND)
+    idx = capi.Index.construct(cases.KAT_NAMES, cases.KAT_SEQS)
+    a = idx.arrays()
+    assert a["seq_len"] == 646 and a["primary"] == int(z["primary"])
+    assert list(a["L2"]) == list(z["L2"])
+    assert np.array_equal(a["bwt"], z["bwt"])
+    assert np.array_equal(a["sa"], z["sa"])
+    assert np.array_equal(a["pac"][:len(z["pac"])], z["pac"])
+    assert idx.n_seqs() == 4 and idx.seq_name(2) == "ref5" and idx.seq_name(4) is None
+    got = capi.align(idx, cases.KAT_QUERIES, capi.default_opt(), z["ids"])
+    assert parity.compare_results(got, gold) == []
+    h = got.read_hits(0)
+    assert len(h) == 2 and got.cigar_str(h[0]) == "38M"
+    assert len(got.read_hits(1)) == 2
+
+
+def test_config1_10kb(capi):
+    """BASELINE config 1: 1k x 150 bp synthetic reads vs a 10 kb in-memory ConstructIndex, bit-exact."""
+    gold, z = goldenlib.load("c1")
+    pac, ctg, ref_ascii = cases.c1_reference()
+    idx = capi.Index.construct(["ref10k"], [ref_ascii])
+    a = idx.arrays()
+    assert a["primary"] == int(z["primary"]) and list(a["L2"]) == list(z["L2"])
+    assert np.array_equal(a["bwt"], z["bwt"]) and np.array_equal(a["sa"], z["sa"])
+    seqs, off = cases.c1_reads(pac, ctg)
+    got = capi.align(idx, (seqs, off), capi.default_opt(), cases.ids_for(len(off) - 1))
+    assert parity.compare_results(got, gold) == []
+    st = capi.last_stats()
+    assert st["n_launches"] > 0 and st["occ_blocks"] > 0
+
+
+@pytest.mark.parametrize("name", ["sim1_5k", "bcr_2k"])
+def test_tiny_fa_reads(capi, name):
+    """The reference's shipped tiny.fa index + its wgsim reads (repeats, split reads, soft clips)."""
+    gold, z = goldenlib.load(name)
+    idx = capi.Index.load(goldenlib.path("tiny", "tiny.fa"))
+    reads = cases.read_lines(goldenlib.path(name + ".txt"))
+    ioff, intv = capi.collect_intv(idx, reads, capi.default_opt())
+    assert np.array_equal(ioff, z["intv_off"])
+    assert np.array_equal(intv, z["intv"])
+    got = capi.align(idx, reads, capi.default_opt(), cases.ids_for(len(reads)))
+    assert parity.compare_results(got, gold) == []
+
+
+def test_small_chunks_and_spill(capi, monkeypatch):
+    """Chunked execution (B200_CHUNK) must not change results."""
+    gold, z = goldenlib.load("bcr_2k")
+    idx = capi.Index.load(goldenlib.path("tiny", "tiny.fa"))
+    reads = cases.read_lines(goldenlib.path("bcr_2k.txt"))
+    monkeypatch.setenv("B200_CHUNK", "1024")
+    got = capi.align(idx, reads, capi.default_opt(), cases.ids_for(len(reads)))
+    assert parity.compare_results(got, gold) == []
+
+
+def test_index_write_load_roundtrip(capi, tmp_path):
+    """WriteIndex/LoadIndex on-disk format: loading tiny.fa and writing it back is byte-identical."""
+    idx = capi.Index.load(goldenlib.path("tiny", "tiny.fa"))
+    out = str(tmp_path / "rt")
+    idx.write(out)
+    for ext in ("bwt", "sa", "pac", "ann", "amb"):
+        assert filecmp.cmp(out + "." + ext, goldenlib.path("tiny", "tiny.fa." + ext), shallow=False), ext
+    idx2 = capi.Index.load(out)
+    assert idx2.n_seqs() == idx.n_seqs() and idx2.l_pac() == idx.l_pac()
+
+
+def test_gpu_builder_reproduces_tiny_index(capi):
+    """The GPU suffix sort must reproduce the reference's shipped tiny.fa.bwt/.sa from the pac alone (real genome, repeats)."""
+    idx = capi.Index.load(goldenlib.path("tiny", "tiny.fa"))
+    a = idx.arrays()
+    built = capi.Index.construct_pac(a["pac"], a["l_pac"], a["contigs"], keep_host=True)
+    b = built.arrays()
+    assert b["primary"] == a["primary"] and list(b["L2"]) == list(a["L2"])
+    assert np.array_equal(b["bwt"], a["bwt"])
+    assert np.array_equal(b["sa"], a["sa"])
+
+
+def test_ksw_extend2_batch(capi):
+    z = np.load(goldenlib.path("ksw_c3.npz"))
+    jobs, qp, tp = cases.c3_tuples(4000)
+    opt = capi.default_opt()
+    out, cells, ms = capi.ksw_extend2_batch(jobs, qp, tp, np.array(list(opt.mat), dtype=np.int8))
+    for f in out.dtype.names:
+        assert np.array_equal(out[f], z["out"][f]), f
+    assert cells > 0
+
+
+def test_against_live_reference_with_indels(capi):
+    """Live oracle/_ref (the reference's bwa compiled in place): 200 kb random reference, reads with subs + indels + Ns."""
+    from oracle import pyref
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from seqlib_b200 import synth
+    l_pac = 200000
+    pac = synth.reference(l_pac, seed=77)
+    ctg = synth.contigs_for(l_pac, 3, "c")
+    names = [c[0] for c in ctg]
+    seqs = [synth.ascii_of(pac, c[1], c[1] + c[2]) for c in ctg]
+    idx = capi.Index.construct(names, seqs)
+    ridx = pyref.RefIndex.construct(names, seqs)
+    a, b = idx.arrays(), ridx.arrays()
+    assert np.array_equal(a["bwt"], b["bwt"]) and np.array_equal(a["sa"], b["sa"]) and a["primary"] == b["primary"]
+    r, off, _, _ = synth.reads(pac, l_pac, ctg, 20000, 150, 0.02, 2e-3, seed=99)
+    r = r.copy()
+    r[::997] = ord("N")                      # sprinkle ambiguous bases
+    ids = cases.ids_for(20000)
+    opt = capi.default_opt()
+    got = capi.align(idx, (r, off), opt, ids)
+    exp, _ = pyref.align(ridx, (r, off), opt, ids, n_threads=4)
+    assert parity.compare_results(got, exp) == []
+
+
+def test_scale_properties(capi):
+    """Size-independent properties on a larger run: idempotence, truth recovery, CIGAR/NM consistency."""
+    from seqlib_b200 import synth
+    l_pac = 4_000_000
+    pac = synth.reference(l_pac, seed=5)
+    ctg = synth.contigs_for(l_pac, 4)
+    idx = capi.Index.construct_pac(pac, l_pac, ctg)
+    n = 200000
+    r, off, pos, strand = synth.reads(pac, l_pac, ctg, n, 150, 0.01, 0.0, seed=6)
+    ids = cases.ids_for(n)
+    opt = capi.default_opt()
+    a = capi.align(idx, (r, off), opt, ids)
+    b = capi.align(idx, (r, off), opt, ids)
+    assert np.array_equal(a.hit_off, b.hit_off) and a.hits.tobytes() == b.hits.tobytes() and np.array_equal(a.cigar, b.cigar)
+    first = a.hits[a.hit_off[:-1][np.diff(a.hit_off) > 0]]
+    coff = np.array([c[1] for c in ctg], dtype=np.int64)
+    has = np.diff(a.hit_off) > 0
+    assert has.mean() > 0.999
+    gpos = coff[first["rid"]] + first["pos"]
+    ok = (np.abs(gpos - pos[has]) <= 8) & (first["is_rev"] == strand[has])
+    assert ok.mean() > 0.995
+    # query span of every hit equals the M/I/S(op3) lengths of its CIGAR
+    ops = a.cigar & 0xf
+    lens = (a.cigar >> 4).astype(np.int64)
+    qlen = np.where((ops == 0) | (ops == 1) | (ops == 3), lens, 0)
+    csum = np.concatenate([[0], np.cumsum(qlen)])
+    per_hit = csum[a.hits["cigar_off"] + a.hits["n_cigar"]] - csum[a.hits["cigar_off"]]
+    assert np.all(per_hit == 150)
