@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of the seed-and-extend hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's own bwa C on the host cores)
+
+A "step" is one pass of the hot path (SMEM seeding -> chaining -> banded SW -> CIGAR/MAPQ, i.e. what
+BWAAligner::alignSequence computes) over one batch of synthetic 150-bp reads per GPU.  Default workload is
+BASELINE.json configs[1]: 10 M reads vs a 3 Gb uniform-random reference (24 contigs) on one B200; with
+N > 1 every GPU gets its own 10 M reads (weak scaling), the index is built once on rank 0 and broadcast
+over NCCL, the read shards are scattered over NCCL.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "ksw"])
+    ap.add_argument("--ref-len", type=int, default=int(os.environ.get("B200_BENCH_REF_LEN", 3_000_000_000)))
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("B200_BENCH_READS", 10_000_000)), help="reads per GPU per step")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def make_workload(args, n_total_reads):
+    from seqlib_b200 import synth
+    l_pac = args.ref_len
+    n_ctg = 24 if l_pac >= 24 * 1000 else 1
+    t0 = time.time()
+    pac = synth.reference(l_pac)
+    ctg = synth.contigs_for(l_pac, n_ctg)
+    seqs, off, pos, strand = synth.reads(pac, l_pac, ctg, n_total_reads, args.read_len, 0.01, 0.0)
+    return pac, ctg, seqs, off, time.time() - t0
+
+
+def cpu_baseline_sample(ridx, seqs, off, read_len, opt, target_s, cores):
+    """The reference's own batched schedule (mem_process_seqs, all cores) on a bounded sample of the same reads."""
+    from oracle import pyref
+    n_all = len(off) - 1
+    probe = min(n_all, 4000)
+    t = pyref.process_seqs(ridx, (seqs[:probe * read_len], off[:probe + 1]), opt, cores)
+    rate = probe / max(t, 1e-6)
+    n = int(min(n_all, max(probe, rate * target_s)))
+    t = pyref.process_seqs(ridx, (seqs[:n * read_len], off[:n + 1]), opt, cores)
+    return n / t, n, t
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's bwa C (oracle/_ref, compiled from the mount) on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyref
+    from seqlib_b200 import capi
+    cores = os.cpu_count() or 1
+    capi.set_device(0)
+    pac, ctg, seqs, off, t_gen = make_workload(args, min(args.reads, 2_000_000))
+    # the 3 Gb FM-index is a pure function of the text; the GPU builder only prepares the input of the timed reference code
+    t0 = time.time()
+    idx = capi.Index.construct_pac(pac, args.ref_len, ctg, keep_host=True)
+    t_index = time.time() - t0
+    ridx = pyref.RefIndex.from_view(idx.view(), keep=idx)
+    opt = pyref.default_opt()
+    probe = min(len(off) - 1, 4000)
+    t = pyref.process_seqs(ridx, (seqs[:probe * args.read_len], off[:probe + 1]), opt, cores)
+    rate = probe / max(t, 1e-6)
+    n = int(min(len(off) - 1, max(probe, rate * args.cpu_seconds)))
+    sub = (seqs[:n * args.read_len], off[:n + 1])
+    for _ in range(max(0, min(args.warmup, 1))):
+        pyref.process_seqs(ridx, sub, opt, cores)
+    times = [pyref.process_seqs(ridx, sub, opt, cores) for _ in range(args.steps)]
+    tot = sum(times)
+    value = n * args.steps / tot
+    line = {
+        "impl": "reference", "metric": "150bp reads/sec (seed+chain+SW end-to-end)", "value": value, "unit": "reads/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "10M x 150bp synthetic reads vs %d bp random reference (24 contigs)" % args.ref_len,
+                   "reads_per_step": n, "read_len": args.read_len, "ref_len": args.ref_len, "l2": "inputs larger than L2"},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "reference",
+                         "sample": "%d reads per step through mem_process_seqs (bwa/bwamem.c:1235-1264), %d threads" % (n, cores)},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "index_build_s": t_index,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ksw(args):
+    """Config 3: ksw_extend2 1M x (150 q, 300 r) microbenchmark, GCUPS."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    from seqlib_b200 import capi
+    capi.set_device(0)
+    n = int(os.environ.get("B200_BENCH_KSW_PAIRS", 1_000_000))
+    jobs, qp, tp = cases.c3_tuples_fast(n)
+    opt = capi.default_opt()
+    mat = np.array(list(opt.mat), dtype=np.int8)
+    for _ in range(args.warmup):
+        capi.ksw_extend2_batch(jobs, qp, tp, mat)
+    ms, cells = [], 0
+    for _ in range(args.steps):
+        out, cells, t = capi.ksw_extend2_batch(jobs, qp, tp, mat)
+        ms.append(t)
+    gcups = cells / (np.mean(ms) * 1e-3) / 1e9
+    line = {"metric": "ksw_extend2 GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": {"workload": "ksw_extend2 %d x (150q,300r) pairs" % n, "cells_per_step": int(cells)},
+            "gpu_launches": args.steps}
+    if not args.no_cpu_baseline:
+        from oracle import pyref
+        m = min(n, 20000)
+        cores = os.cpu_count() or 1
+        _, sec = pyref.ksw_extend2_batch(jobs[:m], qp, tp, mat, n_threads=cores)
+        # cells of the sample: proportional share
+        line["cpu_baseline"] = {"value": cells * (m / n) / sec / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                                "sample": "%d pairs, scalar ksw_extend2 (bwa/ksw.c:416-515) on %d threads" % (m, cores)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.workload == "ksw":
+        return run_ksw(args)
+    import torch
+    import torch.distributed as dist
+    from seqlib_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    capi.set_device(local)
+    dev = torch.device("cuda", local)
+    n_per = args.reads
+    L = args.read_len
+    opt = capi.default_opt()
+    cpu_line = None
+    t_index = t_bcast = 0.0
+
+    # ---- inputs: rank 0 generates reference + all reads, builds the index on its GPU ------------------
+    if rank == 0:
+        pac, ctg, seqs_all, off_all, t_gen = make_workload(args, n_per * world)
+        t0 = time.time()
+        want_cpu = (world == 1 and not args.no_cpu_baseline)
+        idx = capi.Index.construct_pac(pac, args.ref_len, ctg, keep_host=want_cpu)
+        torch.cuda.synchronize()
+        t_index = time.time() - t0
+        if want_cpu:
+            try:
+                from oracle import pyref
+                cores = os.cpu_count() or 1
+                ridx = pyref.RefIndex.from_view(idx.view(), keep=idx)
+                v, n_s, t_s = cpu_baseline_sample(ridx, seqs_all, off_all, L, opt, args.cpu_seconds, cores)
+                cpu_line = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
+                            "sample": "%d of the same reads through mem_process_seqs (bwa/bwamem.c:1235-1264), %d threads, %.1f s" % (n_s, cores, t_s)}
+                del ridx
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                cpu_line = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+    if world > 1:
+        # one NCCL broadcast of the index image, one NCCL scatter of the read shards
+        nb = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            nb[0] = idx.blob_bytes()
+        dist.broadcast(nb, 0)
+        blob = torch.empty(int(nb.item()), dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idx.export_blob(blob.data_ptr())
+            idx.close()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.time()
+        dist.broadcast(blob, 0)
+        torch.cuda.synchronize()
+        t_bcast = time.time() - t0
+        idx = capi.Index.attach_blob(blob.data_ptr(), blob.numel(), keep=blob)
+        shard = torch.empty(n_per * L, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            full = torch.from_numpy(seqs_all).pin_memory()
+            parts = [full[r * n_per * L:(r + 1) * n_per * L].to(dev, non_blocking=True) for r in range(world)]
+            torch.cuda.synchronize()
+            dist.scatter(shard, parts, src=0)
+            del parts
+        else:
+            dist.scatter(shard, None, src=0)
+        torch.cuda.synchronize()
+        seqs = shard.cpu().numpy()
+        del shard
+    else:
+        seqs = seqs_all
+    off = np.arange(n_per + 1, dtype=np.int64) * L
+    ids = (np.arange(n_per, dtype=np.int64) + rank * n_per) * 7919 + 13
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value leg: reads resident in HBM, all kernels, results left on the device ----------------------
+    batch = capi.Batch(idx, (seqs, off), opt, ids)
+    for _ in range(args.warmup):
+        batch.run()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    launches = 0
+    dev_ms = 0.0
+    stage = {"ms_seed": 0.0, "ms_chain": 0.0, "ms_extend": 0.0, "ms_finalize": 0.0}
+    stats = None
+    for _ in range(args.steps):
+        launches += batch.run()
+        stats = capi.last_stats()
+        dev_ms += stats["ms_total"]
+        for k in stage:
+            stage[k] += stats[k]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms / 1000.0, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, wall_s = float(t[0]), float(t[1])
+    n_hits_dev = None
+    res = batch.fetch()
+    n_hits_dev = len(res.hits)
+    mapped = float((np.diff(res.hit_off) > 0).mean())
+    del res
+    batch.close()
+
+    # ---- e2e leg: the C ABI call on pinned host buffers, H2D of reads and D2H of results inside the timed region
+    pin_seqs = torch.from_numpy(seqs).pin_memory()
+    pin_off = torch.from_numpy(off).pin_memory()
+    pin_ids = torch.from_numpy(ids).pin_memory()
+    seqs_p, off_p, ids_p = pin_seqs.numpy(), pin_off.numpy(), pin_ids.numpy()
+    h = capi.align_raw(idx, seqs_p, off_p, opt, ids_p)
+    summ = capi.results_summary(h)
+    capi.results_free(h)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        h = capi.align_raw(idx, seqs_p, off_p, opt, ids_p)
+        capi.results_free(h)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    h2d = int(seqs.nbytes + off.nbytes + ids.nbytes)
+    d2h = int(summ["n_hits"] * 144 + summ["n_cigar"] * 4 + summ["n_md"] + (n_per + 1) * 8)
+
+    if rank == 0:
+        peaks, how = measured_peaks()
+        total_reads = n_per * world * args.steps
+        value = total_reads / dev_s
+        # roofline of the dominant kernel (k_seed): algorithmic bytes = 32 B per Occ block fetched + the read bases + the emitted intervals
+        seed_s = stage["ms_seed"] / 1000.0 / args.steps
+        occ_per_step = stats["occ_blocks"]
+        alg_bytes = occ_per_step * 32 + n_per * L
+        achieved = alg_bytes / seed_s / 1e9 if seed_s > 0 else 0.0
+        line = {
+            "metric": "150bp reads/sec (seed+chain+SW end-to-end)", "value": value, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "%d x %dbp synthetic reads per GPU vs %d bp random reference (24 contigs), 1%% substitutions" % (n_per, L, args.ref_len),
+                       "reads_per_gpu_per_step": n_per, "read_len": L, "ref_len": args.ref_len,
+                       "parallelism": "reads sharded x%d, index replicated (one NCCL broadcast)" % world,
+                       "l2": "inputs larger than L2 (index %.1f GB, reads %.2f GB per GPU)" % (idx.blob_bytes() / 1e9, n_per * L / 1e9)},
+            "e2e": {"value": n_per * world * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_stage<0> (SMEM seeding)", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                         "frac": achieved / peaks.get("hbm_gbs", 6650.0), "traffic": None, "peak_source": how,
+                         "algorithmic_bytes_per_read": alg_bytes / n_per, "kernel_ms": 1000.0 * seed_s},
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "wall_s_timed_region": wall_s, "mapped_fraction": mapped, "hits_per_step": n_hits_dev,
+            "index_build_s": t_index, "index_bcast_s": t_bcast, "spill_reads_per_step": stats["n_overflow"],
+            "sw_cells_per_step": stats["sw_cells"], "occ_blocks_per_read": occ_per_step / n_per,
+        }
+        if cpu_line is not None:
+            line["cpu_baseline"] = cpu_line
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

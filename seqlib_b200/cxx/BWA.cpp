@@ -1,0 +1,291 @@
+// BWA.cpp -- host side of the drop-in classes BWAIndex, BWAAligner and the legacy BWAWrapper.
+// Compute goes through the C ABI (include/seqlib_b200.h) into the CUDA engine; what stays here is the
+// reference's own host-side record assembly, restated from src/BWAIndex.cpp:19-180,382-418 and
+// src/BWAAligner.cpp:7-265 (argument checks, exception types, hit sorting/filtering quirks Q1-Q6 of
+// SURVEY.md 8b, bam1_t packing, NA/NM/AS tags).
+#include <algorithm>
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+#include "SeqLib/BWAIndex.h"
+#include "SeqLib/BWAAligner.h"
+#include "SeqLib/BWAWrapper.h"
+#include "seqlib_b200.h"
+
+namespace SeqLib {
+
+// ------------------------------------------------------------------ BWAIndex
+BWAIndex::~BWAIndex() { if (idx_) b200_index_destroy(idx_); }
+
+void BWAIndex::LoadIndex(const std::string &prefix)
+{
+    b200_index *n = nullptr;
+    if (b200_index_load(prefix.c_str(), &n) != B200_OK || !n) throw std::runtime_error("Failed to load BWA index");
+    if (idx_) b200_index_destroy(idx_);
+    idx_ = n;
+}
+
+BamHeader BWAIndex::HeaderFromIndex() const { return BamHeader(printSamHeader()); }
+
+int BWAIndex::NumSequences() const { return idx_ ? b200_index_n_seqs(idx_) : 0; }
+
+std::string BWAIndex::ChrIDToName(int id) const
+{
+    if (!idx_) throw std::runtime_error("Index has not be loaded / constructed");
+    int n = b200_index_n_seqs(idx_);
+    if (id < 0 || id >= n) {
+        std::ostringstream ss;
+        ss << "BWAIndex::ChrIDToName - id out of bounds of refs in index for id of " << id << " on IDX of size " << n;
+        throw std::out_of_range(ss.str());
+    }
+    return std::string(b200_index_seq_name(idx_, id));
+}
+
+std::string BWAIndex::printSamHeader() const
+{
+    if (!idx_) return "";
+    std::ostringstream out;
+    int n = b200_index_n_seqs(idx_);
+    for (int i = 0; i < n; ++i) out << "@SQ\tSN:" << b200_index_seq_name(idx_, i) << "\tLN:" << b200_index_seq_len(idx_, i) << "\n";
+    return out.str();
+}
+
+void BWAIndex::ConstructIndex(const UnalignedSequenceVector &refs)
+{
+    if (refs.empty()) return;
+    for (auto const &r : refs)
+        if (r.Name.empty() || r.Seq.empty())
+            throw std::invalid_argument("BWAIndex::Construct each reference must have non-empty Name and Seq");
+    if (idx_) { b200_index_destroy(idx_); idx_ = nullptr; }
+    std::vector<const char *> names, seqs;
+    for (auto const &r : refs) { names.push_back(r.Name.c_str()); seqs.push_back(r.Seq.c_str()); }
+    b200_index *n = nullptr;
+    int rc = b200_index_construct((int)refs.size(), names.data(), seqs.data(), 1, &n);
+    if (rc != B200_OK || !n) throw std::runtime_error(std::string("BWAIndex::Construct BWT construction failed: ") + b200_last_error());
+    idx_ = n;
+}
+
+void BWAIndex::WriteIndex(const std::string &prefix) const
+{
+    if (!idx_) throw std::runtime_error("BWAIndex::writeIndex: no index loaded");
+    int rc = b200_index_write(idx_, prefix.c_str());
+    if (rc != B200_OK) throw std::runtime_error(std::string("BWAIndex::writeIndex: ") + b200_last_error());
+}
+
+std::ostream &operator<<(std::ostream &os, const BWAIndex &idx)
+{
+    if (!idx.idx_) os << "[BWAIndex] <no index loaded>";
+    else os << "[BWAIndex] #seqs=" << b200_index_n_seqs(idx.idx_) << " pac_len=" << b200_index_l_pac(idx.idx_);
+    return os;
+}
+
+// ------------------------------------------------------------------ BWAAligner
+BWAAligner::BWAAligner(BWAIndexPtr idx) : index_(std::move(idx))
+{
+    b200_mem_opt_init(&opt_);
+    opt_.flag |= 0x200;                               // MEM_F_SOFTCLIP (SeqLib/BWAAligner.h:17)
+}
+
+#define NONNEG(v, what) do { if ((v) < 0) throw std::invalid_argument(what); } while (0)
+void BWAAligner::SetGapOpen(int v) { NONNEG(v, "SetGapOpen: gap_open must be >= 0"); opt_.o_ins = opt_.o_del = v; }
+void BWAAligner::SetGapExtension(int v) { NONNEG(v, "SetGapExtension: gap_ext must be >= 0"); opt_.e_ins = opt_.e_del = v; }
+void BWAAligner::SetMismatchPenalty(int v) { NONNEG(v, "SetMismatchPenalty: mismatch must be >= 0"); opt_.b = v; b200_fill_scmat(opt_.a, opt_.b, opt_.mat); }
+void BWAAligner::SetZDropoff(int v) { NONNEG(v, "SetZDropoff: zdrop must be >= 0"); opt_.zdrop = v; }
+void BWAAligner::SetAScore(int a)
+{   // scales the penalties but, like the reference, leaves `mat` alone (src/BWAAligner.cpp:43-59)
+    NONNEG(a, "SetAScore: a must be >= 0");
+    opt_.a = a; opt_.b *= a; opt_.T *= a; opt_.o_ins *= a; opt_.o_del *= a; opt_.e_ins *= a; opt_.e_del *= a;
+    opt_.zdrop *= a; opt_.pen_clip5 *= a; opt_.pen_clip3 *= a; opt_.pen_unpaired *= a;
+}
+void BWAAligner::Set3primeClippingPenalty(int v) { NONNEG(v, "Set3primeClippingPenalty: penalty must be >= 0"); opt_.pen_clip3 = v; }
+void BWAAligner::Set5primeClippingPenalty(int v) { NONNEG(v, "Set5primeClippingPenalty: penalty must be >= 0"); opt_.pen_clip5 = v; }
+void BWAAligner::SetBandwidth(int v) { NONNEG(v, "SetBandwidth: bandwidth must be >= 0"); opt_.w = v; }
+void BWAAligner::SetReseedTrigger(float v) { if (v < 0.0f) throw std::invalid_argument("SetReseedTrigger: trigger must be >= 0"); opt_.split_factor = v; }
+
+namespace {
+
+struct HitRef { const b200_hit_t *h; };
+
+// sort by descending MAPQ, then (rid, pos)  (src/BWAAligner.cpp:7-11)
+bool aln_sort(const HitRef &a, const HitRef &b)
+{
+    if (a.h->mapq != b.h->mapq) return a.h->mapq > b.h->mapq;
+    if (a.h->rid != b.h->rid) return a.h->rid < b.h->rid;
+    return a.h->pos < b.h->pos;
+}
+
+// Turns the hits of one read into BamRecords (src/BWAAligner.cpp:111-248).
+void emit_records(const std::string &seq, const std::string &name, const b200_results_view_t &v, int64_t read, bool hardclip,
+                  double keepSecFrac, int maxSecondary, bool primary_first, BamRecordPtrVector &out)
+{
+    int64_t b0 = v.hit_off[read], b1 = v.hit_off[read + 1];
+    int n_regs = (int)(b1 - b0);
+    double primaryScore = 0;
+    std::vector<HitRef> hits;
+    hits.reserve(n_regs);
+    for (int64_t i = b0; i < b1; ++i) {
+        const b200_hit_t &r = v.hits[i];
+        // Q1: tests the int `secondary` (-1 = primary is non-zero too)
+        if (r.secondary && (keepSecFrac < 0.0 || keepSecFrac > 1.0)) continue;
+        HitRef h; h.h = &r; hits.push_back(h);
+    }
+    std::sort(hits.begin(), hits.end(), aln_sort);
+    if (primary_first)            // legacy BWAWrapper ordering: primaries ahead of secondaries, otherwise as sorted
+        std::stable_partition(hits.begin(), hits.end(), [](const HitRef &x) { return !(x.h->flag & BAM_FSECONDARY); });
+    for (size_t i = 0; i < hits.size(); ++i) {
+        const b200_hit_t &h = *hits[i].h;
+        bool isSec = (h.flag & BAM_FSECONDARY);
+        bool tooLow = isSec && (primaryScore * keepSecFrac > h.score);
+        bool tooMany = isSec && (int(i) > maxSecondary);                 // Q2: rank, not a secondary counter
+        if (tooLow || tooMany) continue;
+        if (!isSec) primaryScore = h.score;                             // Q3
+        auto rec = std::make_shared<BamRecord>();
+        bam1_t *b = rec->b.get();
+        b->core.tid = h.rid; b->core.pos = h.pos; b->core.qual = (uint8_t)h.mapq; b->core.flag = (uint16_t)h.flag;
+        b->core.n_cigar = (uint32_t)h.n_cigar; b->core.mtid = -1; b->core.mpos = -1; b->core.isize = 0;
+        if (h.is_rev) b->core.flag |= BAM_FREVERSE;
+        const uint32_t *cig = v.cigar + h.cigar_off;
+        std::string clipped = seq;
+        if (hardclip) {                                                  // Q6
+            size_t tstart = 0, clen = 0;
+            for (int c = 0; c < h.n_cigar; ++c) {
+                uint32_t op = bam_cigar_op(cig[c]);
+                if (c == 0 && op == BAM_CREF_SKIP) tstart = bam_cigar_oplen(cig[c]);
+                else if (bam_cigar_type(op) & 1) clen += bam_cigar_oplen(cig[c]);
+            }
+            clipped = seq.substr(tstart, clen);
+        }
+        b->core.l_qname = (uint16_t)(name.size() + 1);
+        b->core.l_qseq = (int32_t)clipped.size();
+        b->l_data = b->core.l_qname + (h.n_cigar << 2) + ((b->core.l_qseq + 1) >> 1) + b->core.l_qseq;
+        b->data = (uint8_t *)std::malloc(b->l_data ? b->l_data : 1);
+        if (!b->data) throw std::bad_alloc();
+        b->m_data = (uint32_t)b->l_data;
+        std::memset(b->data, 0, b->l_data);
+        std::memcpy(b->data, name.c_str(), name.size() + 1);
+        uint32_t *dst = bam_get_cigar(b);
+        uint32_t newOp = hardclip ? BAM_CHARD_CLIP : BAM_CSOFT_CLIP;
+        for (int k = 0; k < h.n_cigar; ++k) {
+            uint32_t c = cig[k];
+            if ((c & BAM_CIGAR_MASK) == BAM_CREF_SKIP) c = (c & ~(uint32_t)BAM_CIGAR_MASK) | newOp;
+            std::memcpy((uint8_t *)dst + 4 * k, &c, 4);
+        }
+        uint8_t *sb = bam_get_seq(b);
+        int sl = (int)clipped.size();
+        if (h.is_rev) {
+            int j = 0;
+            for (int p = sl - 1; p >= 0; --p, ++j) {
+                uint8_t x = 15;
+                switch (clipped[p]) { case 'A': x = 8; break; case 'C': x = 2; break; case 'G': x = 4; break; case 'T': x = 1; break; }
+                sb[j >> 1] = (uint8_t)((sb[j >> 1] & ~(0xF << ((~j & 1) << 2))) | x << ((~j & 1) << 2));
+            }
+        } else {
+            for (int p = 0; p < sl; ++p) {
+                uint8_t x = 15;
+                switch (clipped[p]) { case 'A': x = 1; break; case 'C': x = 2; break; case 'G': x = 4; break; case 'T': x = 8; break; }
+                sb[p >> 1] = (uint8_t)((sb[p >> 1] & ~(0xF << ((~p & 1) << 2))) | x << ((~p & 1) << 2));
+            }
+        }
+        // Q4: the reference sets qual[0] = 0xff and leaves the rest uninitialised; here the whole string is "absent"
+        if (sl) std::memset(bam_get_qual(b), 0xff, sl);
+        rec->AddIntTag("NA", n_regs);
+        rec->AddIntTag("NM", h.NM);
+        rec->AddIntTag("AS", h.score);                                   // Q5: no XA tag is ever produced
+        out.push_back(rec);
+    }
+}
+
+} // namespace
+
+void BWAAligner::alignSequence(const std::string &seq, const std::string &name, BamRecordPtrVector &out, bool hardclip,
+                               double keepSecFrac, int maxSecondary) const
+{
+    if (index_->IsEmpty()) return;
+    int64_t off[2] = {0, (int64_t)seq.size()};
+    int64_t id = lrand48();                                            // mem_align1's tie-break draw (bwa/bwamem_extra.c:112)
+    b200_results_t *res = nullptr;
+    int rc = b200_mem_align_batch(index_->handle(), &opt_, 1, seq.data(), off, &id, &res);
+    if (rc != B200_OK) throw std::runtime_error(std::string("BWAAligner::alignSequence: ") + b200_last_error());
+    b200_results_view_t v;
+    b200_results_view(res, &v);
+    try { emit_records(seq, name, v, 0, hardclip, keepSecFrac, maxSecondary, false, out); }
+    catch (...) { b200_results_free(res); throw; }
+    b200_results_free(res);
+}
+
+void BWAAligner::alignSequence(const UnalignedSequence &us, BamRecordPtrVector &out, bool hardclip, double keepSecFrac,
+                               int maxSecondary) const
+{
+    alignSequence(us.Seq, us.Name, out, hardclip, keepSecFrac, maxSecondary);
+    if (!copyComment_) return;
+    for (auto &rec : out) rec->AddZTag("BC", us.Com);
+}
+
+void BWAAligner::alignSequences(const UnalignedSequenceVector &reads, std::vector<BamRecordPtrVector> &out, bool hardclip,
+                                double keepSecFrac, int maxSecondary) const
+{
+    out.clear();
+    out.resize(reads.size());
+    if (index_->IsEmpty() || reads.empty()) return;
+    std::vector<int64_t> off(reads.size() + 1, 0), ids(reads.size());
+    for (size_t i = 0; i < reads.size(); ++i) { off[i + 1] = off[i] + (int64_t)reads[i].Seq.size(); ids[i] = lrand48(); }
+    std::string all;
+    all.reserve((size_t)off.back());
+    for (auto &r : reads) all += r.Seq;
+    b200_results_t *res = nullptr;
+    int rc = b200_mem_align_batch(index_->handle(), &opt_, (int64_t)reads.size(), all.data(), off.data(), ids.data(), &res);
+    if (rc != B200_OK) throw std::runtime_error(std::string("BWAAligner::alignSequences: ") + b200_last_error());
+    b200_results_view_t v;
+    b200_results_view(res, &v);
+    try {
+        for (size_t i = 0; i < reads.size(); ++i)
+            emit_records(reads[i].Seq, reads[i].Name, v, (int64_t)i, hardclip, keepSecFrac, maxSecondary, false, out[i]);
+    } catch (...) { b200_results_free(res); throw; }
+    b200_results_free(res);
+}
+
+// ------------------------------------------------------------------ BWAWrapper (legacy facade)
+BWAWrapper::BWAWrapper() : index_(std::make_shared<BWAIndex>()), aligner_(std::make_shared<BWAAligner>(index_)) {}
+
+void BWAWrapper::ConstructIndex(const UnalignedSequenceVector &v) { index_->ConstructIndex(v); }
+
+bool BWAWrapper::LoadIndex(const std::string &file)
+{
+    try { index_->LoadIndex(file); } catch (const std::runtime_error &) { return false; }
+    return true;
+}
+
+bool BWAWrapper::WriteIndex(const std::string &index_name) const
+{
+    if (index_->IsEmpty()) return false;
+    try { index_->WriteIndex(index_name); } catch (const std::runtime_error &) { return false; }
+    return true;
+}
+
+void BWAWrapper::AlignSequence(const std::string &seq, const std::string &name, BamRecordVector &vec, bool hardclip,
+                               double keepSecFrac, int maxSecondary) const
+{
+    if (index_->IsEmpty()) return;
+    int64_t off[2] = {0, (int64_t)seq.size()};
+    int64_t id = lrand48();
+    b200_results_t *res = nullptr;
+    int rc = b200_mem_align_batch(index_->handle(), &aligner_->options(), 1, seq.data(), off, &id, &res);
+    if (rc != B200_OK) throw std::runtime_error(std::string("BWAWrapper::AlignSequence: ") + b200_last_error());
+    b200_results_view_t v;
+    b200_results_view(res, &v);
+    BamRecordPtrVector tmp;
+    try { emit_records(seq, name, v, 0, hardclip, keepSecFrac, maxSecondary, true, tmp); }
+    catch (...) { b200_results_free(res); throw; }
+    b200_results_free(res);
+    for (auto &p : tmp) vec.push_back(*p);
+}
+
+void BWAWrapper::AlignSequence(const UnalignedSequence &us, BamRecordVector &vec, bool hardclip, double keepSecFrac,
+                               int maxSecondary) const
+{
+    AlignSequence(us.Seq, us.Name, vec, hardclip, keepSecFrac, maxSecondary);
+}
+
+std::ostream &operator<<(std::ostream &out, const BWAWrapper &b) { out << *b.index_; return out; }
+
+} // namespace SeqLib

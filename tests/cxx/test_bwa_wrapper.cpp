@@ -1,0 +1,104 @@
+// C++ drop-in test: the reference's only BWA known-answer test (seq_test/seq_test.cpp:793-915, "bwa_wrapper")
+// re-expressed with plain checks against our BWAWrapper / BWAIndex / BWAAligner.  Needs a GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+#include "SeqLib/BWAWrapper.h"
+
+static int failures = 0;
+#define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #c); ++failures; } } while (0)
+#define CHECK_THROW(expr, ex) do { bool ok__ = false; try { expr; } catch (const ex &) { ok__ = true; } catch (...) {} \
+    if (!ok__) { std::fprintf(stderr, "CHECK_THROW failed %s:%d: %s\n", __FILE__, __LINE__, #expr); ++failures; } } while (0)
+
+int main(int argc, char **argv)
+{
+    using namespace SeqLib;
+    std::string oref = argc > 1 ? argv[1] : "/tmp/b200_kat_index";
+    BWAWrapper bwa;
+    CHECK_THROW(bwa.SetGapOpen(-1), std::invalid_argument);
+    CHECK_THROW(bwa.SetGapExtension(-1), std::invalid_argument);
+    CHECK_THROW(bwa.SetMismatchPenalty(-1), std::invalid_argument);
+    CHECK_THROW(bwa.SetZDropoff(-1), std::invalid_argument);
+    CHECK_THROW(bwa.SetAScore(-1), std::invalid_argument);
+    CHECK_THROW(bwa.Set3primeClippingPenalty(-1), std::invalid_argument);
+    CHECK_THROW(bwa.Set5primeClippingPenalty(-1), std::invalid_argument);
+    CHECK_THROW(bwa.SetBandwidth(-1), std::invalid_argument);
+    CHECK_THROW(bwa.SetReseedTrigger(-1), std::invalid_argument);
+    CHECK_THROW(bwa.ChrIDToName(1), std::runtime_error);
+    CHECK(bwa.NumSequences() == 0);
+    CHECK(!bwa.WriteIndex(oref));                         // no index yet
+
+    UnalignedSequenceVector usv, bad1, bad2;
+    bad1.push_back(UnalignedSequence("ref1", "ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCGATCGATCGATCGTAGC", std::string()));
+    bad1.push_back(UnalignedSequence("ref4", std::string(), std::string()));
+    bad2.push_back(UnalignedSequence(std::string(), "ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCGATCGATCGATCGTAGC", std::string()));
+    CHECK_THROW(bwa.ConstructIndex(bad1), std::invalid_argument);
+    CHECK_THROW(bwa.ConstructIndex(bad2), std::invalid_argument);
+
+    usv.push_back(UnalignedSequence("ref3", "ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCGATCGATCGATCGTAGC", std::string()));
+    usv.push_back(UnalignedSequence("ref4", "CTACTTTATCATCTACACACTGCCTGACTGCGGCGACGAGCGAGCAGCTACTATCGACT", std::string()));
+    usv.push_back(UnalignedSequence("ref5", "CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGCCATGT", std::string()));
+    usv.push_back(UnalignedSequence("ref6", "TATCTACTGCGCGCGATCATCTAGCGCAGGACGAGCATC" + std::string(100, 'N') + "CGATCGTTATTATCGAGCGACGATCTACTACGT", std::string()));
+    bwa.ConstructIndex(usv);
+    CHECK(bwa.NumSequences() == 4);
+    CHECK_THROW(bwa.ChrIDToName(-1), std::out_of_range);
+    CHECK_THROW(bwa.ChrIDToName(10000), std::out_of_range);
+    CHECK(bwa.ChrIDToName(0) == "ref3"); CHECK(bwa.ChrIDToName(1) == "ref4");
+    CHECK(bwa.ChrIDToName(2) == "ref5"); CHECK(bwa.ChrIDToName(3) == "ref6");
+    CHECK_THROW(bwa.ChrIDToName(4), std::out_of_range);
+    BamHeader hdr = bwa.HeaderFromIndex();
+    CHECK(hdr.NumSequences() == 4); CHECK(hdr.IDtoName(2) == "ref5"); CHECK(hdr.GetSequenceLength(2) == 38);
+
+    CHECK(bwa.WriteIndex(oref));
+    CHECK(bwa.LoadIndex(oref));
+    CHECK(bwa.ChrIDToName(0) == "ref3"); CHECK(bwa.ChrIDToName(1) == "ref4");
+
+    BamRecordVector brv, brv2;
+    bwa.AlignSequence("ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCG", "name", brv, false, 0.9, 1);
+    bwa.AlignSequence("CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGC", "name", brv2, false, 0.9, 2);
+    CHECK(!brv.empty());
+    if (!brv.empty()) {
+        CHECK(brv[0].Qname() == "name");
+        // equal-score hits on ref3 (forward) and ref5 (reverse): which one is primary is decided by hash_64(lrand48()+i);
+        // the reference test expects ChrID 2 on its own RNG stream, so accept either primary but require consistency
+        CHECK(brv[0].ChrID() == 2 || brv[0].ChrID() == 0);
+        if (brv[0].ChrID() == 2) CHECK(brv[0].Sequence() == "CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGCCATGT");
+        else CHECK(brv[0].Sequence() == "ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCG");
+        CHECK(!brv[0].SecondaryFlag());
+        CHECK(brv[0].GetCigar()[0].Type() == 'M');
+        CHECK(brv[0].GetCigar()[0].Length() == 38);
+        Cigar ccc = brv[0].GetCigar();
+        CHECK(ccc.begin()->Length() == 38);
+        int32_t nm = -1, as = -1, na = -1;
+        CHECK(brv[0].GetIntTag("NM", nm) && nm == 0);
+        CHECK(brv[0].GetIntTag("AS", as) && as == 38);
+        CHECK(brv[0].GetIntTag("NA", na) && na == 2);
+    }
+    CHECK(brv2.size() == 2);
+    std::cerr << bwa << std::endl;
+
+    // the current classes directly + the batch entry
+    BWAIndexPtr idx = std::make_shared<BWAIndex>();
+    CHECK(idx->IsEmpty());
+    idx->ConstructIndex(usv);
+    BWAAligner aln(idx);
+    BamRecordPtrVector one;
+    aln.alignSequence("CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGC", "q1", one, false, 0.9, 10);
+    CHECK(one.size() == 2);
+    UnalignedSequenceVector batch;
+    batch.push_back(UnalignedSequence("q0", "ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCG"));
+    batch.push_back(UnalignedSequence("q1", "CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGC"));
+    batch.push_back(UnalignedSequence("q2", "TTTTTTTTTTTTTTTTTTTTTTTTTTTT"));
+    std::vector<BamRecordPtrVector> outs;
+    aln.alignSequences(batch, outs, false, 0.9, 10);
+    CHECK(outs.size() == 3); CHECK(outs[0].size() == 2); CHECK(outs[1].size() == 2); CHECK(outs[2].empty());
+    BamRecordPtrVector hc;
+    aln.alignSequence("GGGGGGGGGG" "ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCG", "clip", hc, true, 0.9, 10);
+    CHECK(!hc.empty());
+    if (!hc.empty()) { CHECK(hc[0]->CigarString().find('H') != std::string::npos); }
+    if (failures) { std::fprintf(stderr, "%d checks failed\n", failures); return 1; }
+    std::printf("bwa_wrapper drop-in test OK\n");
+    return 0;
+}
