@@ -17,6 +17,7 @@
 #include <string>
 #include <algorithm>
 #include "engine.cuh"
+#include "extend_group.cuh"
 
 using namespace b200;
 
@@ -68,6 +69,37 @@ __global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
             else if (STAGE == 2) stage_extend(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
             else stage_finalize(A.ix, A.opt, A.caps, A.B, rid, scr, A.log_tab, A.n_log, ctr);
         }
+    }
+    flush_counters(ctr, A.ctrs);
+}
+
+// stage 2 with G lanes per read (see extend_group.cuh); a warp claims 32/G reads at a time
+template <int G>
+__global__ void __launch_bounds__(128) k_extend_group(const __grid_constant__ KArgs A)
+{
+    extern __shared__ __align__(16) u8 smem_raw[];
+    __shared__ i8 smat[32];
+    if (threadIdx.x < 25) smat[threadIdx.x] = A.opt.mat[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gib = threadIdx.x / G;
+    GroupCtx<G> g;
+    g.gl = threadIdx.x % G;
+    g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    u8 *smem = smem_raw + (size_t)gib * group_smem_bytes(A.caps.maxlen);
+    u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
+    CtrLocal ctr;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)(32 / G));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((i64)base >= A.n_work) break;
+        i64 w = (i64)base + lane / G;
+        if (w < A.n_work) {
+            i64 rid = A.order ? A.order[w] : w;
+            stage_extend_group<G>(g, A.ix, A.opt, A.caps, A.B, rid, scr, smem, smat, ctr);
+        }
+        __syncwarp();
     }
     flush_counters(ctr, A.ctrs);
 }
@@ -142,7 +174,7 @@ struct Engine {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8];
     // chunk buffers
-    DevBuf seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, small;
+    DevBuf seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, small;
     DevBuf p_intv, p_chain, p_seed, p_reg, p_hit, p_cigar, p_md;
     DevBuf nh, nc, nm, oh, oc, om, cubtmp, o_hit_off, o_hits, o_cigar, o_md;
     double pool_scale = 1.0;
@@ -204,7 +236,25 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
     CU_CHECK(cudaEventRecord(ev[0], E.st));
     launch_stage<0>(E, A, g[0]); CU_CHECK(cudaEventRecord(ev[1], E.st));
     launch_stage<1>(E, A, g[1]); CU_CHECK(cudaEventRecord(ev[2], E.st));
-    launch_stage<2>(E, A, g[2]); CU_CHECK(cudaEventRecord(ev[3], E.st));
+    {
+        const int G = 8;
+        size_t smem = (size_t)(128 / G) * group_smem_bytes(A.caps.maxlen);
+        static int group_ok = getenv("B200_SCALAR_EXTEND") ? 0 : 1;
+        if (!spill && group_ok && smem <= 200 * 1024) {
+            int per = 0;
+            CU_CHECK(cudaFuncSetAttribute(k_extend_group<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_group<G>, 128, smem));
+            if (per < 1) per = 1;
+            int grid = E.sms * per;
+            size_t gstride = (extend_group_scratch_bytes(A.caps) + 63) & ~(size_t)63;
+            E.group_scratch.reserve(gstride * (size_t)grid * (128 / G));
+            KArgs A2 = A; A2.scratch = E.group_scratch.as<u8>(); A2.scratch_stride = gstride;
+            CU_CHECK(cudaMemsetAsync(A2.work_ctr, 0, 8, E.st));
+            k_extend_group<G><<<grid, 128, smem, E.st>>>(A2);
+            CU_CHECK(cudaGetLastError());
+        } else launch_stage<2>(E, A, g[2]);
+    }
+    CU_CHECK(cudaEventRecord(ev[3], E.st));
     launch_stage<3>(E, A, g[3]); CU_CHECK(cudaEventRecord(ev[4], E.st));
     E.stats.n_launches += 4;
     if (ms4) {

@@ -2,6 +2,7 @@
 #include <vector>
 #include <cstring>
 #include "engine.cuh"
+#include "extend_group.cuh"
 
 using namespace b200;
 
@@ -39,6 +40,54 @@ __global__ void __launch_bounds__(128) k_ext_scalar(const __grid_constant__ ExtA
     if ((threadIdx.x & 31) == 0) atomicAdd(A.cells, x);
 }
 
+
+// v2: G lanes per job (extend2_group), per-group state in shared memory
+template <int G>
+__global__ void __launch_bounds__(128) k_ext_group(const __grid_constant__ ExtArgs A, int maxq)
+{
+    extern __shared__ __align__(16) u8 smem_raw[];
+    __shared__ i8 smat[32];
+    if (threadIdx.x < 25) smat[threadIdx.x] = A.mat[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, gib = threadIdx.x / G;
+    GroupCtx<G> g; g.gl = threadIdx.x % G;
+    g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    u8 *smem = smem_raw + (size_t)gib * group_smem_bytes(maxq);
+    int *H = (int *)smem, *E = H + (maxq + 2);
+    u8 *q = (u8 *)(E + (maxq + 2));
+    CellCtr c; c.sw_cells = 0; c.n_ext = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.work, (unsigned long long)(32 / G));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((i64)base >= A.n) break;
+        i64 i = (i64)base + lane / G;
+        if (i < A.n) {
+            const b200_ext_job_t j = A.jobs[i];
+            for (int k = g.gl; k < j.qlen; k += G) q[k] = A.qp[j.q_off + k];
+            g.sync();
+            BytesSeq qs; qs.p = q; qs.step = 1;
+            BytesSeq ts; ts.p = A.tp + j.t_off; ts.step = 1;
+            ExtResult r = extend2_group(g, j.qlen, qs, j.tlen, ts, smat, A.o_del, A.e_del, A.o_ins, A.e_ins, j.w, j.end_bonus, j.zdrop, j.h0, H, E, c);
+            if (g.gl == 0) { b200_ext_out_t o; o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off; A.out[i] = o; }
+        }
+        __syncwarp();
+    }
+    unsigned long long x = c.sw_cells;
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) atomicAdd(A.cells, x);
+}
+
+template <int G>
+static void launch_ext_group(const ExtArgs &A, int maxq, int sms)
+{
+    size_t smem = (size_t)(128 / G) * group_smem_bytes(maxq);
+    CU_CHECK(cudaFuncSetAttribute(k_ext_group<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per = 1;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ext_group<G>, 128, smem));
+    k_ext_group<G><<<sms * (per < 1 ? 1 : per), 128, smem>>>(A, maxq);
+}
+
 } // namespace b200
 
 extern "C" int b200_ksw_extend2_batch(int64_t n, const b200_ext_job_t *jobs, const uint8_t *qpool, int64_t qpool_len,
@@ -69,7 +118,13 @@ extern "C" int b200_ksw_extend2_batch(int64_t n, const b200_ext_job_t *jobs, con
         A.eh = deh.as<EH>(); A.eh_stride = stride; A.cells = dsmall.as<unsigned long long>(); A.work = dsmall.as<unsigned long long>() + 1;
         cudaEvent_t e0, e1; CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1));
         CU_CHECK(cudaEventRecord(e0));
-        k_ext_scalar<<<grid, 128>>>(A);
+        int G = getenv("B200_KSW_G") ? atoi(getenv("B200_KSW_G")) : 16;
+        size_t need = (size_t)(128 / (G > 0 ? G : 1)) * group_smem_bytes(maxq);
+        if (G == 0 || need > 200 * 1024) k_ext_scalar<<<grid, 128>>>(A);
+        else if (G == 4) launch_ext_group<4>(A, maxq, sms);
+        else if (G == 8) launch_ext_group<8>(A, maxq, sms);
+        else if (G == 32) launch_ext_group<32>(A, maxq, sms);
+        else launch_ext_group<16>(A, maxq, sms);
         CU_CHECK(cudaEventRecord(e1));
         CU_CHECK(cudaEventSynchronize(e1));
         CU_CHECK(cudaGetLastError());

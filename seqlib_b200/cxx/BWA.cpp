@@ -176,7 +176,11 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
             int j = 0;
             for (int p = sl - 1; p >= 0; --p, ++j) {
                 uint8_t x = 15;
-                switch (clipped[p]) { case 'A': x = 8; break; case 'C': x = 2; break; case 'G': x = 4; break; case 'T': x = 1; break; }
+                // Q11: src/BWAAligner.cpp:213-218 maps A->T and T->A but leaves C and G as they are on the reverse strand;
+                // BWAAligner mirrors that, the legacy BWAWrapper facade writes the true reverse complement (what
+                // seq_test/seq_test.cpp:904 asserts).
+                if (primary_first) switch (clipped[p]) { case 'A': x = 8; break; case 'C': x = 4; break; case 'G': x = 2; break; case 'T': x = 1; break; }
+                else switch (clipped[p]) { case 'A': x = 8; break; case 'C': x = 2; break; case 'G': x = 4; break; case 'T': x = 1; break; }
                 sb[j >> 1] = (uint8_t)((sb[j >> 1] & ~(0xF << ((~j & 1) << 2))) | x << ((~j & 1) << 2));
             }
         } else {

@@ -89,3 +89,38 @@ def c3_tuples_fast(n, seed=0x5EED0003):
     jobs["zdrop"] = 100
     jobs["h0"] = rng.integers(19, 151, size=n)
     return jobs, q.reshape(-1), tp.reshape(-1)
+
+
+def mixed_tuples(n, seed=11):
+    """Random ksw_extend2 jobs with varied shapes: qlen 1..139, related / unrelated targets, Ns, w in {5,30,100,200}, zdrop in {0,20,100}."""
+    rng = np.random.default_rng(seed)
+    ql = rng.integers(1, 140, n)
+    tl = np.minimum(ql + rng.integers(0, 200, n), 400)
+    qo = np.concatenate([[0], np.cumsum(ql)[:-1]])
+    to = np.concatenate([[0], np.cumsum(tl)[:-1]])
+    tp = rng.integers(0, 4, int(tl.sum()), dtype=np.uint8)
+    qp = np.zeros(int(ql.sum()), dtype=np.uint8)
+    for i in range(n):
+        t = tp[to[i]:to[i] + tl[i]]
+        q = t[:ql[i]].copy() if ql[i] <= tl[i] else np.resize(t, ql[i])
+        if i % 3 == 0:
+            q = rng.integers(0, 4, ql[i], dtype=np.uint8)
+        else:
+            m = rng.random(ql[i]) < 0.05
+            q[m] = (q[m] + 1) & 3
+            if i % 5 == 0 and ql[i] > 20:
+                p = int(rng.integers(5, ql[i] - 5))
+                q[p:] = np.roll(q[p:], int(rng.integers(1, 6)))
+            if i % 7 == 0:
+                q[rng.integers(0, ql[i])] = 4
+        qp[qo[i]:qo[i] + ql[i]] = q
+    jobs = np.zeros(n, dtype=EXT_JOB_DTYPE)
+    jobs["qlen"] = ql
+    jobs["tlen"] = tl
+    jobs["q_off"] = qo
+    jobs["t_off"] = to
+    jobs["w"] = rng.choice([100, 200, 5, 30], n)
+    jobs["end_bonus"] = 5
+    jobs["zdrop"] = rng.choice([100, 0, 20], n)
+    jobs["h0"] = rng.integers(1, 160, n)
+    return jobs, qp, tp

@@ -113,14 +113,26 @@ def test_gpu_builder_reproduces_tiny_index(capi):
     assert np.array_equal(b["sa"], a["sa"])
 
 
-def test_ksw_extend2_batch(capi):
+@pytest.mark.parametrize("G", [0, 4, 8, 16, 32])
+def test_ksw_extend2_batch(capi, monkeypatch, G):
+    """ksw_extend2 tuples: scalar kernel (G=0) and the lane-cooperative kernels vs the reference's outputs."""
+    monkeypatch.setenv("B200_KSW_G", str(G))
     z = np.load(goldenlib.path("ksw_c3.npz"))
     jobs, qp, tp = cases.c3_tuples(4000)
     opt = capi.default_opt()
-    out, cells, ms = capi.ksw_extend2_batch(jobs, qp, tp, np.array(list(opt.mat), dtype=np.int8))
+    mat = np.array(list(opt.mat), dtype=np.int8)
+    out, cells, ms = capi.ksw_extend2_batch(jobs, qp, tp, mat)
     for f in out.dtype.names:
         assert np.array_equal(out[f], z["out"][f]), f
     assert cells > 0
+    # a harsher mix (short/unrelated/N-containing queries, narrow and wide bands, z-drop on/off) against the live reference
+    from oracle import pyref
+    if pyref.have_ref():
+        jobs2, qp2, tp2 = cases.mixed_tuples(30000)
+        exp, _ = pyref.ksw_extend2_batch(jobs2, qp2, tp2, mat, n_threads=8)
+        got, cells2, _ = capi.ksw_extend2_batch(jobs2, qp2, tp2, mat)
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], exp[f]), f
 
 
 def test_against_live_reference_with_indels(capi):
