@@ -16,13 +16,16 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <time.h>
 #include "engine.cuh"
 #include "extend_group.cuh"
+#include "finalize_group.cuh"
 
 using namespace b200;
 
 namespace b200 {
 
+static double wall_now();
 struct DevCounters { unsigned long long v[8]; };   // occ_blocks, sa_reads, ref_bytes, sw_cells, n_ext, n_global, n_ovf, pool_fail
 
 __device__ __forceinline__ void flush_counters(const CtrLocal &c, DevCounters *g)
@@ -104,6 +107,35 @@ __global__ void __launch_bounds__(128) k_extend_group(const __grid_constant__ KA
     flush_counters(ctr, A.ctrs);
 }
 
+// gapped CIGARs: G lanes per queued hit (see finalize_group.cuh)
+template <int G>
+__global__ void __launch_bounds__(128) k_finalize_dp(const __grid_constant__ KArgs A)
+{
+    extern __shared__ __align__(16) u8 smem_raw[];
+    __shared__ i8 smat[32];
+    if (threadIdx.x < 25) smat[threadIdx.x] = A.opt.mat[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gib = threadIdx.x / G;
+    GroupCtx<G> g;
+    g.gl = threadIdx.x % G;
+    g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    u8 *smem = smem_raw + (size_t)gib * findp_smem_bytes(A.caps.maxlen);
+    u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
+    const i64 n_jobs = (i64)*A.B.n_dp_jobs < A.B.cap_dp_jobs ? (i64)*A.B.n_dp_jobs : A.B.cap_dp_jobs;
+    CtrLocal ctr;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)(32 / G));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((i64)base >= n_jobs) break;
+        i64 w = (i64)base + lane / G;
+        if (w < n_jobs) finalize_dp_job<G>(g, A.ix, A.opt, A.caps, A.B, A.B.dp_jobs[w], scr, smem, smat, ctr);
+        __syncwarp();
+    }
+    flush_counters(ctr, A.ctrs);
+}
+
 // ASCII -> nt4 codes (nst_nt4_table, bwa/bntseq.c:46-63; mem_align1_core keeps codes < 4 as they are, bwa/bwamem.c:1087-1088)
 __global__ void k_encode(const u8 *__restrict__ in, u8 *__restrict__ out, i64 n)
 {
@@ -174,7 +206,7 @@ struct Engine {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8];
     // chunk buffers
-    DevBuf seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, small;
+    DevBuf seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, dp_scratch, dp_jobs, small;
     DevBuf p_intv, p_chain, p_seed, p_reg, p_hit, p_cigar, p_md;
     DevBuf nh, nc, nm, oh, oc, om, cubtmp, o_hit_off, o_hits, o_cigar, o_md;
     double pool_scale = 1.0;
@@ -255,7 +287,24 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
         } else launch_stage<2>(E, A, g[2]);
     }
     CU_CHECK(cudaEventRecord(ev[3], E.st));
-    launch_stage<3>(E, A, g[3]); CU_CHECK(cudaEventRecord(ev[4], E.st));
+    launch_stage<3>(E, A, g[3]);
+    if (A.B.dp_jobs) {
+        const int G = 8;
+        size_t smem = (size_t)(128 / G) * findp_smem_bytes(A.caps.maxlen);
+        int per = 0;
+        CU_CHECK(cudaFuncSetAttribute(k_finalize_dp<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_finalize_dp<G>, 128, smem));
+        if (per < 1) per = 1;
+        int grid = E.sms * per;
+        size_t gstride = (findp_scratch_bytes(A.caps) + 63) & ~(size_t)63;
+        E.dp_scratch.reserve(gstride * (size_t)grid * (128 / G));
+        KArgs A3 = A; A3.scratch = E.dp_scratch.as<u8>(); A3.scratch_stride = gstride;
+        CU_CHECK(cudaMemsetAsync(A3.work_ctr, 0, 8, E.st));
+        k_finalize_dp<G><<<grid, 128, smem, E.st>>>(A3);
+        CU_CHECK(cudaGetLastError());
+        E.stats.n_launches += 1;
+    }
+    CU_CHECK(cudaEventRecord(ev[4], E.st));
     E.stats.n_launches += 4;
     if (ms4) {
         CU_CHECK(cudaEventSynchronize(ev[4]));
@@ -292,9 +341,20 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         for (int k = 0; k < N_POOLS; ++k) P.cap[k] = cap[k];
         P.used = d_small + 8;
         A.order = nullptr; A.n_work = n; A.work_ctr = d_small; A.ctrs = (DevCounters *)(d_small + 16);
+        {   // queue of hits that need a banded global alignment (drained by k_finalize_dp)
+            size_t smem = (size_t)(128 / 8) * findp_smem_bytes(maxlen);
+            static int dp_ok = getenv("B200_SCALAR_FINALIZE") ? 0 : 1;
+            if (dp_ok && smem <= 200 * 1024) {
+                E.dp_jobs.reserve((size_t)cap[POOL_HIT] * sizeof(DpJob));
+                A.B.dp_jobs = E.dp_jobs.as<DpJob>(); A.B.n_dp_jobs = d_small + 2; A.B.cap_dp_jobs = cap[POOL_HIT];
+            }
+        }
         A.log_tab = d_log; A.n_log = n_log;
         float ms4[4] = {0, 0, 0, 0};
+        static int trace = getenv("B200_TRACE") ? 1 : 0;
+        double tw0 = wall_now();
         run_stages(E, A, false, ms4);
+        double tw1 = wall_now();
         // spill pass for reads that overflowed their scratch slot
         const u32 SCR = OVF_INTV | OVF_SEED | OVF_CHAIN | OVF_REG | OVF_OUT | OVF_SCRATCH;
         k_list_ovf<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n, SCR, E.list.as<i32>(), d_small + 1);
@@ -305,10 +365,11 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         if (n_sp) {
             E.stats.n_overflow += (u64)n_sp;
             k_clear_list<<<(unsigned)((n_sp + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), E.list.as<i32>(), n_sp);
-            KArgs S = A; S.caps = big; S.order = E.list.as<i32>(); S.n_work = n_sp;
+            KArgs S = A; S.caps = big; S.order = E.list.as<i32>(); S.n_work = n_sp; S.B.dp_jobs = nullptr;
             run_stages(E, S, true, ms4);
             E.stats.n_launches += 1;
         }
+        double tw2 = wall_now();
         // any read still flagged?  pool exhaustion => retry the chunk with larger pools; anything else is a hard limit
         CU_CHECK(cudaMemsetAsync(d_small + 1, 0, 8, E.st));
         k_list_ovf<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n, 0xffffffffu, E.list.as<i32>(), d_small + 1);
@@ -350,10 +411,14 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
                                                                     E.o_hit_off.as<i64>(), E.o_hits.as<b200_hit_t>(), E.o_cigar.as<u32>(), E.o_md.as<char>());
         CU_CHECK(cudaGetLastError());
         E.stats.n_launches += 5;
+        if (trace) { CU_CHECK(cudaStreamSynchronize(E.st)); double tw3 = wall_now();
+            fprintf(stderr, "[b200 trace] chunk n=%lld stages %.1f ms, spill(%lld reads) %.1f ms, compact %.1f ms; stage ms %.1f %.1f %.1f %.1f\n", (long long)n, 1e3 * (tw1 - tw0), (long long)n_sp, 1e3 * (tw2 - tw1), 1e3 * (tw3 - tw2), ms4[0], ms4[1], ms4[2], ms4[3]); }
         return out;
     }
     throw std::runtime_error("pool growth did not converge");
 }
+
+static double wall_now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 static i64 chunk_reads()
 {
@@ -434,21 +499,25 @@ int b200_batch_run(b200_batch_t *b, int *n_launches)
         Engine &E = engine();
         memset(&E.stats, 0, sizeof(E.stats));
         CU_CHECK(cudaEventRecord(E.ev[6], E.st));
-        for (auto c : b->chunks) delete c;
-        b->chunks.clear();
         i64 CH = chunk_reads(), bh = 0, bc = 0, bm = 0;
-        for (i64 r0 = 0; r0 < b->n; r0 += CH) {
+        size_t ci = 0;
+        for (i64 r0 = 0; r0 < b->n; r0 += CH, ++ci) {
             i64 n = std::min(CH, b->n - r0);
+            b200_batch::Chunk *c = ci < b->chunks.size() ? b->chunks[ci] : nullptr;
+            if (c) {    // hand the previous run's result buffers back to the engine so they are reused, not re-allocated
+                std::swap(c->hit_off.p, E.o_hit_off.p); std::swap(c->hit_off.cap, E.o_hit_off.cap);
+                std::swap(c->hits.p, E.o_hits.p); std::swap(c->hits.cap, E.o_hits.cap);
+                std::swap(c->cigar.p, E.o_cigar.p); std::swap(c->cigar.cap, E.o_cigar.cap);
+                std::swap(c->md.p, E.o_md.p); std::swap(c->md.cap, E.o_md.cap);
+            } else { c = new b200_batch::Chunk; b->chunks.push_back(c); }
             ChunkOut o = process_chunk(E, b->idx, b->opt, b->maxlen, b->d_seq.as<u8>(), b->d_off.as<i64>() + r0, b->d_ids.as<i64>() + r0, n, bh, bc, bm,
                                        b->d_log.as<double>(), b->n_log);
-            b200_batch::Chunk *c = new b200_batch::Chunk;
             c->r0 = r0; c->n = n; c->out = o;
             // keep the compact result on the device (swap buffers with the engine's output buffers)
             std::swap(c->hit_off.p, E.o_hit_off.p); std::swap(c->hit_off.cap, E.o_hit_off.cap);
             std::swap(c->hits.p, E.o_hits.p); std::swap(c->hits.cap, E.o_hits.cap);
             std::swap(c->cigar.p, E.o_cigar.p); std::swap(c->cigar.cap, E.o_cigar.cap);
             std::swap(c->md.p, E.o_md.p); std::swap(c->md.cap, E.o_md.cap);
-            b->chunks.push_back(c);
             bh += o.n_hits; bc += o.n_cigar; bm += o.n_md;
         }
         CU_CHECK(cudaEventRecord(E.ev[7], E.st));

@@ -319,37 +319,33 @@ struct AlnOut {      // mem_aln_t essentials
     bool overflow, need_host;
 };
 
-// cigar: capacity cap_cigar words (incl. room for two clips); md: cap_md bytes.
-template <class Ctr>
-HD AlnOut reg2aln(const DevIndex &ix, const Opt &opt, int l_query, const u8 *query, const Reg *ar,
-                  FinScratch &fs, u32 *cigar, int cap_cigar, char *md, int cap_md, Ctr &ctr)
+// first part of mem_reg2aln (bwa/bwamem.c:1136-1144): MAPQ, secondary flag, inferred band width
+struct AlnPlan { int mapq, flag, w2; bool need_host; };
+
+HD AlnPlan reg2aln_plan(const Opt &opt, const Reg *ar, const FinScratch &fs)
 {
-    AlnOut a;
-    a.pos = -1; a.rid = -1; a.flag = 0; a.is_rev = 0; a.mapq = 0; a.NM = 0; a.n_cigar = 0; a.md_len = 0; a.score = 0; a.sub = 0;
-    a.overflow = false; a.need_host = false;
-    if (ar->rb < 0 || ar->re < 0) { a.flag |= 0x4; return a; }
-    int qb = ar->qb, qe = ar->qe, i, w2, tmp, score = 0, last_sc = -(1 << 30), is_rev;
-    i64 rb = ar->rb, re = ar->re, pos;
-    a.mapq = ar->secondary < 0 ? approx_mapq_se(opt, ar, fs, &a.need_host) : 0;
-    if (ar->secondary >= 0) a.flag |= 0x100;
+    AlnPlan p; p.need_host = false; p.flag = 0;
+    int qb = ar->qb, qe = ar->qe, tmp, w2;
+    i64 rb = ar->rb, re = ar->re;
+    p.mapq = ar->secondary < 0 ? approx_mapq_se(opt, ar, fs, &p.need_host) : 0;
+    if (ar->secondary >= 0) p.flag |= 0x100;
     tmp = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_del, opt.e_del);
     w2 = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_ins, opt.e_ins);
     w2 = w2 > tmp ? w2 : tmp;
     if (w2 > opt.w) w2 = w2 < ar->w ? w2 : ar->w;
-    i = 0;
-    GenCigarOut g;
-    g.n_cigar = 0; g.NM = -1; g.md_len = 0; g.ok = false;
-    do {
-        w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
-        g = gen_cigar2(ix, opt, w2, qe - qb, query + qb, rb, re, fs, cigar, cap_cigar - 2, md, cap_md, ctr);
-        if (g.overflow) { a.overflow = true; return a; }
-        score = g.score;
-        if (score == last_sc || w2 == opt.w << 2) break;
-        last_sc = score;
-        w2 <<= 1;
-    } while (++i < 3 && score < ar->truesc - opt.a);
-    a.NM = g.NM; a.n_cigar = g.n_cigar; a.md_len = g.md_len;
-    pos = depos(ix, rb < ix.l_pac ? rb : re - 1, &is_rev);
+    p.w2 = w2;
+    return p;
+}
+
+// true when every bwa_gen_cigar2 call of the retry loop takes the no-DP branch (bwa/bwa.c:169-178): w2 = 0 stays 0 when doubled
+HD bool reg2aln_is_ungapped(const Reg *ar, int w2) { return w2 == 0 && (i64)(ar->qe - ar->qb) == ar->re - ar->rb; }
+
+// last part of mem_reg2aln (bwa/bwamem.c:1157-1187): strand/pos, squeeze a leading/trailing deletion, add clips
+HD void reg2aln_finish(const DevIndex &ix, int l_query, const Reg *ar, u32 *cigar, AlnOut &a)
+{
+    int qb = ar->qb, qe = ar->qe, i, is_rev;
+    i64 rb = ar->rb, re = ar->re;
+    i64 pos = depos(ix, rb < ix.l_pac ? rb : re - 1, &is_rev);
     a.is_rev = is_rev;
     if (a.n_cigar > 0) {
         if ((cigar[0] & 0xf) == 2) {
@@ -371,6 +367,34 @@ HD AlnOut reg2aln(const DevIndex &ix, const Opt &opt, int l_query, const u8 *que
     a.rid = pos2rid(ix, pos);
     a.pos = pos - ix.contig_off[a.rid];
     a.score = ar->score; a.sub = ar->sub > ar->csub ? ar->sub : ar->csub;
+}
+
+// cigar: capacity cap_cigar words (incl. room for two clips); md: cap_md bytes.
+template <class Ctr>
+HD AlnOut reg2aln(const DevIndex &ix, const Opt &opt, int l_query, const u8 *query, const Reg *ar,
+                  FinScratch &fs, u32 *cigar, int cap_cigar, char *md, int cap_md, Ctr &ctr)
+{
+    AlnOut a;
+    a.pos = -1; a.rid = -1; a.flag = 0; a.is_rev = 0; a.mapq = 0; a.NM = 0; a.n_cigar = 0; a.md_len = 0; a.score = 0; a.sub = 0;
+    a.overflow = false; a.need_host = false;
+    if (ar->rb < 0 || ar->re < 0) { a.flag |= 0x4; return a; }
+    AlnPlan pl = reg2aln_plan(opt, ar, fs);
+    a.mapq = pl.mapq; a.flag = pl.flag; a.need_host = pl.need_host;
+    int qb = ar->qb, qe = ar->qe, i = 0, w2 = pl.w2, score = 0, last_sc = -(1 << 30);
+    i64 rb = ar->rb, re = ar->re;
+    GenCigarOut g;
+    g.n_cigar = 0; g.NM = -1; g.md_len = 0; g.ok = false;
+    do {
+        w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
+        g = gen_cigar2(ix, opt, w2, qe - qb, query + qb, rb, re, fs, cigar, cap_cigar - 2, md, cap_md, ctr);
+        if (g.overflow) { a.overflow = true; return a; }
+        score = g.score;
+        if (score == last_sc || w2 == opt.w << 2) break;
+        last_sc = score;
+        w2 <<= 1;
+    } while (++i < 3 && score < ar->truesc - opt.a);
+    a.NM = g.NM; a.n_cigar = g.n_cigar; a.md_len = g.md_len;
+    reg2aln_finish(ix, l_query, ar, cigar, a);
     return a;
 }
 

@@ -67,25 +67,26 @@ HD void occ4_pair(const DevIndex &ix, u64 k, u64 l, u64 ck[4], u64 cl[4], Ctr &c
     }
 }
 
-// bwt_extend (bwa/bwt.c:262-275): all four children of a bi-interval.
+// bwt_extend (bwa/bwt.c:262-275) restricted to the one child the callers use: ok[c].
+// All four Occ differences are still needed (the reverse-side start of child c skips the children > c);
+// everything stays in registers -- no array is indexed by the run-time base c.
 template <class Ctr>
-HD void extend4(const DevIndex &ix, const Intv &ik, Intv ok[4], int is_back, Ctr &ctr)
+HD void extend_c(const DevIndex &ix, const Intv &ik, int c, int is_back, Intv &oc, Ctr &ctr)
 {
     u64 tk[4], tl[4];
     u64 a = is_back ? ik.x0 : ik.x1;      // x[!is_back]
     u64 o = is_back ? ik.x1 : ik.x0;      // x[is_back]
     occ4_pair(ix, a - 1, a - 1 + ik.x2, tk, tl, ctr);
-    u64 na[4], ns[4], no[4];
-    for (int i = 0; i < 4; ++i) { na[i] = ix.L2[i] + 1 + tk[i]; ns[i] = tl[i] - tk[i]; }
-    no[3] = o + (a <= ix.primary && a + ik.x2 - 1 >= ix.primary);
-    no[2] = no[3] + ns[3];
-    no[1] = no[2] + ns[2];
-    no[0] = no[1] + ns[1];
-    for (int i = 0; i < 4; ++i) {
-        ok[i].x2 = ns[i];
-        if (is_back) { ok[i].x0 = na[i]; ok[i].x1 = no[i]; }
-        else { ok[i].x1 = na[i]; ok[i].x0 = no[i]; }
-    }
+    u64 s0 = tl[0] - tk[0], s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
+    u64 no3 = o + (a <= ix.primary && a + ik.x2 - 1 >= ix.primary);
+    u64 no2 = no3 + s3, no1 = no2 + s2, no0 = no1 + s1;
+    u64 tkc = c == 0 ? tk[0] : c == 1 ? tk[1] : c == 2 ? tk[2] : tk[3];
+    u64 sc = c == 0 ? s0 : c == 1 ? s1 : c == 2 ? s2 : s3;
+    u64 noc = c == 0 ? no0 : c == 1 ? no1 : c == 2 ? no2 : no3;
+    u64 nac = ix.L2[c] + 1 + tkc;
+    oc.x2 = sc;
+    if (is_back) { oc.x0 = nac; oc.x1 = noc; }
+    else { oc.x1 = nac; oc.x0 = noc; }
 }
 
 // bwt_set_intv (bwa/bwt.h:82)

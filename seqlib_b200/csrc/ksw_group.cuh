@@ -131,4 +131,86 @@ __device__ ExtResult extend2_group(const GroupCtx<G> &g, int qlen, const QSeq &q
     return R;
 }
 
+// Lane-cooperative ksw_global2 (bwa/ksw.c:540-642): same chunked rows, F by an exact max-plus scan (no zero clamp here:
+// F(i,j+1) = max(F(i,j) - e_ins, M(i,j) - oe_ins) with F(i,beg) = MINUS_INF), direction bytes z[i*n_col + j-beg] written by
+// the lane that owns the column.  z == NULL: score only.  Proven equal to the scalar loop (score and every direction
+// byte) by tests/hostsim/group_emul.cpp.  Returns eh[qlen].h.
+template <int G, class QSeq, class TSeq>
+__device__ int global2_group(const GroupCtx<G> &g, int qlen, const QSeq &query, int tlen, const TSeq &target, const i8 *smat,
+                             int o_del, int e_del, int o_ins, int e_ins, int w, int *H, int *E, u8 *z, unsigned long long *cells_out)
+{
+    const int MINF = KSW_MINUS_INF, SENT = -2147483000;
+    const int gl = g.gl;
+    int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    for (int j = gl; j <= qlen; j += G) {
+        if (j == 0) { H[0] = 0; E[0] = MINF; }
+        else if (j <= w) { H[j] = -(o_ins + e_ins * j); E[j] = MINF; }
+        else { H[j] = MINF; E[j] = MINF; }
+    }
+    unsigned long long cells = 0;
+    g.sync();
+    for (int i = 0; i < tlen; ++i) {
+        const i8 *qrow = smat + target[i] * 5;
+        int beg = i > w ? i - w : 0, end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        int h1_init = beg == 0 ? -(o_del + e_del * (i + 1)) : MINF;
+        const int W = end - beg;
+        const int C = W > 0 ? (W + G - 1) / G : 0;
+        cells += W > 0 ? W : 0;
+        int j0 = beg + gl * C, j1 = j0 + C < end ? j0 + C : end;
+        if (j0 > end) j0 = j1 = end;
+        int L = SENT, n = 0;
+        int saved = j0 < j1 ? H[j0] : 0;
+        for (int j = j0; j < j1; ++j) {
+            int m = H[j] + qrow[query[j]];
+            int t = m - oe_ins;
+            L = n == 0 ? t : (L - e_ins > t ? L - e_ins : t);
+            ++n;
+        }
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            int L2 = g.up(L, d), n2 = g.up(n, d);
+            if (gl >= d) {
+                if (n == 0) { L = L2; n = n2; }
+                else if (n2 != 0) { int c = L2 - n * e_ins; L = c > L ? c : L; n += n2; }
+            }
+        }
+        int Lp = g.up(L, 1), np = g.up(n, 1);
+        int fin;
+        if (gl == 0 || np == 0) fin = MINF;
+        else { int c = MINF - np * e_ins; fin = c > Lp ? c : Lp; }
+        g.sync();
+        int f = fin, hp = saved, hl = 0;
+        if (gl == 0) H[beg] = h1_init;
+        u8 *zi = z ? z + (i64)i * n_col - beg : (u8 *)0;
+        for (int j = j0; j < j1; ++j) {
+            int hp_next = j + 1 < j1 ? H[j + 1] : 0;
+            int m = hp + qrow[query[j]], e = E[j];
+            int d = m >= e ? 0 : 1;
+            int h = m >= e ? m : e;
+            d = h >= f ? d : 2;
+            h = h >= f ? h : f;
+            int t = m - oe_del;
+            e -= e_del;
+            d |= e > t ? 1 << 2 : 0;
+            e = e > t ? e : t;
+            E[j] = e;
+            t = m - oe_ins;
+            f -= e_ins;
+            d |= f > t ? 2 << 4 : 0;
+            f = f > t ? f : t;
+            if (zi) zi[j] = (u8)d;
+            H[j + 1] = h;
+            hl = h; hp = hp_next;
+        }
+        (void)hl;
+        if (gl == 0) { if (W <= 0) H[end] = h1_init; E[end] = MINF; }
+        g.sync();
+    }
+    int score = H[qlen];
+    g.sync();
+    if (cells_out && gl == 0) *cells_out += cells;
+    return score;
+}
+
 } // namespace b200

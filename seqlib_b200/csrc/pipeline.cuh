@@ -50,7 +50,10 @@ struct ReadRec {
     float frac_rep;
 };
 
+struct DpJob { i64 hit; i32 rid, w2; };   // a hit whose CIGAR needs a banded global alignment
+
 struct Batch {
+    DpJob *dp_jobs; unsigned long long *n_dp_jobs; i64 cap_dp_jobs;   // NULL: resolve every hit inline
     i64 n_reads;
     const u8 *seq;           // nt4 codes, concatenated
     const i64 *seq_off;      // n_reads + 1
@@ -204,6 +207,29 @@ HD void stage_finalize(const DevIndex &ix, const Opt &opt, const Caps &caps, con
     b200_hit_t *H = B.pool.hits + hoff;
     int tot_c = 0, tot_m = 0;
     for (int i = 0; i < n; ++i) {
+        b200_hit_t &h = H[i];
+        const Reg &r = a[i];
+        h.rb = r.rb; h.re = r.re; h.hash = r.hash; h.qb = r.qb; h.qe = r.qe; h.rid = r.rid;
+        h.score = r.score; h.truesc = r.truesc; h.sub = r.sub; h.alt_sc = r.alt_sc; h.csub = r.csub; h.sub_n = r.sub_n;
+        h.w = r.w; h.seedcov = r.seedcov; h.secondary = r.secondary; h.secondary_all = r.secondary_all;
+        h.seedlen0 = r.seedlen0; h.n_comp = r.n_comp; h.is_alt = r.is_alt; h.frac_rep = r.frac_rep;
+        if (B.dp_jobs && r.rb >= 0 && r.re >= 0) {
+            AlnPlan pl = reg2aln_plan(opt, &r, fs);
+            if (pl.need_host) { B.ovf[rid] |= OVF_OUT; return; }
+            if (!reg2aln_is_ungapped(&r, pl.w2)) {             // queue for k_finalize_dp
+#if defined(__CUDA_ARCH__)
+                i64 slot = (i64)atomicAdd(B.n_dp_jobs, 1ull);
+#else
+                i64 slot = (i64)(*B.n_dp_jobs)++;
+#endif
+                if (slot >= B.cap_dp_jobs) { B.ovf[rid] |= OVF_POOL; return; }
+                DpJob j; j.hit = hoff + i; j.rid = (i32)rid; j.w2 = pl.w2;
+                B.dp_jobs[slot] = j;
+                h.flag = pl.flag; h.mapq = pl.mapq; h.pos = -1; h.is_rev = 0; h.NM = 0; h.aln_sub = 0; h.n_cigar = 0; h.md_len = 0;
+                h.cigar_off = 0; h.md_off = 0;
+                continue;
+            }
+        }
         AlnOut o = reg2aln(ix, opt, len, seq, &a[i], fs, cg, caps.cigar, md, caps.md, ctr);
         if (o.overflow || o.need_host) { B.ovf[rid] |= OVF_OUT; return; }
         i64 co = pool_alloc(B.pool, POOL_CIGAR, o.n_cigar), mo = pool_alloc(B.pool, POOL_MD, o.md_len + 1);
@@ -212,12 +238,7 @@ HD void stage_finalize(const DevIndex &ix, const Opt &opt, const Caps &caps, con
         for (int k = 0; k < o.md_len; ++k) B.pool.md[mo + k] = md[k];
         B.pool.md[mo + o.md_len] = 0;
         tot_c += o.n_cigar; tot_m += o.md_len + 1;
-        b200_hit_t &h = H[i];
-        const Reg &r = a[i];
-        h.rb = r.rb; h.re = r.re; h.pos = o.pos; h.hash = r.hash; h.qb = r.qb; h.qe = r.qe; h.rid = r.rid;
-        h.score = r.score; h.truesc = r.truesc; h.sub = r.sub; h.alt_sc = r.alt_sc; h.csub = r.csub; h.sub_n = r.sub_n;
-        h.w = r.w; h.seedcov = r.seedcov; h.secondary = r.secondary; h.secondary_all = r.secondary_all;
-        h.seedlen0 = r.seedlen0; h.n_comp = r.n_comp; h.is_alt = r.is_alt; h.frac_rep = r.frac_rep;
+        h.pos = o.pos;
         h.flag = o.flag; h.is_rev = o.is_rev; h.mapq = o.mapq; h.NM = o.NM; h.aln_sub = o.sub;
         h.n_cigar = o.n_cigar; h.md_len = o.md_len; h.cigar_off = co; h.md_off = mo;
         if (o.rid != r.rid) h.rid = -1000;   // the reference asserts equality (bwa/bwamem.c:1183)

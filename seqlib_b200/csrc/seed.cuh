@@ -33,19 +33,20 @@ HD int smem1(const DevIndex &ix, int len, const u8 *q, int x, int min_intv,
     *n_new = 0;
     if (q[x] > 3) return x + 1;
     if (min_intv < 1) min_intv = 1;
-    Intv ik, ok[4];
+    Intv ik, oc;
     int i, j, c, ncurr = 0, nprev;
     set_intv(ix, q[x], ik);
     ik.info = x + 1;
+    oc.x0 = oc.x1 = oc.x2 = oc.info = 0;
     for (i = x + 1; i < len; ++i) {            // forward extension
         if (q[i] < 4) {
             c = 3 - q[i];
-            extend4(ix, ik, ok, 0, ctr);
-            if (ok[c].x2 != ik.x2) {
+            extend_c(ix, ik, c, 0, oc, ctr);
+            if (oc.x2 != ik.x2) {
                 curr[ncurr++] = ik;
-                if (ok[c].x2 < (u64)min_intv) break;
+                if (oc.x2 < (u64)min_intv) break;
             }
-            ik = ok[c]; ik.info = i + 1;
+            ik = oc; ik.info = i + 1;
         } else {
             curr[ncurr++] = ik;
             break;
@@ -62,8 +63,8 @@ HD int smem1(const DevIndex &ix, int len, const u8 *q, int x, int min_intv,
         ncurr = 0;
         for (j = 0; j < nprev; ++j) {
             Intv *p = &prev[j];
-            if (c >= 0) extend4(ix, *p, ok, 1, ctr);
-            if (c < 0 || ok[c].x2 < (u64)min_intv) {
+            if (c >= 0) extend_c(ix, *p, c, 1, oc, ctr);
+            if (c < 0 || oc.x2 < (u64)min_intv) {
                 if (ncurr == 0) {
                     if (out.n == base || (u64)(i + 1) < (out.a[out.n - 1].info >> 32)) {
                         ik = *p; ik.info |= (u64)(i + 1) << 32;
@@ -71,9 +72,9 @@ HD int smem1(const DevIndex &ix, int len, const u8 *q, int x, int min_intv,
                         if (out.overflow) return ret;
                     }
                 }
-            } else if (ncurr == 0 || ok[c].x2 != curr[ncurr - 1].x2) {
-                ok[c].info = p->info;
-                curr[ncurr++] = ok[c];
+            } else if (ncurr == 0 || oc.x2 != curr[ncurr - 1].x2) {
+                oc.info = p->info;
+                curr[ncurr++] = oc;
             }
         }
         if (ncurr == 0) break;
@@ -88,20 +89,20 @@ HD int smem1(const DevIndex &ix, int len, const u8 *q, int x, int min_intv,
 template <class Ctr>
 HD int seed_strategy1(const DevIndex &ix, int len, const u8 *q, int x, int min_len, int max_intv, Intv *mem, Ctr &ctr)
 {
-    Intv ik, ok[4];
+    Intv ik, oc;
     mem->x0 = mem->x1 = mem->x2 = mem->info = 0;
     if (q[x] > 3) return x + 1;
     set_intv(ix, q[x], ik);
     for (int i = x + 1; i < len; ++i) {
         if (q[i] < 4) {
             int c = 3 - q[i];
-            extend4(ix, ik, ok, 0, ctr);
-            if (ok[c].x2 < (u64)max_intv && i - x >= min_len) {
-                *mem = ok[c];
+            extend_c(ix, ik, c, 0, oc, ctr);
+            if (oc.x2 < (u64)max_intv && i - x >= min_len) {
+                *mem = oc;
                 mem->info = (u64)x << 32 | (u64)(i + 1);
                 return i + 1;
             }
-            ik = ok[c];
+            ik = oc;
         } else return i + 1;
     }
     return len;

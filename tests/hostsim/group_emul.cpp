@@ -135,3 +135,97 @@ extern "C" int group_emul_check(int G, long n, const int *qlens, const int *tlen
     }
     return bad;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// lock-step emulation of global2_group (ksw_group.cuh): banded global alignment with traceback directions
+static int global2_group_emul(int G, int qlen, const u8 *query, int tlen, const u8 *target, const i8 *mat, int o_del, int e_del, int o_ins, int e_ins,
+                              int w, std::vector<u8> &z)
+{
+    const int MINF = KSW_MINUS_INF, SENT = -2147483000;
+    std::vector<int> H(qlen + 2), E(qlen + 2);
+    int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+    int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+    z.assign((size_t)n_col * tlen + 1, 0);
+    H[0] = 0; E[0] = MINF;
+    for (int j = 1; j <= qlen; ++j) { if (j <= w) { H[j] = -(o_ins + e_ins * j); E[j] = MINF; } else H[j] = E[j] = MINF; }
+    std::vector<int> n(G), L(G), fin(G), saved(G), j0v(G), j1v(G);
+    for (int i = 0; i < tlen; ++i) {
+        const i8 *qrow = mat + target[i] * 5;
+        int beg = i > w ? i - w : 0, end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        int h1_init = beg == 0 ? -(o_del + e_del * (i + 1)) : MINF;
+        int W = end - beg, C = W > 0 ? (W + G - 1) / G : 0;
+        for (int l = 0; l < G; ++l) {
+            int j0 = beg + l * C, j1 = std::min(j0 + C, end);
+            if (j0 > end) j0 = j1 = end;
+            j0v[l] = j0; j1v[l] = j1;
+            int Ll = SENT, nl = 0;
+            saved[l] = j0 < j1 ? H[j0] : 0;
+            for (int j = j0; j < j1; ++j) { int m = H[j] + qrow[query[j]]; int t = m - oe_ins; Ll = nl == 0 ? t : std::max(Ll - e_ins, t); ++nl; }
+            n[l] = nl; L[l] = Ll;
+        }
+        for (int d = 1; d < G; d <<= 1) {
+            std::vector<int> n2(n), L2(L);
+            for (int l = d; l < G; ++l) {
+                if (n[l] == 0) { L[l] = L2[l - d]; n[l] = n2[l - d]; }
+                else if (n2[l - d] == 0) { /* keep */ }
+                else { L[l] = std::max(L2[l - d] - n[l] * e_ins, L[l]); n[l] += n2[l - d]; }
+            }
+        }
+        for (int l = 0; l < G; ++l) {
+            if (l == 0 || n[l - 1] == 0) fin[l] = MINF - 0;
+            else fin[l] = std::max(MINF - n[l - 1] * e_ins, L[l - 1]);
+        }
+        int hlast = h1_init;
+        for (int l = 0; l < G; ++l) {
+            int j0 = j0v[l], j1 = j1v[l];
+            int f = fin[l], hp = saved[l];
+            if (l == 0) H[beg] = h1_init;
+            for (int j = j0; j < j1; ++j) {
+                int hp_next = j + 1 < j1 ? H[j + 1] : 0;
+                int m = hp + qrow[query[j]], e = E[j];
+                u8 d = m >= e ? 0 : 1;
+                int h = m >= e ? m : e;
+                d = h >= f ? d : 2;
+                h = h >= f ? h : f;
+                int t = m - oe_del;
+                e -= e_del;
+                d |= e > t ? 1 << 2 : 0;
+                e = e > t ? e : t;
+                E[j] = e;
+                t = m - oe_ins;
+                f -= e_ins;
+                d |= f > t ? 2 << 4 : 0;
+                f = f > t ? f : t;
+                z[(size_t)i * n_col + (j - beg)] = d;
+                H[j + 1] = h;
+                if (j == end - 1) hlast = h;
+                hp = hp_next;
+            }
+        }
+        if (W <= 0) H[end] = hlast;
+        E[end] = MINF;
+    }
+    return H[qlen];
+}
+
+extern "C" int global_emul_check(int G, long n, const int *qlens, const int *tlens, const long *qoff, const long *toff, const u8 *qp, const u8 *tp,
+                                 const int *ws, const i8 *mat, int o_del, int e_del, int o_ins, int e_ins, long *first_bad)
+{
+    int bad = 0;
+    for (long i = 0; i < n; ++i) {
+        int ql = qlens[i], tl = tlens[i], w = ws[i];
+        std::vector<EH> eh(ql + 2);
+        int n_col = ql < 2 * w + 1 ? ql : 2 * w + 1;
+        std::vector<u8> z((size_t)n_col * tl + 1), z2;
+        std::vector<u32> cg(ql + tl + 8);
+        struct C2 { unsigned long long sw_cells = 0, n_global = 0; } c;
+        BytesSeq q; q.p = qp + qoff[i]; q.step = 1;
+        BytesSeq t; t.p = tp + toff[i]; t.step = 1;
+        int nc = 0;
+        int sa = global2(ql, q, tl, t, mat, o_del, e_del, o_ins, e_ins, w, eh.data(), z.data(), cg.data(), (int)cg.size(), &nc, c);
+        int sb = global2_group_emul(G, ql, qp + qoff[i], tl, tp + toff[i], mat, o_del, e_del, o_ins, e_ins, w, z2);
+        bool ok = sa == sb && memcmp(z.data(), z2.data(), (size_t)n_col * tl) == 0;
+        if (!ok) { if (!bad && first_bad) *first_bad = i; ++bad; }
+    }
+    return bad;
+}
