@@ -16,6 +16,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <mutex>
 #include <time.h>
 #include "engine.cuh"
 #include "extend_group.cuh"
@@ -67,10 +68,57 @@ __global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
         if (w - (threadIdx.x & 31) >= A.n_work) break;
         if (w < A.n_work) {
             i64 rid = A.order ? A.order[w] : w;
-            if (STAGE == 0) stage_seed(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
+            if (STAGE == 0) stage_seed_t<true>(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
             else if (STAGE == 1) stage_chain(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
             else if (STAGE == 2) stage_extend(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
             else stage_finalize(A.ix, A.opt, A.caps, A.B, rid, scr, A.log_tab, A.n_log, ctr);
+        }
+    }
+    flush_counters(ctr, A.ctrs);
+}
+
+// Seeding with one converged extension site per warp (seed_fsm.cuh).  A lane that finishes its read commits the
+// intervals and claims the next read on its own, so the 32 lanes keep issuing Occ gathers together.
+__global__ void __launch_bounds__(128, 4) k_seed_fsm(const __grid_constant__ KArgs A)
+{
+    u8 *scr = A.scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.scratch_stride;
+    Intv *prev = (Intv *)scr, *curr = prev + (A.caps.maxlen + 1);
+    IntvSink out; out.a = curr + (A.caps.maxlen + 1); out.n = 0; out.cap = A.caps.intv; out.overflow = false;
+    CtrLocal ctr;
+    SeedFsm f; f.state = S_DONE;
+    i64 rid = -1;
+    int len = 0;
+    const u8 *seq = nullptr;
+    bool pending = false, done = false;
+    for (;;) {
+        if (!pending && !done) {
+            if (rid >= 0) {                                     // commit the read that just finished
+                ReadRec &R = A.B.rec[rid];
+                if (out.overflow) A.B.ovf[rid] |= OVF_INTV;
+                else {
+                    i64 off = pool_alloc(A.B.pool, POOL_INTV, out.n);
+                    if (off < 0) A.B.ovf[rid] |= OVF_POOL;
+                    else { for (int i = 0; i < out.n; ++i) A.B.pool.intv[off + i] = out.a[i]; R.n_intv = out.n; R.intv_off = off; }
+                }
+                rid = -1;
+            }
+            i64 w = (i64)atomicAdd(A.work_ctr, 1ull);
+            if (w >= A.n_work) done = true;
+            else {
+                rid = A.order ? A.order[w] : w;
+                ReadRec &R = A.B.rec[rid];
+                R.n_intv = 0; R.intv_off = 0;
+                len = (int)(A.B.seq_off[rid + 1] - A.B.seq_off[rid]);
+                seq = A.B.seq + A.B.seq_off[rid];
+                out.n = 0; out.overflow = false;
+                if (A.B.ovf[rid] || len < A.opt.min_seed_len) { if (A.B.ovf[rid]) rid = -1; pending = false; }
+                else { seed_fsm_init(f, prev, curr); pending = seed_step(A.ix, A.opt, len, seq, out, f); }
+            }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (pending) {
+            extend_c(A.ix, f.req, f.req_c, f.req_back, f.res, ctr);
+            pending = seed_step(A.ix, A.opt, len, seq, out, f);
         }
     }
     flush_counters(ctr, A.ctrs);
@@ -152,6 +200,7 @@ __global__ void k_encode(const u8 *__restrict__ in, u8 *__restrict__ out, i64 n)
     }
 }
 
+__global__ void k_iota32(i32 *a, i64 n) { i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = (i32)i; }
 __global__ void k_clear_u32(u32 *a, i64 n) { i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = 0; }
 __global__ void k_clear_list(u32 *a, const i32 *list, i64 n) { i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[list[i]] = 0; }
 
@@ -197,8 +246,58 @@ __global__ void k_gather(const ReadRec *__restrict__ rec, i64 n, Pools P, const 
 }
 
 // ---------------------------------------------------------------------------------------
+// Pinned host buffers for results, recycled through a small free list: a results handle owns its buffers until
+// b200_results_free() hands them back, so steady-state calls pay neither cudaHostAlloc nor page faults nor zero fill.
+struct PinBuf {
+    void *p = nullptr; size_t cap = 0;
+};
+struct PinPool {
+    std::vector<PinBuf> free_list;
+    std::mutex mu;
+    PinBuf get(size_t bytes)
+    {
+        if (bytes == 0) bytes = 64;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int best = -1;
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].cap >= bytes && (best < 0 || free_list[i].cap < free_list[best].cap)) best = (int)i;
+            if (best >= 0) { PinBuf b = free_list[best]; free_list.erase(free_list.begin() + best); return b; }
+        }
+        PinBuf b; b.cap = bytes + (bytes >> 3) + 4096;
+        if (cudaHostAlloc(&b.p, b.cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; }
+        if (!b.p) throw std::bad_alloc();
+        return b;
+    }
+    void put(PinBuf b)
+    {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> g(mu);
+        if (free_list.size() >= 16) {            // drop the smallest
+            size_t k = 0;
+            for (size_t i = 1; i < free_list.size(); ++i) if (free_list[i].cap < free_list[k].cap) k = i;
+            if (free_list[k].cap < b.cap) { cudaFreeHost(free_list[k].p); free_list[k] = b; } else cudaFreeHost(b.p);
+            return;
+        }
+        free_list.push_back(b);
+    }
+};
+static PinPool &pin_pool() { static PinPool p; return p; }
+
 struct HostResults {
-    std::vector<i64> hit_off; std::vector<b200_hit_t> hits; std::vector<u32> cigar; std::vector<char> md;
+    PinBuf b_off, b_hits, b_cigar, b_md;
+    i64 n_reads = 0, n_hits = 0, n_cigar = 0, n_md = 0;
+    i64 *hit_off() const { return (i64 *)b_off.p; }
+    b200_hit_t *hits() const { return (b200_hit_t *)b_hits.p; }
+    u32 *cigar() const { return (u32 *)b_cigar.p; }
+    char *md() const { return (char *)b_md.p; }
+    void alloc(i64 nr, i64 nh, i64 nc, i64 nm)
+    {
+        n_reads = nr; n_hits = nh; n_cigar = nc; n_md = nm;
+        b_off = pin_pool().get((size_t)(nr + 1) * 8); b_hits = pin_pool().get((size_t)nh * sizeof(b200_hit_t));
+        b_cigar = pin_pool().get((size_t)nc * 4); b_md = pin_pool().get((size_t)nm);
+    }
+    ~HostResults() { pin_pool().put(b_off); pin_pool().put(b_hits); pin_pool().put(b_cigar); pin_pool().put(b_md); }
 };
 
 struct Engine {
@@ -206,7 +305,7 @@ struct Engine {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8];
     // chunk buffers
-    DevBuf seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, dp_scratch, dp_jobs, small;
+    DevBuf seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
     DevBuf p_intv, p_chain, p_seed, p_reg, p_hit, p_cigar, p_md;
     DevBuf nh, nc, nm, oh, oc, om, cubtmp, o_hit_off, o_hits, o_cigar, o_md;
     double pool_scale = 1.0;
@@ -256,9 +355,12 @@ static void launch_stage(Engine &E, KArgs &A, int grid)
 static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
 {
     int g[4];
-    if (!spill) { g[0] = stage_grid<0>(E.sms); g[1] = stage_grid<1>(E.sms); g[2] = stage_grid<2>(E.sms); g[3] = stage_grid<3>(E.sms); }
+    if (!spill) { { int perf = 0; CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perf, k_seed_fsm, 128, 0)); g[0] = E.sms * (perf < 1 ? 1 : perf); }
+                  if (!getenv("B200_SEED_FSM")) g[0] = stage_grid<0>(E.sms); g[1] = stage_grid<1>(E.sms); g[2] = stage_grid<2>(E.sms); g[3] = stage_grid<3>(E.sms); }
     else g[0] = g[1] = g[2] = g[3] = std::max<int>(1, (int)std::min<i64>((A.n_work + 127) / 128, 8));
-    size_t stride = max4(seed_scratch_bytes(A.caps), chain_scratch_bytes(A.caps), extend_scratch_bytes(A.caps), finalize_scratch_bytes(A.caps));
+    Caps tc = A.caps;
+    if (A.B.dp_jobs) tc.z = 64;          // gapped hits go to k_finalize_dp, the thread-per-read stage needs no direction matrix
+    size_t stride = max4(seed_scratch_bytes(tc), chain_scratch_bytes(tc), extend_scratch_bytes(tc), finalize_scratch_bytes(tc));
     stride = (stride + 63) & ~(size_t)63;
     int gmax = std::max(std::max(g[0], g[1]), std::max(g[2], g[3]));
     DevBuf &S = spill ? E.spill_scratch : E.scratch;
@@ -266,28 +368,46 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
     A.scratch = S.as<u8>(); A.scratch_stride = stride;
     cudaEvent_t *ev = E.ev;
     CU_CHECK(cudaEventRecord(ev[0], E.st));
-    launch_stage<0>(E, A, g[0]); CU_CHECK(cudaEventRecord(ev[1], E.st));
+    {
+        static int fsm_ok = getenv("B200_SEED_FSM") ? 1 : 0;
+        if (fsm_ok) {
+            CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
+            k_seed_fsm<<<g[0], 128, 0, E.st>>>(A);
+            CU_CHECK(cudaGetLastError());
+        } else launch_stage<0>(E, A, g[0]);
+    }
+    CU_CHECK(cudaEventRecord(ev[1], E.st));
     launch_stage<1>(E, A, g[1]); CU_CHECK(cudaEventRecord(ev[2], E.st));
     {
         const int G = 8;
         size_t smem = (size_t)(128 / G) * group_smem_bytes(A.caps.maxlen);
         static int group_ok = getenv("B200_SCALAR_EXTEND") ? 0 : 1;
-        if (!spill && group_ok && smem <= 200 * 1024) {
+        if (group_ok && smem <= 200 * 1024) {
             int per = 0;
             CU_CHECK(cudaFuncSetAttribute(k_extend_group<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_group<G>, 128, smem));
             if (per < 1) per = 1;
-            int grid = E.sms * per;
+            int grid = (int)std::min<i64>((i64)E.sms * per, std::max<i64>(1, (A.n_work + (128 / G) - 1) / (128 / G)));
             size_t gstride = (extend_group_scratch_bytes(A.caps) + 63) & ~(size_t)63;
-            E.group_scratch.reserve(gstride * (size_t)grid * (128 / G));
-            KArgs A2 = A; A2.scratch = E.group_scratch.as<u8>(); A2.scratch_stride = gstride;
+            (spill ? E.group_scratch2 : E.group_scratch).reserve(gstride * (size_t)grid * (128 / G));
+            KArgs A2 = A; A2.scratch = (spill ? E.group_scratch2 : E.group_scratch).as<u8>(); A2.scratch_stride = gstride;
+            if (!spill && A.B.work && !A.order) {       // heaviest reads first, equal work side by side in a warp
+                i64 n = A.n_work;
+                E.sort_keys.reserve(n * 4 + 64); E.sort_vals.reserve(n * 4 + 64); E.sort_vals2.reserve(n * 4 + 64);
+                k_iota32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.sort_vals.as<i32>(), n);
+                size_t tb = 0;
+                cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 20, E.st);
+                E.cubtmp.reserve(tb);
+                CU_CHECK(cub::DeviceRadixSort::SortPairsDescending(E.cubtmp.p, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 20, E.st));
+                A2.order = E.sort_vals2.as<i32>();
+            }
             CU_CHECK(cudaMemsetAsync(A2.work_ctr, 0, 8, E.st));
             k_extend_group<G><<<grid, 128, smem, E.st>>>(A2);
             CU_CHECK(cudaGetLastError());
         } else launch_stage<2>(E, A, g[2]);
     }
     CU_CHECK(cudaEventRecord(ev[3], E.st));
-    launch_stage<3>(E, A, g[3]);
+    { KArgs At = A; At.caps = tc; launch_stage<3>(E, At, g[3]); }
     if (A.B.dp_jobs) {
         const int G = 8;
         size_t smem = (size_t)(128 / G) * findp_smem_bytes(A.caps.maxlen);
@@ -295,10 +415,10 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
         CU_CHECK(cudaFuncSetAttribute(k_finalize_dp<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_finalize_dp<G>, 128, smem));
         if (per < 1) per = 1;
-        int grid = E.sms * per;
+        int grid = spill ? std::min(E.sms * per, 64) : E.sms * per;
         size_t gstride = (findp_scratch_bytes(A.caps) + 63) & ~(size_t)63;
-        E.dp_scratch.reserve(gstride * (size_t)grid * (128 / G));
-        KArgs A3 = A; A3.scratch = E.dp_scratch.as<u8>(); A3.scratch_stride = gstride;
+        (spill ? E.dp_scratch2 : E.dp_scratch).reserve(gstride * (size_t)grid * (128 / G));
+        KArgs A3 = A; A3.scratch = (spill ? E.dp_scratch2 : E.dp_scratch).as<u8>(); A3.scratch_stride = gstride;
         CU_CHECK(cudaMemsetAsync(A3.work_ctr, 0, 8, E.st));
         k_finalize_dp<G><<<grid, 128, smem, E.st>>>(A3);
         CU_CHECK(cudaGetLastError());
@@ -340,6 +460,7 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         P.hits = E.p_hit.as<b200_hit_t>(); P.cigar = E.p_cigar.as<u32>(); P.md = E.p_md.as<char>();
         for (int k = 0; k < N_POOLS; ++k) P.cap[k] = cap[k];
         P.used = d_small + 8;
+        { static int bal = getenv("B200_NO_BALANCE") ? 0 : 1; if (bal) { E.work.reserve(n * 4 + 64); A.B.work = E.work.as<u32>(); } }
         A.order = nullptr; A.n_work = n; A.work_ctr = d_small; A.ctrs = (DevCounters *)(d_small + 16);
         {   // queue of hits that need a banded global alignment (drained by k_finalize_dp)
             size_t smem = (size_t)(128 / 8) * findp_smem_bytes(maxlen);
@@ -364,8 +485,17 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         i64 n_sp = (i64)h_small[1];
         if (n_sp) {
             E.stats.n_overflow += (u64)n_sp;
+            KArgs S = A; S.caps = big; S.order = E.list.as<i32>(); S.n_work = n_sp;
+            CU_CHECK(cudaMemsetAsync(d_small + 2, 0, 8, E.st));       // the main pass's DP queue has been drained
+            if (trace) {
+                std::vector<i32> lst(n_sp); std::vector<u32> fl(n);
+                CU_CHECK(cudaMemcpy(lst.data(), E.list.p, n_sp * 4, cudaMemcpyDeviceToHost));
+                CU_CHECK(cudaMemcpy(fl.data(), E.ovf.p, n * 4, cudaMemcpyDeviceToHost));
+                int cnt[8] = {0};
+                for (i64 k = 0; k < n_sp; ++k) for (int b = 0; b < 8; ++b) if (fl[lst[k]] >> b & 1) ++cnt[b];
+                fprintf(stderr, "[b200 trace] spill reasons: intv %d seed %d chain %d reg %d out %d scratch %d pool %d\n", cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], cnt[6]);
+            }
             k_clear_list<<<(unsigned)((n_sp + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), E.list.as<i32>(), n_sp);
-            KArgs S = A; S.caps = big; S.order = E.list.as<i32>(); S.n_work = n_sp; S.B.dp_jobs = nullptr;
             run_stages(E, S, true, ms4);
             E.stats.n_launches += 1;
         }
@@ -538,17 +668,17 @@ int b200_batch_fetch(b200_batch_t *b, b200_results_t **out)
         i64 th = 0, tc = 0, tm = 0;
         for (auto c : b->chunks) { th += c->out.n_hits; tc += c->out.n_cigar; tm += c->out.n_md; }
         HostResults &H = R->r;
-        H.hit_off.resize(b->n + 1); H.hits.resize(th); H.cigar.resize(tc); H.md.resize(tm);
+        H.alloc(b->n, th, tc, tm);
         i64 ph = 0, pc = 0, pm = 0;
         for (auto c : b->chunks) {
-            CU_CHECK(cudaMemcpyAsync(H.hit_off.data() + c->r0, c->hit_off.p, c->n * 8, cudaMemcpyDeviceToHost, E.st));
-            if (c->out.n_hits) CU_CHECK(cudaMemcpyAsync(H.hits.data() + ph, c->hits.p, c->out.n_hits * sizeof(b200_hit_t), cudaMemcpyDeviceToHost, E.st));
-            if (c->out.n_cigar) CU_CHECK(cudaMemcpyAsync(H.cigar.data() + pc, c->cigar.p, c->out.n_cigar * 4, cudaMemcpyDeviceToHost, E.st));
-            if (c->out.n_md) CU_CHECK(cudaMemcpyAsync(H.md.data() + pm, c->md.p, c->out.n_md, cudaMemcpyDeviceToHost, E.st));
+            CU_CHECK(cudaMemcpyAsync(H.hit_off() + c->r0, c->hit_off.p, c->n * 8, cudaMemcpyDeviceToHost, E.st));
+            if (c->out.n_hits) CU_CHECK(cudaMemcpyAsync(H.hits() + ph, c->hits.p, c->out.n_hits * sizeof(b200_hit_t), cudaMemcpyDeviceToHost, E.st));
+            if (c->out.n_cigar) CU_CHECK(cudaMemcpyAsync(H.cigar() + pc, c->cigar.p, c->out.n_cigar * 4, cudaMemcpyDeviceToHost, E.st));
+            if (c->out.n_md) CU_CHECK(cudaMemcpyAsync(H.md() + pm, c->md.p, c->out.n_md, cudaMemcpyDeviceToHost, E.st));
             ph += c->out.n_hits; pc += c->out.n_cigar; pm += c->out.n_md;
         }
         CU_CHECK(cudaStreamSynchronize(E.st));
-        H.hit_off[b->n] = th;
+        H.hit_off()[b->n] = th;
     } catch (const std::exception &e) { delete R; return fail(B200_ERR_CUDA, e.what()); }
     *out = R;
     return B200_OK;
@@ -574,9 +704,8 @@ int b200_results_view(const b200_results_t *res, b200_results_view_t *v)
 {
     if (!res || !v) return fail(B200_ERR_ARG, "bad argument");
     const HostResults &H = res->r;
-    v->n_reads = (int64_t)H.hit_off.size() - 1; v->hit_off = H.hit_off.data(); v->hits = H.hits.data();
-    v->cigar = H.cigar.data(); v->md = H.md.data();
-    v->n_hits = (int64_t)H.hits.size(); v->n_cigar = (int64_t)H.cigar.size(); v->n_md = (int64_t)H.md.size();
+    v->n_reads = H.n_reads; v->hit_off = H.hit_off(); v->hits = H.hits(); v->cigar = H.cigar(); v->md = H.md();
+    v->n_hits = H.n_hits; v->n_cigar = H.n_cigar; v->n_md = H.n_md;
     return B200_OK;
 }
 

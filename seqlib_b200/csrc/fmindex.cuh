@@ -54,17 +54,17 @@ HD void occ4_pair(const DevIndex &ix, u64 k, u64 l, u64 ck[4], u64 cl[4], Ctr &c
     if (k == NEG1) { ck[0] = ck[1] = ck[2] = ck[3] = 0; }
     if (l == NEG1) { cl[0] = cl[1] = cl[2] = cl[3] = 0; }
     u64 bk = kk >> 6, bl = ll >> 6;
-    if (k != NEG1) {
-        OccLoad b = load_block(ix, bk);
-        ctr.occ_blocks++;
-        block_rank4(b, (int)(kk & 63) + 1, ck);
-        if (l != NEG1 && bl == bk) { block_rank4(b, (int)(ll & 63) + 1, cl); return; }
+    if (k != NEG1 && l != NEG1) {
+        // both blocks are requested before either is used: two gathers in flight per lane instead of one
+        OccLoad b1 = load_block(ix, bk);
+        OccLoad b2 = bl != bk ? load_block(ix, bl) : b1;
+        ctr.occ_blocks += bl != bk ? 2 : 1;
+        block_rank4(b1, (int)(kk & 63) + 1, ck);
+        block_rank4(b2, (int)(ll & 63) + 1, cl);
+        return;
     }
-    if (l != NEG1) {
-        OccLoad b = load_block(ix, bl);
-        ctr.occ_blocks++;
-        block_rank4(b, (int)(ll & 63) + 1, cl);
-    }
+    if (k != NEG1) { OccLoad b = load_block(ix, bk); ctr.occ_blocks++; block_rank4(b, (int)(kk & 63) + 1, ck); }
+    if (l != NEG1) { OccLoad b = load_block(ix, bl); ctr.occ_blocks++; block_rank4(b, (int)(ll & 63) + 1, cl); }
 }
 
 // bwt_extend (bwa/bwt.c:262-275) restricted to the one child the callers use: ok[c].

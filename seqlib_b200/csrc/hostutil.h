@@ -38,7 +38,7 @@ inline Caps default_caps(int maxlen, bool tiny = false)
     Caps c;
     c.maxlen = maxlen;
     if (tiny) { c.intv = 6; c.wchains = 3; c.wseeds = 6; c.seeds = 4; c.regs = 2; c.cigar = 3; c.md = 6; c.z = 1024; }
-    else { c.intv = 64; c.wchains = 64; c.wseeds = 160; c.seeds = 96; c.regs = 24; c.cigar = 24; c.md = 96; c.z = (i64)maxlen * 64; }
+    else { c.intv = 64; c.wchains = 64; c.wseeds = 160; c.seeds = 96; c.regs = 24; c.cigar = 24; c.md = 96; c.z = (i64)maxlen * 256; }
     return c;
 }
 

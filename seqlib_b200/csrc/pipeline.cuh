@@ -16,6 +16,7 @@
 #pragma once
 #include "common.cuh"
 #include "seed.cuh"
+#include "seed_fsm.cuh"
 #include "chain.cuh"
 #include "extend.cuh"
 #include "finalize.cuh"
@@ -59,6 +60,7 @@ struct Batch {
     const i64 *seq_off;      // n_reads + 1
     const i64 *hash_id;      // n_reads
     u32 *ovf;                // per read overflow bits
+    u32 *work;               // optional: per read estimate of extension work (for load-balanced scheduling)
     ReadRec *rec;            // per read
     Pools pool;
 };
@@ -84,7 +86,8 @@ HD u8 *align8(u8 *p) { return (u8 *)(((uintptr_t)p + 7) & ~(uintptr_t)7); }
 // ------------------------------------------------------------------ seed
 HD size_t seed_scratch_bytes(const Caps &c) { return sizeof(Intv) * (2 * (size_t)(c.maxlen + 1) + (size_t)c.intv); }
 
-HD void stage_seed(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
+template <bool LOOPS>
+HD void stage_seed_t(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
 {
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
     const u8 *seq = B.seq + B.seq_off[rid];
@@ -93,12 +96,20 @@ HD void stage_seed(const DevIndex &ix, const Opt &opt, const Caps &caps, const B
     if (B.ovf[rid]) return;
     Intv *prev = (Intv *)scratch, *curr = prev + (caps.maxlen + 1);
     IntvSink out; out.a = curr + (caps.maxlen + 1); out.n = 0; out.cap = caps.intv; out.overflow = false;
-    if (len >= opt.min_seed_len) collect_intv(ix, opt, len, seq, out, prev, curr, ctr);
+    if (len >= opt.min_seed_len) {
+        if (LOOPS) collect_intv(ix, opt, len, seq, out, prev, curr, ctr);        // the reference's loop nest (seed.cuh)
+        else collect_intv_fsm(ix, opt, len, seq, out, prev, curr, ctr);        // the same, as the state machine the GPU kernel uses
+    }
     if (out.overflow) { B.ovf[rid] |= OVF_INTV; return; }
     i64 off = pool_alloc(B.pool, POOL_INTV, out.n);
     if (off < 0) { B.ovf[rid] |= OVF_POOL; return; }
     for (int i = 0; i < out.n; ++i) B.pool.intv[off + i] = out.a[i];
     R.n_intv = out.n; R.intv_off = off;
+}
+
+HD void stage_seed(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
+{
+    stage_seed_t<false>(ix, opt, caps, B, rid, scratch, ctr);
 }
 
 // ------------------------------------------------------------------ chain
@@ -113,6 +124,7 @@ HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const 
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
     ReadRec &R = B.rec[rid];
     R.n_chains = 0; R.n_seeds = 0; R.chain_off = R.seed_off = 0; R.frac_rep = 0.f;
+    if (B.work) B.work[rid] = 0;
     if (B.ovf[rid]) return;
     ChainWork w;
     u8 *p = scratch;
@@ -143,6 +155,11 @@ HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const 
     }
     R.n_chains = n; R.n_seeds = ns; R.chain_off = coff; R.seed_off = soff;
     R.frac_rep = (float)l_rep / len;
+    if (B.work) {       // query bases left to extend, summed over the seeds that will be tried (scheduling hint only)
+        u32 est = 0;
+        for (int i = 0; i < ns; ++i) est += (u32)(len - os[i].len);
+        B.work[rid] = est < 0xFFFFFu ? est : 0xFFFFFu;
+    }
 }
 
 // ------------------------------------------------------------------ extend

@@ -100,3 +100,87 @@ def test_synth_is_deterministic():
     b = synth.reads(p1, 10000, ctg, 100)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     assert synth.ascii_of(p1, 0, 20) == "AGTAAATGTTCCTCAGACTG"
+
+
+def _opt_default():
+    """mem_opt_init + MEM_F_SOFTCLIP without needing any shared library."""
+    from seqlib_b200.abi import MemOpt
+    o = MemOpt()
+    o.a, o.b, o.o_del, o.e_del, o.o_ins, o.e_ins = 1, 4, 6, 1, 6, 1
+    o.pen_unpaired, o.pen_clip5, o.pen_clip3, o.w, o.zdrop = 17, 5, 5, 100, 100
+    o.max_mem_intv, o.T, o.flag, o.min_seed_len, o.min_chain_weight, o.max_chain_extend = 20, 30, 0x200, 19, 0, 1 << 30
+    o.split_factor, o.split_width, o.max_occ, o.max_chain_gap, o.n_threads, o.chunk_size = 1.5, 10, 500, 10000, 1, 10000000
+    o.mask_level, o.drop_ratio, o.XA_drop_ratio, o.mask_level_redun = 0.5, 0.5, 0.8, 0.95
+    o.mapQ_coef_len, o.mapQ_coef_fac, o.max_ins, o.max_matesw, o.max_XA_hits, o.max_XA_hits_alt = 50, 3, 10000, 50, 5, 200
+    m = []
+    for i in range(4):
+        m += [1 if i == j else -4 for j in range(4)] + [-1]
+    m += [-1] * 5
+    for i, x in enumerate(m):
+        o.mat[i] = x
+    return o
+
+
+@pytest.mark.parametrize("name", ["sim1_5k", "bcr_2k"])
+def test_c_restatement_vs_golden_tiny(name):
+    """oracle/oracle_bwa.c (plain-C restatement) reproduces the golden vectors made by the reference's own bwa."""
+    from oracle import pyoracle
+    if not pyoracle.have():
+        pytest.skip("oracle/liboracle.so not built")
+    gold, z = goldenlib.load(name)
+    view = pyoracle.load_bwa_index(goldenlib.path("tiny", "tiny.fa"))
+    reads = cases.read_lines(goldenlib.path(name + ".txt"))
+    got = pyoracle.align(view, reads, _opt_default(), cases.ids_for(len(reads)))
+    assert parity.compare_results(got, gold) == []
+
+
+def test_c_restatement_vs_golden_kat_and_c1():
+    from oracle import pyoracle
+    if not pyoracle.have():
+        pytest.skip("oracle/liboracle.so not built")
+    gold, z = goldenlib.load("kat")
+    v = pyoracle.View(z["primary"], z["L2"], z["bwt"], z["sa"], 32, 323, z["pac"], [(n, sum(len(s) for s in cases.KAT_SEQS[:i]), len(cases.KAT_SEQS[i]))
+                                                                                       for i, n in enumerate(cases.KAT_NAMES)])
+    got = pyoracle.align(v, cases.KAT_QUERIES, _opt_default(), z["ids"])
+    assert parity.compare_results(got, gold) == []
+    gold, z = goldenlib.load("c1")
+    pac, ctg, _ = cases.c1_reference()
+    v = pyoracle.View(z["primary"], z["L2"], z["bwt"], z["sa"], 32, 10000, pac, ctg)
+    seqs, off = cases.c1_reads(pac, ctg)
+    got = pyoracle.align(v, (seqs, off), _opt_default(), cases.ids_for(len(off) - 1))
+    assert parity.compare_results(got, gold) == []
+
+
+def test_c_restatement_ksw_vs_golden():
+    from oracle import pyoracle
+    if not pyoracle.have():
+        pytest.skip("oracle/liboracle.so not built")
+    z = np.load(goldenlib.path("ksw_c3.npz"))
+    jobs, qp, tp = cases.c3_tuples(4000)
+    out = pyoracle.ksw_extend2_batch(jobs, qp, tp, np.array(list(_opt_default().mat), dtype=np.int8))
+    for f in out.dtype.names:
+        assert np.array_equal(out[f], z["out"][f]), f
+
+
+def test_c_restatement_vs_live_reference_random():
+    """Random reference + reads with indels and Ns: restatement == the reference's compiled bwa."""
+    from oracle import pyoracle, pyref
+    if not (pyoracle.have() and pyref.have_ref()):
+        pytest.skip("needs liboracle.so and oracle/_ref")
+    from seqlib_b200 import synth
+    l_pac = 50000
+    pac = synth.reference(l_pac, seed=123)
+    ctg = synth.contigs_for(l_pac, 2, "k")
+    names = [c[0] for c in ctg]
+    seqs = [synth.ascii_of(pac, c[1], c[1] + c[2]) for c in ctg]
+    ridx = pyref.RefIndex.construct(names, seqs)
+    a = ridx.arrays()
+    v = pyoracle.View(a["primary"], a["L2"], a["bwt"], a["sa"], 32, l_pac, a["pac"], ctg)
+    r, off, _, _ = synth.reads(pac, l_pac, ctg, 3000, 150, 0.03, 3e-3, seed=321)
+    r = r.copy()
+    r[::613] = ord("N")
+    ids = cases.ids_for(3000)
+    opt = pyref.default_opt()
+    exp, _ = pyref.align(ridx, (r, off), opt, ids)
+    got = pyoracle.align(v, (r, off), opt, ids)
+    assert parity.compare_results(got, exp) == []
