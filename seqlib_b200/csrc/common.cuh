@@ -39,7 +39,8 @@ HD int popc64(u64 x)
 // Device image of the FM-index (DESIGN.md "data layout in HBM").
 //   occ  : one 32-byte block per 64 BWT symbols:
 //            u32 cnt[4]  = number of A/C/G/T in bwt[0, 64*blk)   (16 B)
-//            u64 sym[2]  = 64 symbols, symbol j in bits 2j..2j+1 of sym[j>>5] (16 B)
+//            u64 sym[2]  = the 64 symbols as two bit planes: bit j of sym[0] = low bit, bit j of sym[1] = high bit
+//                          of symbol j (16 B); a rank needs three 64-bit popcounts under one mask
 //          ($ is removed exactly as in bwa: ranks >= primary shift down by one.)
 //   sa   : u64 suffix-array samples every 2^sa_shift ranks, sa[0] = (u64)-1
 //   text : forward + reverse-complement reference, 2 bits/base, 32 bases per u64,
@@ -49,6 +50,9 @@ struct OccBlock {
     u32 cnt[4];
     u64 sym[2];
 };
+
+HD int occ_sym(const OccBlock &b, int j) { return (int)((b.sym[0] >> j) & 1) | (int)((b.sym[1] >> j) & 1) << 1; }
+HD void occ_set_sym(OccBlock &b, int j, u64 s) { b.sym[0] |= (s & 1) << j; b.sym[1] |= (s >> 1) << j; }
 
 #define B200_MAX_CONTIGS_CONST 0
 

@@ -77,29 +77,62 @@ __global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
     flush_counters(ctr, A.ctrs);
 }
 
-// Seeding with one converged extension site per warp (seed_fsm.cuh).  A lane that finishes its read commits the
-// intervals and claims the next read on its own, so the 32 lanes keep issuing Occ gathers together.
-__global__ void __launch_bounds__(128, 4) k_seed_fsm(const __grid_constant__ KArgs A)
+// ---------------------------------------------------------------------------------------
+// Seeding, main pass: the single-extension-site machine of seed2.cuh.
+//   shared memory per block: CAP packed intervals per thread (entry e of thread t at [e * 128 + t], 16 B each, so a
+//   warp's access is four conflict-free 128-byte wavefronts) + the read as 2-bit words (word w of thread t at [w * 128 + t]).
+//   A lane whose read is finished records it and claims the next one by itself, so the 32 lanes stay inside the one
+//   loop and reach the Occ gathers together.  Intervals go straight to the read's fixed slot of the interval pool
+//   (read r owns [r * stride, (r+1) * stride)), in production order; k_sort_intv orders them afterwards.
+//   Reads the machine does not take (N bases, list or slot overflow) get OVF_INTV and go through the spill pass,
+//   i.e. the reference-shaped k_stage<0>.
+struct SmemList {
+    uint4 *p;
+    __device__ __forceinline__ PIntv get(int e) const { uint4 v = p[e * 128]; PIntv r; r.w0 = v.x; r.w1 = v.y; r.w2 = v.z; r.w3 = v.w; return r; }
+    __device__ __forceinline__ void set(int e, const PIntv &r) { p[e * 128] = make_uint4(r.w0, r.w1, r.w2, r.w3); }
+};
+struct SmemQuery {
+    const u32 *p;
+    __device__ __forceinline__ int operator[](int i) const { return (int)((p[(i >> 4) * 128] >> ((i & 15) * 2)) & 3u); }
+};
+
+// 2-bit words of every read (16 bases per word, base i in bits 2(i&15)..) + a flag for reads with a base > 3
+__global__ void k_pack_reads(const u8 *__restrict__ seq, const i64 *__restrict__ off, i64 n, int qw, u32 *__restrict__ packed, u32 *__restrict__ bad)
 {
-    u8 *scr = A.scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.scratch_stride;
-    Intv *prev = (Intv *)scr, *curr = prev + (A.caps.maxlen + 1);
-    IntvSink out; out.a = curr + (A.caps.maxlen + 1); out.n = 0; out.cap = A.caps.intv; out.overflow = false;
+    i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * qw) return;
+    i64 r = t / qw; int w = (int)(t - r * qw);
+    i64 b = off[r], len = off[r + 1] - b;
+    u32 v = 0; bool n_base = false;
+    for (int k = 0; k < 16; ++k) {
+        i64 i = (i64)w * 16 + k;
+        if (i >= len) break;
+        u32 c = seq[b + i];
+        if (c > 3) { n_base = true; c = 0; }
+        v |= c << (2 * k);
+    }
+    packed[t] = v;
+    if (n_base || (w == 0 && len > (i64)qw * 16)) atomicOr(bad + r, 1u);
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(128, 4) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride)
+{
+    extern __shared__ uint4 seed_smem[];
+    SmemList L; L.p = seed_smem + threadIdx.x;
+    u32 *myq = (u32 *)(seed_smem + CAP * 128) + threadIdx.x;
+    SmemQuery Q; Q.p = myq;
+    SeedMachine<SmemList, SmemQuery> m;
+    m.mode = 0; m.ovf = 0;
     CtrLocal ctr;
-    SeedFsm f; f.state = S_DONE;
     i64 rid = -1;
-    int len = 0;
-    const u8 *seq = nullptr;
-    bool pending = false, done = false;
+    bool done = false;
     for (;;) {
-        if (!pending && !done) {
-            if (rid >= 0) {                                     // commit the read that just finished
+        if (m.mode == 0 && !done) {
+            if (rid >= 0) {                                     // record the read that just finished
                 ReadRec &R = A.B.rec[rid];
-                if (out.overflow) A.B.ovf[rid] |= OVF_INTV;
-                else {
-                    i64 off = pool_alloc(A.B.pool, POOL_INTV, out.n);
-                    if (off < 0) A.B.ovf[rid] |= OVF_POOL;
-                    else { for (int i = 0; i < out.n; ++i) A.B.pool.intv[off + i] = out.a[i]; R.n_intv = out.n; R.intv_off = off; }
-                }
+                if (m.ovf) { A.B.ovf[rid] |= OVF_INTV; R.n_intv = 0; R.intv_off = 0; }
+                else { R.n_intv = m.out.n; R.intv_off = rid * stride; }
                 rid = -1;
             }
             i64 w = (i64)atomicAdd(A.work_ctr, 1ull);
@@ -107,22 +140,38 @@ __global__ void __launch_bounds__(128, 4) k_seed_fsm(const __grid_constant__ KAr
             else {
                 rid = A.order ? A.order[w] : w;
                 ReadRec &R = A.B.rec[rid];
-                R.n_intv = 0; R.intv_off = 0;
-                len = (int)(A.B.seq_off[rid + 1] - A.B.seq_off[rid]);
-                seq = A.B.seq + A.B.seq_off[rid];
-                out.n = 0; out.overflow = false;
-                if (A.B.ovf[rid] || len < A.opt.min_seed_len) { if (A.B.ovf[rid]) rid = -1; pending = false; }
-                else { seed_fsm_init(f, prev, curr); pending = seed_step(A.ix, A.opt, len, seq, out, f); }
+                int len = (int)(A.B.seq_off[rid + 1] - A.B.seq_off[rid]);
+                if (A.B.ovf[rid] || bad[rid]) {
+                    if (!A.B.ovf[rid]) A.B.ovf[rid] = OVF_INTV;
+                    R.n_intv = 0; R.intv_off = 0; rid = -1;
+                } else {
+                    const u32 *src = packed + rid * qw;
+                    for (int k = 0; k < qw; ++k) myq[k * 128] = src[k];
+                    IntvSink out; out.a = A.B.pool.intv + rid * stride; out.n = 0; out.cap = stride; out.overflow = false;
+                    m.init(A.opt, len, CAP, L, Q, out);
+                    m.start(A.ix);
+                }
             }
         }
         if (__all_sync(0xffffffffu, done)) break;
-        if (pending) {
-            extend_c(A.ix, f.req, f.req_c, f.req_back, f.res, ctr);
-            pending = seed_step(A.ix, A.opt, len, seq, out, f);
+        if (m.mode != 0) {
+            u64 a, o, s, na, no, ns; int c;
+            m.request(a, o, s, c);
+            extend_lean(A.ix, a, o, s, c, na, no, ns, ctr);
+            m.consume(A.ix, na, no, ns);
         }
     }
     flush_counters(ctr, A.ctrs);
 }
+
+// order each read's intervals by (start, end) -- the ks_introsort of mem_collect_intv (bwa/bwamem.c:186); equal keys are identical intervals
+__global__ void k_sort_intv(const ReadRec *__restrict__ rec, const u32 *__restrict__ ovf, i64 n, Intv *__restrict__ pool)
+{
+    i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || ovf[r]) return;
+    sort_intv_by_info(pool + rec[r].intv_off, rec[r].n_intv);
+}
+__global__ void k_set_u64(unsigned long long *p, unsigned long long v) { *p = v; }
 
 // stage 2 with G lanes per read (see extend_group.cuh); a warp claims 32/G reads at a time
 template <int G>
@@ -305,7 +354,7 @@ struct Engine {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8];
     // chunk buffers
-    DevBuf seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
+    DevBuf packed, seedflag, seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
     DevBuf p_intv, p_chain, p_seed, p_reg, p_hit, p_cigar, p_md;
     DevBuf nh, nc, nm, oh, oc, om, cubtmp, o_hit_off, o_hits, o_cigar, o_md;
     double pool_scale = 1.0;
@@ -351,12 +400,41 @@ static void launch_stage(Engine &E, KArgs &A, int grid)
     CU_CHECK(cudaGetLastError());
 }
 
+// Main-pass seeding with k_seed2: usable for batches of short reads on indexes below 2^36 symbols.
+static const int SEED2_CAP = 24;          // work-list entries per read in shared memory
+static const int SEED2_STRIDE = 40;       // interval slots per read in the pool
+static bool seed2_enabled() { static int on = getenv("B200_SEED_V1") ? 0 : 1; return on != 0; }
+static bool seed2_usable(const KArgs &A)
+{
+    return seed2_enabled() && !A.order && A.caps.maxlen <= 256 && A.ix.seq_len < (1ull << 36) && A.B.pool.cap[POOL_INTV] >= A.B.n_reads * (i64)SEED2_STRIDE;
+}
+static void launch_seed2(Engine &E, KArgs &A)
+{
+    const i64 n = A.n_work;
+    const int qw = (A.caps.maxlen + 15) / 16;
+    E.packed.reserve((size_t)n * qw * 4 + 64); E.seedflag.reserve((size_t)n * 4 + 64);
+    CU_CHECK(cudaMemsetAsync(E.seedflag.p, 0, (size_t)n * 4, E.st));
+    k_pack_reads<<<(unsigned)((n * qw + 255) / 256), 256, 0, E.st>>>(A.B.seq, A.B.seq_off, n, qw, E.packed.as<u32>(), E.seedflag.as<u32>());
+    k_set_u64<<<1, 1, 0, E.st>>>(A.B.pool.used + POOL_INTV, (unsigned long long)(n * SEED2_STRIDE));   // spill-pass allocations start after the fixed slots
+    size_t smem = (size_t)128 * (SEED2_CAP * 16 + qw * 4);
+    static bool attr = false;
+    if (!attr) { CU_CHECK(cudaFuncSetAttribute(k_seed2<SEED2_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+    int per = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<SEED2_CAP>, 128, smem));
+    if (per < 1) per = 1;
+    CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
+    k_seed2<SEED2_CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
+    CU_CHECK(cudaGetLastError());
+    k_sort_intv<<<(unsigned)((n + 127) / 128), 128, 0, E.st>>>(A.B.rec, A.B.ovf, n, A.B.pool.intv);
+    CU_CHECK(cudaGetLastError());
+    E.stats.n_launches += 3;
+}
+
 // Runs the four stages over `n_work` reads (all reads of the chunk, or the spill list).
 static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
 {
     int g[4];
-    if (!spill) { { int perf = 0; CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perf, k_seed_fsm, 128, 0)); g[0] = E.sms * (perf < 1 ? 1 : perf); }
-                  if (!getenv("B200_SEED_FSM")) g[0] = stage_grid<0>(E.sms); g[1] = stage_grid<1>(E.sms); g[2] = stage_grid<2>(E.sms); g[3] = stage_grid<3>(E.sms); }
+    if (!spill) { g[0] = stage_grid<0>(E.sms); g[1] = stage_grid<1>(E.sms); g[2] = stage_grid<2>(E.sms); g[3] = stage_grid<3>(E.sms); }
     else g[0] = g[1] = g[2] = g[3] = std::max<int>(1, (int)std::min<i64>((A.n_work + 127) / 128, 8));
     Caps tc = A.caps;
     if (A.B.dp_jobs) tc.z = 64;          // gapped hits go to k_finalize_dp, the thread-per-read stage needs no direction matrix
@@ -368,14 +446,8 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
     A.scratch = S.as<u8>(); A.scratch_stride = stride;
     cudaEvent_t *ev = E.ev;
     CU_CHECK(cudaEventRecord(ev[0], E.st));
-    {
-        static int fsm_ok = getenv("B200_SEED_FSM") ? 1 : 0;
-        if (fsm_ok) {
-            CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
-            k_seed_fsm<<<g[0], 128, 0, E.st>>>(A);
-            CU_CHECK(cudaGetLastError());
-        } else launch_stage<0>(E, A, g[0]);
-    }
+    if (!spill && seed2_usable(A)) launch_seed2(E, A);
+    else launch_stage<0>(E, A, g[0]);
     CU_CHECK(cudaEventRecord(ev[1], E.st));
     launch_stage<1>(E, A, g[1]); CU_CHECK(cudaEventRecord(ev[2], E.st));
     {
@@ -445,7 +517,7 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
     unsigned long long *d_small = E.small.as<unsigned long long>();   // [0]=work ctr, [1]=list count, [8..15]=pool used, [16..]=DevCounters
     for (int attempt = 0; attempt < 6; ++attempt) {
         double sc = E.pool_scale;
-        i64 cap[N_POOLS] = {(i64)(n * 24 * sc) + 65536, (i64)(n * 6 * sc) + 65536, (i64)(n * 24 * sc) + 65536, (i64)(n * 6 * sc) + 65536,
+        i64 cap[N_POOLS] = {(i64)(n * (seed2_enabled() ? SEED2_STRIDE + 8 : 24) * sc) + 65536, (i64)(n * 6 * sc) + 65536, (i64)(n * 24 * sc) + 65536, (i64)(n * 6 * sc) + 65536,
                             (i64)(n * 3 * sc) + 65536, (i64)(n * 12 * sc) + 65536, (i64)(n * 48 * sc) + 65536};
         E.p_intv.reserve(cap[POOL_INTV] * sizeof(Intv)); E.p_chain.reserve(cap[POOL_CHAIN] * sizeof(Chain)); E.p_seed.reserve(cap[POOL_SEED] * sizeof(Seed));
         E.p_reg.reserve(cap[POOL_REG] * sizeof(Reg)); E.p_hit.reserve(cap[POOL_HIT] * sizeof(b200_hit_t)); E.p_cigar.reserve(cap[POOL_CIGAR] * 4);
@@ -730,7 +802,7 @@ int b200_debug_collect_intv(const b200_index_t *idx, const b200_mem_opt_t *opt, 
         Engine &E = engine();
         Caps big = big_caps(b->maxlen, b->opt);
         E.ovf.reserve(n * 4 + 64); E.rec.reserve(n * sizeof(ReadRec) + 64); E.small.reserve(4096);
-        i64 cap = n * (i64)big.intv + 1024;
+        i64 cap = n * (i64)(big.intv + SEED2_STRIDE) + 1024;
         E.p_intv.reserve(cap * sizeof(Intv));
         CU_CHECK(cudaMemsetAsync(E.small.p, 0, 4096, E.st));
         k_clear_u32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n);
@@ -745,7 +817,20 @@ int b200_debug_collect_intv(const b200_index_t *idx, const b200_mem_opt_t *opt, 
         int grid = 8;
         E.spill_scratch.reserve(stride * grid * 128);
         A.scratch = E.spill_scratch.as<u8>(); A.scratch_stride = stride;
-        launch_stage<0>(E, A, grid);
+        if (seed2_usable(A) && !getenv("B200_DEBUG_SEED_V1")) {
+            // the production path: k_seed2 for every read it takes, the reference-shaped kernel for the rest
+            launch_seed2(E, A);
+            E.list.reserve(n * 4 + 64);
+            k_list_ovf<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n, 0xffffffffu, E.list.as<i32>(), d_small + 1);
+            unsigned long long n_sp = 0;
+            CU_CHECK(cudaMemcpyAsync(&n_sp, d_small + 1, 8, cudaMemcpyDeviceToHost, E.st));
+            CU_CHECK(cudaStreamSynchronize(E.st));
+            if (n_sp) {
+                k_clear_list<<<(unsigned)((n_sp + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), E.list.as<i32>(), (i64)n_sp);
+                KArgs S = A; S.order = E.list.as<i32>(); S.n_work = (i64)n_sp;
+                launch_stage<0>(E, S, grid);
+            }
+        } else launch_stage<0>(E, A, grid);
         std::vector<ReadRec> rec(n);
         CU_CHECK(cudaMemcpyAsync(rec.data(), E.rec.p, n * sizeof(ReadRec), cudaMemcpyDeviceToHost, E.st));
         CU_CHECK(cudaStreamSynchronize(E.st));

@@ -39,7 +39,7 @@ struct BlobHeader {          // first bytes of the device image
     i32 sa_shift, n_seqs;
     u64 off_occ, off_sa, off_text, off_coff, off_calt, off_names, names_bytes;
 };
-static const u64 BLOB_MAGIC = 0x3142303032424c42ull; // "BLB200B1"
+static const u64 BLOB_MAGIC = 0x3242303032424c42ull; // "BLB200B2" (B2: Occ symbols stored as two bit planes)
 
 struct ContigMeta { std::string name, anno; i64 offset; i32 len, n_ambs; u32 gi; i32 is_alt; };
 struct HoleMeta { i64 offset; i32 len; char amb; };

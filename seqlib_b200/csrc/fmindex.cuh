@@ -24,23 +24,14 @@ HD OccLoad load_block(const DevIndex &ix, u64 blk)
     return r;
 }
 
-// number of symbols equal to c among the lowest n (0..32) symbols of w
-HD int cnt_word(u64 w, int c, int n)
-{
-    u64 t = w ^ (0x5555555555555555ull * (u64)c);       // matching symbols become 00
-    u64 z = ~(t | (t >> 1)) & 0x5555555555555555ull;
-    u64 m = n >= 32 ? ~0ull : ((1ull << (2 * n)) - 1);
-    return popc64(z & m);
-}
-
-// counts of A,C,G,T in the first r (1..64) symbols of a loaded block, added to the block base
+// counts of A,C,G,T in the first r (1..64) symbols of a loaded block, added to the block base.
+// s0 / s1 are the low / high bit planes of the 64 symbols: three popcounts under one mask give all four counts.
 HD void block_rank4(const OccLoad &b, int r, u64 cnt[4])
 {
-    int n0 = r < 32 ? r : 32, n1 = r - n0;
-    int a = cnt_word(b.s0, 0, n0) + cnt_word(b.s1, 0, n1);
-    int c = cnt_word(b.s0, 1, n0) + cnt_word(b.s1, 1, n1);
-    int g = cnt_word(b.s0, 2, n0) + cnt_word(b.s1, 2, n1);
-    cnt[0] = b.c0 + a; cnt[1] = b.c1 + c; cnt[2] = b.c2 + g; cnt[3] = b.c3 + (r - a - c - g);
+    u64 m = r >= 64 ? ~0ull : ((1ull << r) - 1);
+    u64 lo = b.s0 & m, hi = b.s1 & m;
+    int pl = popc64(lo), ph = popc64(hi), pt = popc64(lo & hi);
+    cnt[0] = b.c0 + (u64)(r - pl - ph + pt); cnt[1] = b.c1 + (u64)(pl - pt); cnt[2] = b.c2 + (u64)(ph - pt); cnt[3] = b.c3 + (u64)pt;
 }
 
 // bwt_2occ4 (bwa/bwt.c:189-220) on ranks k <= l; k or l may be (u64)-1.
@@ -96,7 +87,7 @@ HD void set_intv(const DevIndex &ix, int c, Intv &ik)
 }
 
 // bwt_B0 (bwa/bwt.h:80): symbol x of the $-less BWT
-HD int bwt_sym(const OccLoad &b, int j) { return (int)(((j < 32 ? b.s0 : b.s1) >> (2 * (j & 31))) & 3); }
+HD int bwt_sym(const OccLoad &b, int j) { return (int)((b.s0 >> j) & 1) | (int)((b.s1 >> j) & 1) << 1; }
 
 // bwt_invPsi (bwa/bwt.c:53-59) with bwt_occ (bwa/bwt.c:107-129)
 template <class Ctr>

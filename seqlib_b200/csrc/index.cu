@@ -120,7 +120,7 @@ __global__ void k_occ_from_bwa(const u32 *__restrict__ bwt, u64 seq_len, OccBloc
             if (x0 + j >= seq_len) break;
             u32 v = w[j >> 4];
             u64 s = (v >> ((15 - (j & 15)) << 1)) & 3;
-            o.sym[j >> 5] |= s << (2 * (j & 31));
+            occ_set_sym(o, j, s);
         }
     } else {                                          // sentinel block past the end: totals
         // filled by the caller through L2 (kept zero symbols)
@@ -172,7 +172,7 @@ __global__ void k_bwa_from_occ(const OccBlock *__restrict__ occ, u64 seq_len, u3
             if (x >= seq_len) break;
             const OccBlock &b = occ[x >> 6];
             int jj = (int)(x & 63);
-            u32 s = (u32)((b.sym[jj >> 5] >> (2 * (jj & 31))) & 3);
+            u32 s = (u32)occ_sym(b, jj);
             v |= s << ((15 - k) << 1);
         }
         blk[8 + w] = v;

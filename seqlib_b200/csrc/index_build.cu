@@ -151,7 +151,7 @@ __global__ void k_pack_blocks(const u8 *__restrict__ bwt8, u64 N, u64 primary, O
         u64 f = x < primary ? x : x + 1;
         u64 s = bwt8[f];
         ++c.c[s];
-        if (j < 32) s0 |= s << (2 * j); else s1 |= s << (2 * (j - 32));
+        s0 |= (s & 1) << j; s1 |= (s >> 1) << j;
     }
     occ[b].sym[0] = s0; occ[b].sym[1] = s1;
     cnt[b] = c;
@@ -358,7 +358,7 @@ void build_fm_index_device(b200_index *idx, const BlobHeader &h)
     u64 totals[4] = {last.c[0], last.c[1], last.c[2], last.c[3]};
     {
         u64 x0 = (h.n_occ - 1) * 64;
-        for (u64 x = x0; x < N; ++x) { int j = (int)(x - x0); ++totals[(lb.sym[j >> 5] >> (2 * (j & 31))) & 3]; }
+        for (u64 x = x0; x < N; ++x) { int j = (int)(x - x0); ++totals[occ_sym(lb, j)]; }
     }
     idx->primary = primary;
     idx->L2[0] = 0;

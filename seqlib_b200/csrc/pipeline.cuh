@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "seed.cuh"
 #include "seed_fsm.cuh"
+#include "seed2.cuh"
 #include "chain.cuh"
 #include "extend.cuh"
 #include "finalize.cuh"
@@ -110,6 +111,27 @@ HD void stage_seed_t(const DevIndex &ix, const Opt &opt, const Caps &caps, const
 HD void stage_seed(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
 {
     stage_seed_t<false>(ix, opt, caps, B, rid, scratch, ctr);
+}
+
+// The single-extension-site machine of seed2.cuh with a `list_cap`-entry work list, falling back to the reference-shaped
+// loops when the read is not eligible or the list overflows: what k_seed2 + the spill pass compute together.
+HD void stage_seed_v2(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr, int list_cap)
+{
+    int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
+    const u8 *seq = B.seq + B.seq_off[rid];
+    ReadRec &R = B.rec[rid];
+    R.n_intv = 0; R.intv_off = 0;
+    if (B.ovf[rid]) return;
+    Intv *prev = (Intv *)scratch, *curr = prev + (caps.maxlen + 1);
+    IntvSink out; out.a = curr + (caps.maxlen + 1); out.n = 0; out.cap = caps.intv; out.overflow = false;
+    if (list_cap > caps.maxlen + 1) list_cap = caps.maxlen + 1;
+    bool ok = seed2_eligible(ix, len, seq) && collect_intv_v2(ix, opt, len, seq, out, (PIntv *)prev, list_cap, ctr);
+    if (!ok && !out.overflow) { out.n = 0; if (len >= opt.min_seed_len) collect_intv(ix, opt, len, seq, out, prev, curr, ctr); }
+    if (out.overflow) { B.ovf[rid] |= OVF_INTV; return; }
+    i64 off = pool_alloc(B.pool, POOL_INTV, out.n);
+    if (off < 0) { B.ovf[rid] |= OVF_POOL; return; }
+    for (int i = 0; i < out.n; ++i) B.pool.intv[off + i] = out.a[i];
+    R.n_intv = out.n; R.intv_off = off;
 }
 
 // ------------------------------------------------------------------ chain

@@ -1,0 +1,278 @@
+// seed2.cuh -- mem_collect_intv (bwa/bwamem.c:140-188) shaped for the GPU: one extension site.
+//
+// seed.cuh states SMEM seeding as the reference does (bwt_smem1a / bwt_seed_strategy1, bwa/bwt.c:289-379): nested
+// loops with bwt_extend in three places, two work lists of 32-byte intervals per read in scratch memory.  Profiled on
+// a B200 that shape is bound by instruction issue (a third of the lanes active) and by scratch traffic, not by the
+// Occ gathers.  Here the same computation is a small machine that yields every extension:
+//
+//     request(a, o, s, c)  ->  extend_lean  ->  consume(na, no, ns)
+//
+// so a warp has ONE place where the two dependent 32-byte Occ gathers and the popcounts happen, reached by all lanes
+// together.  The work list is a single array of 16-byte packed intervals (coordinates < 2^36, end < 2^16) that the
+// forward sweep fills from the top down -- it is born reversed, as the reference wants it after its in-place
+// reversal -- and that the backward sweep compacts in place (row i+1 never has more survivors than row i read so
+// far).  The caller keeps that list in shared memory.  SMEMs shorter than min_seed_len are dropped when they are
+// produced (the reference drops them after each bwt_smem1 call; the "is this SMEM contained in the previous one"
+// test uses the unfiltered start, kept in a register).  Intervals leave in production order; the final order is
+// the sort by (start, end), done by the caller -- equal keys mean the same substring and therefore identical
+// intervals, so the reference's unstable introsort cannot order them differently in any visible way.
+//
+// Restrictions (the caller routes everything else to seed.cuh): no base > 3 in the read, len < 65536,
+// seq_len < 2^36, and the list capacity.
+#pragma once
+#include "common.cuh"
+#include "fmindex.cuh"
+#include "seed.cuh"
+
+namespace b200 {
+
+struct PIntv { u32 w0, w1, w2, w3; };   // x0, x1, x2 low words; w3 = x0>>32 | (x1>>32)<<4 | (x2>>32)<<8 | end<<16
+
+HD PIntv pintv_pack(u64 x0, u64 x1, u64 x2, u32 end)
+{
+    PIntv p;
+    p.w0 = (u32)x0; p.w1 = (u32)x1; p.w2 = (u32)x2;
+    p.w3 = (u32)(x0 >> 32) | (u32)(x1 >> 32) << 4 | (u32)(x2 >> 32) << 8 | end << 16;
+    return p;
+}
+HD void pintv_unpack(const PIntv &p, u64 &x0, u64 &x1, u64 &x2, u32 &end)
+{
+    x0 = (u64)p.w0 | (u64)(p.w3 & 15u) << 32;
+    x1 = (u64)p.w1 | (u64)((p.w3 >> 4) & 15u) << 32;
+    x2 = (u64)p.w2 | (u64)((p.w3 >> 8) & 15u) << 32;
+    end = p.w3 >> 16;
+}
+
+// bwt_extend (bwa/bwt.c:262-275) for the one child the callers use, on raw coordinates:
+//   a = the coordinate the Occ ranks are taken on (x[!is_back]), o = the other one, s = interval size.
+// Ranks a-1 and a-1+s are never -1 here (every interval starts at L2[c]+1 >= 1).
+template <class Ctr>
+HD void extend_lean(const DevIndex &ix, u64 a, u64 o, u64 s, int c, u64 &na, u64 &no, u64 &ns, Ctr &ctr)
+{
+    const u64 k = a - 1, l = k + s;
+    const u32 dk = k >= ix.primary, dl = l >= ix.primary;
+    const u64 kk = k - dk, ll = l - dl;
+    const u64 bk = kk >> 6, bl = ll >> 6;
+    OccLoad b1 = load_block(ix, bk);
+    OccLoad b2 = b1;
+    if (bl != bk) b2 = load_block(ix, bl);
+    ctr.occ_blocks += bl != bk ? 2 : 1;
+    const int rk = (int)(kk & 63), rl = (int)(ll & 63);          // ranks inside the block, minus one
+    const u64 mk = (2ull << rk) - 1, ml = (2ull << rl) - 1;      // rk == 63: 2<<63 wraps to 0, minus 1 = all ones
+    const u64 klo = b1.s0 & mk, khi = b1.s1 & mk, llo = b2.s0 & ml, lhi = b2.s1 & ml;
+    const u32 kpl = popc64(klo), kph = popc64(khi), kpt = popc64(klo & khi);
+    const u32 lpl = popc64(llo), lph = popc64(lhi), lpt = popc64(llo & lhi);
+    // counts of C, G, T up to k and up to l (A only where needed)
+    const u32 tk1 = b1.c1 + (kpl - kpt), tk2 = b1.c2 + (kph - kpt), tk3 = b1.c3 + kpt;
+    const u32 tl1 = b2.c1 + (lpl - lpt), tl2 = b2.c2 + (lph - lpt), tl3 = b2.c3 + lpt;
+    const u32 s1 = tl1 - tk1, s2 = tl2 - tk2, s3 = tl3 - tk3;
+    const u32 tk0 = b1.c0 + ((u32)rk + 1 - kpl - kph + kpt);
+    const u32 tl0 = b2.c0 + ((u32)rl + 1 - lpl - lph + lpt);
+    const u32 s0 = tl0 - tk0;
+    const u32 tkc = c == 0 ? tk0 : c == 1 ? tk1 : c == 2 ? tk2 : tk3;
+    const u32 sc = c == 0 ? s0 : c == 1 ? s1 : c == 2 ? s2 : s3;
+    const u64 gt = c == 0 ? (u64)s1 + s2 + s3 : c == 1 ? (u64)s2 + s3 : c == 2 ? (u64)s3 : 0ull;   // children > c come first on the other side
+    na = ix.L2[c] + 1 + tkc;
+    no = o + (dl - dk) + gt;        // dl - dk = 1 iff the '$' rank lies inside [a, a+s)
+    ns = sc;
+}
+
+// One read's seeding as a resumable machine.  List: get(e) / set(e, PIntv) over `cap` entries; Query: operator[](i) in 0..3.
+template <class List, class Query>
+struct SeedMachine {
+    enum { M_DONE = 0, M_FWD, M_BWD, M_P3, M_TASK, M_ENDFWD, M_LASTROW };
+    int mode, pass, x, k2, old_n, sx, i, j, nprev, ncurr, top, ret, last_start, first, ovf;
+    int len, cap, min_seed_len, split_len, split_width, max_intv3, min_intv;
+    u64 x0, x1, x2, lastcurr;     // ik of the forward sweeps / last size pushed in this backward row
+    u64 p0, p1, p2;               // the list entry being extended backwards
+    u32 iend, pend;
+    List L; Query q; IntvSink out;
+
+    HD void init(const Opt &opt, int len_, int cap_, const List &L_, const Query &q_, const IntvSink &out_)
+    {
+        len = len_; cap = cap_; L = L_; q = q_; out = out_;
+        min_seed_len = opt.min_seed_len;
+        split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
+        split_width = opt.split_width;
+        max_intv3 = (int)opt.max_mem_intv;
+        pass = 1; x = 0; k2 = 0; old_n = 0; ovf = 0; mode = M_DONE;
+        out.n = 0; out.overflow = false;
+    }
+
+    HD void fail() { ovf = 1; mode = M_DONE; }
+
+    HD void emit(u64 e0, u64 e1, u64 e2, u64 info)
+    {
+        Intv v; v.x0 = e0; v.x1 = e1; v.x2 = e2; v.info = info;
+        out.push(v);
+        if (out.overflow) fail();
+    }
+
+    HD void push_fwd()
+    {
+        if (top == 0) { fail(); return; }
+        L.set(--top, pintv_pack(x0, x1, x2, iend));
+        ret = (int)iend;
+    }
+
+    // Everything between two extensions that is not the per-extension bookkeeping: ending a forward sweep, the row
+    // i == -1 of a backward sweep, picking the next bwt_smem1 / bwt_seed_strategy1 call (bwa/bwamem.c:150-184).
+    // A loop over transient modes instead of mutually recursive helpers, so that it inlines and the state stays in registers.
+    HD void settle(const DevIndex &ix)
+    {
+        for (;;) {
+            if (mode == M_ENDFWD) {
+                nprev = cap - top; ncurr = 0; j = 0; first = 1; last_start = 0;
+                i = sx - 1;
+                mode = i < 0 ? M_LASTROW : M_BWD;
+            } else if (mode == M_LASTROW) {
+                // bwa/bwt.c:325-345 with c = -1: only the longest survivor can be reported, with start 0
+                if (first || 0 < last_start) {
+                    u64 e0, e1, e2; u32 e;
+                    pintv_unpack(L.get(top), e0, e1, e2, e);
+                    if ((int)e >= min_seed_len) { emit(e0, e1, e2, (u64)e); if (ovf) return; }
+                }
+                mode = M_TASK;
+                if (pass == 1) x = ret;
+            } else if (mode == M_TASK) {
+                if (pass == 1) {
+                    if (x >= len) { pass = 2; old_n = out.n; k2 = 0; }
+                    else { sx = x; min_intv = 1; }
+                }
+                if (pass == 2) {
+                    bool have = false;
+                    while (k2 < old_n) {
+                        const Intv p = out.a[k2++];
+                        int start = (int)(p.info >> 32), end = (int)(i32)p.info;
+                        if (end - start < split_len || p.x2 > (u64)split_width) continue;
+                        sx = (start + end) >> 1; min_intv = (int)p.x2 + 1;
+                        have = true;
+                        break;
+                    }
+                    if (!have) {
+                        pass = 3; x = 0;
+                        if (max_intv3 <= 0) { mode = M_DONE; return; }
+                    }
+                }
+                if (pass == 3) {
+                    if (x >= len) { mode = M_DONE; return; }
+                    Intv t; set_intv(ix, q[x], t);
+                    x0 = t.x0; x1 = t.x1; x2 = t.x2;
+                    i = x + 1;
+                    mode = i < len ? M_P3 : M_DONE;      // a start on the last base extends nothing and reports nothing
+                    return;
+                }
+                // begin the forward sweep of bwt_smem1a at sx
+                Intv t; set_intv(ix, q[sx], t);
+                x0 = t.x0; x1 = t.x1; x2 = t.x2; iend = (u32)(sx + 1);
+                top = cap;
+                i = sx + 1;
+                mode = M_FWD;
+                if (i >= len) { push_fwd(); if (ovf) return; mode = M_ENDFWD; }
+            } else return;
+        }
+    }
+
+    HD void start(const DevIndex &ix)
+    {
+        if (len < min_seed_len) { mode = M_DONE; return; }
+        mode = M_TASK;
+        settle(ix);
+    }
+
+    HD void request(u64 &a, u64 &o, u64 &s, int &c)
+    {
+        if (mode == M_BWD) {
+            pintv_unpack(L.get(top + j), p0, p1, p2, pend);
+            a = p0; o = p1; s = p2; c = q[i];
+        } else { a = x1; o = x0; s = x2; c = 3 - q[i]; }
+    }
+
+    HD void consume(const DevIndex &ix, u64 na, u64 no, u64 ns)
+    {
+        if (mode == M_BWD) {
+            if (ns < (u64)min_intv) {
+                if (ncurr == 0 && (first || i + 1 < last_start)) {
+                    first = 0; last_start = i + 1;
+                    if ((int)pend - (i + 1) >= min_seed_len) { emit(p0, p1, p2, (u64)(i + 1) << 32 | pend); if (ovf) return; }
+                }
+            } else if (ncurr == 0 || ns != lastcurr) {
+                L.set(top + ncurr, pintv_pack(na, no, ns, pend));
+                ++ncurr; lastcurr = ns;
+            }
+            if (++j == nprev) {
+                if (ncurr == 0) { mode = M_TASK; if (pass == 1) x = ret; }
+                else {
+                    nprev = ncurr; ncurr = 0; j = 0;
+                    if (--i < 0) mode = M_LASTROW;
+                }
+            }
+        } else if (mode == M_FWD) {
+            bool stop = false;
+            if (ns != x2) {
+                push_fwd();
+                if (ovf) return;
+                stop = ns < (u64)min_intv;
+            }
+            if (!stop) {
+                x1 = na; x0 = no; x2 = ns; iend = (u32)(i + 1);
+                if (++i == len) { push_fwd(); if (ovf) return; stop = true; }
+            }
+            if (stop) mode = M_ENDFWD;
+        } else {        // M_P3
+            if (ns < (u64)max_intv3 && i - x >= min_seed_len) {
+                if (ns > 0) { emit(no, na, ns, (u64)x << 32 | (u64)(i + 1)); if (ovf) return; }
+                x = i + 1;
+                mode = M_TASK;
+            } else {
+                x1 = na; x0 = no; x2 = ns;
+                if (++i >= len) mode = M_DONE;
+            }
+        }
+        if (mode > M_P3) settle(ix);
+    }
+};
+
+// plain-array list / byte query: the host emulation and the debug path
+struct ArrayList { PIntv *p; HD PIntv get(int e) const { return p[e]; } HD void set(int e, const PIntv &v) { p[e] = v; } };
+struct ByteQuery { const u8 *p; HD int operator[](int i) const { return p[i]; } };
+
+HD bool seed2_eligible(const DevIndex &ix, int len, const u8 *seq)
+{
+    if (len >= 65536 || ix.seq_len >= (1ull << 36)) return false;
+    for (int i = 0; i < len; ++i) if (seq[i] > 3) return false;
+    return true;
+}
+
+HD void sort_intv_by_info(Intv *a, int n)
+{
+    for (int i = 1; i < n; ++i) {
+        Intv v = a[i];
+        int j = i;
+        for (; j > 0 && v.info < a[j - 1].info; --j) a[j] = a[j - 1];
+        a[j] = v;
+    }
+}
+
+// scalar driver: same results as collect_intv() for eligible reads; returns false when the list capacity was exceeded
+template <class Ctr>
+HD bool collect_intv_v2(const DevIndex &ix, const Opt &opt, int len, const u8 *seq, IntvSink &out, PIntv *list, int cap, Ctr &ctr)
+{
+    SeedMachine<ArrayList, ByteQuery> m;
+    ArrayList L; L.p = list;
+    ByteQuery q; q.p = seq;
+    m.init(opt, len, cap, L, q, out);
+    m.start(ix);
+    while (m.mode != 0) {
+        u64 a, o, s, na, no, ns; int c;
+        m.request(a, o, s, c);
+        extend_lean(ix, a, o, s, c, na, no, ns, ctr);
+        m.consume(ix, na, no, ns);
+    }
+    out = m.out;
+    if (m.ovf) return false;
+    sort_intv_by_info(out.a, out.n);
+    return true;
+}
+
+} // namespace b200

@@ -32,7 +32,7 @@ struct HostIndex {
                 // bwt_B0 (bwa/bwt.h:74-80)
                 u32 wv = v.bwt[((x >> 7) << 4) + 8 + ((x & 0x7f) >> 4)];
                 int s = (wv >> ((~x & 0xf) << 1)) & 3;
-                o.sym[j >> 5] |= (u64)s << (2 * (j & 31));
+                occ_set_sym(o, j, (u64)s);
                 ++run[s];
             }
         }

@@ -71,6 +71,7 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
     B.pool.cap[POOL_INTV] = p_intv.size(); B.pool.cap[POOL_CHAIN] = p_chain.size(); B.pool.cap[POOL_SEED] = p_seed.size();
     B.pool.cap[POOL_REG] = p_reg.size(); B.pool.cap[POOL_HIT] = p_hit.size(); B.pool.cap[POOL_CIGAR] = p_cig.size(); B.pool.cap[POOL_MD] = p_md.size();
     bool dbg = getenv("HOSTSIM_DEBUG") != 0;
+    int seed_v2 = getenv("HOSTSIM_SEED_V2") ? atoi(getenv("HOSTSIM_SEED_V2")) : 0;   // list capacity of the seed2.cuh machine, 0 = seed_fsm
     std::vector<std::vector<Reg> > raws(n);
     for (int64_t r = 0; r < n; ++r) {
         for (int pass = 0; pass < 2; ++pass) {
@@ -79,7 +80,8 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
             std::vector<u8> s1(seed_scratch_bytes(c) + 64), s2(chain_scratch_bytes(c) + 64), s3(extend_scratch_bytes(c) + 64), s4(finalize_scratch_bytes(c) + 64);
             ovf[r] = 0;
             if (dbg) fprintf(stderr, "read %ld pass %d\n", (long)r, pass);
-            stage_seed(ix, opt, c, B, r, s1.data(), ctr);
+            if (seed_v2) stage_seed_v2(ix, opt, c, B, r, s1.data(), ctr, seed_v2);
+            else stage_seed(ix, opt, c, B, r, s1.data(), ctr);
             stage_chain(ix, opt, c, B, r, s2.data(), ctr);
             stage_extend(ix, opt, c, B, r, s3.data(), ctr);
             raws[r].assign(B.pool.regs + rec[r].reg_off, B.pool.regs + rec[r].reg_off + rec[r].n_regs);
