@@ -174,8 +174,8 @@ __global__ void k_sort_intv(const ReadRec *__restrict__ rec, const u32 *__restri
 __global__ void k_set_u64(unsigned long long *p, unsigned long long v) { *p = v; }
 
 // stage 2 with G lanes per read (see extend_group.cuh); a warp claims 32/G reads at a time
-template <int G>
-__global__ void __launch_bounds__(128) k_extend_group(const __grid_constant__ KArgs A)
+template <int G, bool REG>
+__global__ void __launch_bounds__(128, REG ? 4 : 3) k_extend_group(const __grid_constant__ KArgs A)
 {
     extern __shared__ __align__(16) u8 smem_raw[];
     __shared__ i8 smat[32];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) k_extend_group(const __grid_constant__ KA
     GroupCtx<G> g;
     g.gl = threadIdx.x % G;
     g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    u8 *smem = smem_raw + (size_t)gib * group_smem_bytes(A.caps.maxlen);
+    u8 *smem = REG ? smem_raw : smem_raw + (size_t)gib * group_smem_bytes(A.caps.maxlen);
     u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
     CtrLocal ctr;
     for (;;) {
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) k_extend_group(const __grid_constant__ KA
         i64 w = (i64)base + lane / G;
         if (w < A.n_work) {
             i64 rid = A.order ? A.order[w] : w;
-            stage_extend_group<G>(g, A.ix, A.opt, A.caps, A.B, rid, scr, smem, smat, ctr);
+            stage_extend_group<G, REG>(g, A.ix, A.opt, A.caps, A.B, rid, scr, smem, smat, ctr);
         }
         __syncwarp();
     }
@@ -368,6 +368,7 @@ struct Engine {
         device = d;
         CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
         CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (const char *g = getenv("B200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
         for (int i = 0; i < 8; ++i) CU_CHECK(cudaEventCreate(&ev[i]));
         memset(&stats, 0, sizeof(stats));
     }
@@ -408,6 +409,16 @@ static bool seed2_usable(const KArgs &A)
 {
     return seed2_enabled() && !A.order && A.caps.maxlen <= 256 && A.ix.seq_len < (1ull << 36) && A.B.pool.cap[POOL_INTV] >= A.B.n_reads * (i64)SEED2_STRIDE;
 }
+template <int CAP>
+static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
+{
+    size_t smem = (size_t)128 * (CAP * 16 + qw * 4);
+    CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    int per = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP>, 128, smem));
+    if (per < 1) per = 1;
+    k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
+}
 static void launch_seed2(Engine &E, KArgs &A)
 {
     const i64 n = A.n_work;
@@ -416,14 +427,11 @@ static void launch_seed2(Engine &E, KArgs &A)
     CU_CHECK(cudaMemsetAsync(E.seedflag.p, 0, (size_t)n * 4, E.st));
     k_pack_reads<<<(unsigned)((n * qw + 255) / 256), 256, 0, E.st>>>(A.B.seq, A.B.seq_off, n, qw, E.packed.as<u32>(), E.seedflag.as<u32>());
     k_set_u64<<<1, 1, 0, E.st>>>(A.B.pool.used + POOL_INTV, (unsigned long long)(n * SEED2_STRIDE));   // spill-pass allocations start after the fixed slots
-    size_t smem = (size_t)128 * (SEED2_CAP * 16 + qw * 4);
-    static bool attr = false;
-    if (!attr) { CU_CHECK(cudaFuncSetAttribute(k_seed2<SEED2_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
-    int per = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<SEED2_CAP>, 128, smem));
-    if (per < 1) per = 1;
+    static int cap_sel = getenv("B200_SEED_CAP") ? atoi(getenv("B200_SEED_CAP")) : SEED2_CAP;
     CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
-    k_seed2<SEED2_CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
+    if (cap_sel == 16) launch_seed2_cap<16>(E, A, qw);
+    else if (cap_sel == 32) launch_seed2_cap<32>(E, A, qw);
+    else launch_seed2_cap<SEED2_CAP>(E, A, qw);
     CU_CHECK(cudaGetLastError());
     k_sort_intv<<<(unsigned)((n + 127) / 128), 128, 0, E.st>>>(A.B.rec, A.B.ovf, n, A.B.pool.intv);
     CU_CHECK(cudaGetLastError());
@@ -452,12 +460,17 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
     launch_stage<1>(E, A, g[1]); CU_CHECK(cudaEventRecord(ev[2], E.st));
     {
         const int G = 8;
-        size_t smem = (size_t)(128 / G) * group_smem_bytes(A.caps.maxlen);
+        static int reg_ok = getenv("B200_EXTEND_SMEM") ? 0 : 1;
+        const bool use_reg = reg_ok && A.caps.maxlen + 1 <= G * EXT_REG_CMAX;      // DP state in registers (ksw_reg.cuh)
+        size_t smem = use_reg ? 0 : (size_t)(128 / G) * group_smem_bytes(A.caps.maxlen);
         static int group_ok = getenv("B200_SCALAR_EXTEND") ? 0 : 1;
         if (group_ok && smem <= 200 * 1024) {
             int per = 0;
-            CU_CHECK(cudaFuncSetAttribute(k_extend_group<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_group<G>, 128, smem));
+            if (use_reg) CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_group<G, true>, 128, 0));
+            else {
+                CU_CHECK(cudaFuncSetAttribute(k_extend_group<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_group<G, false>, 128, smem));
+            }
             if (per < 1) per = 1;
             int grid = (int)std::min<i64>((i64)E.sms * per, std::max<i64>(1, (A.n_work + (128 / G) - 1) / (128 / G)));
             size_t gstride = (extend_group_scratch_bytes(A.caps) + 63) & ~(size_t)63;
@@ -474,7 +487,8 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
                 A2.order = E.sort_vals2.as<i32>();
             }
             CU_CHECK(cudaMemsetAsync(A2.work_ctr, 0, 8, E.st));
-            k_extend_group<G><<<grid, 128, smem, E.st>>>(A2);
+            if (use_reg) k_extend_group<G, true><<<grid, 128, 0, E.st>>>(A2);
+            else k_extend_group<G, false><<<grid, 128, smem, E.st>>>(A2);
             CU_CHECK(cudaGetLastError());
         } else launch_stage<2>(E, A, g[2]);
     }

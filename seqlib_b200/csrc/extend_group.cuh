@@ -5,13 +5,16 @@
 #pragma once
 #include "pipeline.cuh"
 #include "ksw_group.cuh"
+#include "ksw_reg.cuh"
 
 namespace b200 {
 
 // per-group shared memory: H[maxlen+2], E[maxlen+2] ints, then the read as bytes (maxlen, padded to 4)
 __host__ __device__ inline size_t group_smem_bytes(int maxlen) { return (size_t)(maxlen + 2) * 8 + (size_t)((maxlen + 4) & ~3); }
 
-template <int G, class Ctr>
+// REG: the DP state lives in registers (ksw_reg.cuh; reads of at most G * EXT_REG_CMAX - 1 bases), else in shared memory (ksw_group.cuh)
+#define EXT_REG_CMAX 19
+template <int G, bool REG, class Ctr>
 __device__ void chain2aln_group(const GroupCtx<G> &g, const DevIndex &ix, const Opt &opt, const i8 *smat, int l_query, const u8 *query,
                                 const Seed *cs, int cn, int c_rid, float c_frac_rep, RegSink &av, u64 *srt, int *H, int *E, Ctr &ctr)
 {
@@ -86,40 +89,78 @@ __device__ void chain2aln_group(const GroupCtx<G> &g, const DevIndex &ix, const 
         a.w = aw[0] = aw[1] = opt.w;
         a.score = a.truesc = -1;
         a.rid = c_rid;
+        if (REG) {
+            // Left and right extension share ONE call site: a group takes its pending sides in order (left first, the
+            // right extension starts from the left one's score), so groups of a warp that are on different sides of
+            // their seeds still run the DP rows together.
+            const int qe = s.qbeg + s.len;
+            const i64 re = s.rbeg + s.len - rmax[0];
+            if (!s.qbeg) { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
+            if (qe == l_query) { a.qe = l_query; a.re = s.rbeg + s.len; }
+            int pending = (s.qbeg ? 1 : 0) | (qe != l_query ? 2 : 0);
+            while (pending) {
+                const int side = (pending & 1) ? 0 : 1;
+                pending &= ~(1 << side);
+                const int sc0 = side ? a.score : s.len * opt.a;
+                const int ql = side ? l_query - qe : s.qbeg;
+                const int tl = side ? (int)(rmax[1] - rmax[0] - re) : (int)(s.rbeg - rmax[0]);
+                const int pen = side ? opt.pen_clip3 : opt.pen_clip5;
+                BytesSeq qs; qs.p = side ? query + qe : query + s.qbeg - 1; qs.step = side ? 1 : -1;
+                int qle = 0, tle = 0, gtle = 0, gscore = 0;
+#pragma unroll 1
+                for (i = 0; i < B200_MAX_BAND_TRY; ++i) {
+                    int prev = a.score;
+                    aw[side] = opt.w << i;
+                    TextSeqC rc(&ix, side ? rmax[0] + re : s.rbeg - 1, side ? 1 : -1);
+                    ExtResult r = extend2_reg<G, EXT_REG_CMAX>(g, ql, qs, tl, rc, smat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[side], pen, opt.zdrop, sc0, ctr);
+                    a.score = r.score; qle = r.qle; tle = r.tle; gtle = r.gtle; gscore = r.gscore; max_off[side] = r.max_off;
+                    if (a.score == prev || max_off[side] < (aw[side] >> 1) + (aw[side] >> 2)) break;
+                }
+                const bool local = gscore <= 0 || gscore <= a.score - pen;
+                if (side == 0) {
+                    if (local) { a.qb = s.qbeg - qle; a.rb = s.rbeg - tle; a.truesc = a.score; }
+                    else { a.qb = 0; a.rb = s.rbeg - gtle; a.truesc = gscore; }
+                } else {
+                    if (local) { a.qe = qe + qle; a.re = rmax[0] + re + tle; a.truesc += a.score - sc0; }
+                    else { a.qe = l_query; a.re = rmax[0] + re + gtle; a.truesc += gscore - sc0; }
+                }
+            }
+        } else {
         if (s.qbeg) {
-            int qle = 0, tle = 0, gtle = 0, gscore = 0;
-            tmp = s.rbeg - rmax[0];
-            BytesSeq qs; qs.p = query + s.qbeg - 1; qs.step = -1;
-            TextSeq rs; rs.ix = &ix; rs.pos = s.rbeg - 1; rs.step = -1;
-            for (i = 0; i < B200_MAX_BAND_TRY; ++i) {
-                int prev = a.score;
-                aw[0] = opt.w << i;
-                ExtResult r = extend2_group(g, s.qbeg, qs, (int)tmp, rs, smat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins,
-                                            aw[0], opt.pen_clip5, opt.zdrop, s.len * opt.a, H, E, ctr);
-                a.score = r.score; qle = r.qle; tle = r.tle; gtle = r.gtle; gscore = r.gscore; max_off[0] = r.max_off;
-                if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
-            }
-            if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) { a.qb = s.qbeg - qle; a.rb = s.rbeg - tle; a.truesc = a.score; }
-            else { a.qb = 0; a.rb = s.rbeg - gtle; a.truesc = gscore; }
-        } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
-        if (s.qbeg + s.len != l_query) {
-            int qle = 0, tle = 0, qe, gtle = 0, gscore = 0, sc0 = a.score;
-            i64 re;
-            qe = s.qbeg + s.len;
-            re = s.rbeg + s.len - rmax[0];
-            BytesSeq qs; qs.p = query + qe; qs.step = 1;
-            TextSeq rs; rs.ix = &ix; rs.pos = rmax[0] + re; rs.step = 1;
-            for (i = 0; i < B200_MAX_BAND_TRY; ++i) {
-                int prev = a.score;
-                aw[1] = opt.w << i;
-                ExtResult r = extend2_group(g, l_query - qe, qs, (int)(rmax[1] - rmax[0] - re), rs, smat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins,
-                                            aw[1], opt.pen_clip3, opt.zdrop, sc0, H, E, ctr);
-                a.score = r.score; qle = r.qle; tle = r.tle; gtle = r.gtle; gscore = r.gscore; max_off[1] = r.max_off;
-                if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
-            }
-            if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) { a.qe = qe + qle; a.re = rmax[0] + re + tle; a.truesc += a.score - sc0; }
-            else { a.qe = l_query; a.re = rmax[0] + re + gtle; a.truesc += gscore - sc0; }
-        } else { a.qe = l_query; a.re = s.rbeg + s.len; }
+                int qle = 0, tle = 0, gtle = 0, gscore = 0;
+                tmp = s.rbeg - rmax[0];
+                BytesSeq qs; qs.p = query + s.qbeg - 1; qs.step = -1;
+                TextSeq rs; rs.ix = &ix; rs.pos = s.rbeg - 1; rs.step = -1;
+                for (i = 0; i < B200_MAX_BAND_TRY; ++i) {
+                    int prev = a.score;
+                    aw[0] = opt.w << i;
+                    ExtResult r = extend2_group(g, s.qbeg, qs, (int)tmp, rs, smat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins,
+                                                aw[0], opt.pen_clip5, opt.zdrop, s.len * opt.a, H, E, ctr);
+                    a.score = r.score; qle = r.qle; tle = r.tle; gtle = r.gtle; gscore = r.gscore; max_off[0] = r.max_off;
+                    if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
+                }
+                if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) { a.qb = s.qbeg - qle; a.rb = s.rbeg - tle; a.truesc = a.score; }
+                else { a.qb = 0; a.rb = s.rbeg - gtle; a.truesc = gscore; }
+            } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
+            if (s.qbeg + s.len != l_query) {
+                int qle = 0, tle = 0, qe, gtle = 0, gscore = 0, sc0 = a.score;
+                i64 re;
+                qe = s.qbeg + s.len;
+                re = s.rbeg + s.len - rmax[0];
+                BytesSeq qs; qs.p = query + qe; qs.step = 1;
+                TextSeq rs; rs.ix = &ix; rs.pos = rmax[0] + re; rs.step = 1;
+                for (i = 0; i < B200_MAX_BAND_TRY; ++i) {
+                    int prev = a.score;
+                    aw[1] = opt.w << i;
+                    ExtResult r = extend2_group(g, l_query - qe, qs, (int)(rmax[1] - rmax[0] - re), rs, smat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins,
+                                                aw[1], opt.pen_clip3, opt.zdrop, sc0, H, E, ctr);
+                    a.score = r.score; qle = r.qle; tle = r.tle; gtle = r.gtle; gscore = r.gscore; max_off[1] = r.max_off;
+                    if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
+                }
+                if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) { a.qe = qe + qle; a.re = rmax[0] + re + tle; a.truesc += a.score - sc0; }
+                else { a.qe = l_query; a.re = rmax[0] + re + gtle; a.truesc += gscore - sc0; }
+            } else { a.qe = l_query; a.re = s.rbeg + s.len; }
+        }
         for (i = 0, a.seedcov = 0; i < cn; ++i) {
             const Seed &t = cs[i];
             if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
@@ -134,7 +175,7 @@ __device__ void chain2aln_group(const GroupCtx<G> &g, const DevIndex &ix, const 
 }
 
 // One group handles read `rid`.  scratch: per-group slot in HBM (srt + region list); smem: per-group shared memory.
-template <int G>
+template <int G, bool REG>
 __device__ void stage_extend_group(const GroupCtx<G> &g, const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid,
                                    u8 *scratch, u8 *smem, const i8 *smat, CtrLocal &ctr)
 {
@@ -143,8 +184,12 @@ __device__ void stage_extend_group(const GroupCtx<G> &g, const DevIndex &ix, con
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
     const u8 *seq = B.seq + B.seq_off[rid];
     int *H = (int *)smem, *E = H + (caps.maxlen + 2);
-    u8 *q = (u8 *)(E + (caps.maxlen + 2));
-    for (int j = g.gl; j < len; j += G) q[j] = seq[j];
+    const u8 *q = seq;                           // REG: the read is touched once per extension, straight from HBM
+    if (!REG) {
+        u8 *qs = (u8 *)(E + (caps.maxlen + 2));
+        for (int j = g.gl; j < len; j += G) qs[j] = seq[j];
+        q = qs;
+    }
     u8 *p = scratch;
     u64 *srt = (u64 *)p; p += sizeof(u64) * (size_t)caps.seeds;
     RegSink av; av.a = (Reg *)p; av.n = 0; av.cap = caps.regs; av.overflow = false;
@@ -154,7 +199,7 @@ __device__ void stage_extend_group(const GroupCtx<G> &g, const DevIndex &ix, con
     int n_chains = R.n_chains;
     float frac = R.frac_rep;
     for (int i = 0; i < n_chains; ++i) {
-        chain2aln_group(g, ix, opt, smat, len, q, os + oc[i].head, oc[i].n, oc[i].rid, frac, av, srt, H, E, ctr);
+        chain2aln_group<G, REG>(g, ix, opt, smat, len, q, os + oc[i].head, oc[i].n, oc[i].rid, frac, av, srt, H, E, ctr);
         if (av.overflow) { if (g.gl == 0) { B.ovf[rid] |= OVF_REG; R.n_regs = 0; R.reg_off = 0; } return; }
     }
     i64 off = 0;

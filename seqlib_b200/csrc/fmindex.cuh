@@ -12,10 +12,12 @@ HD OccLoad load_block(const DevIndex &ix, u64 blk)
 {
     OccLoad r;
 #if defined(__CUDA_ARCH__)
-    const uint4 *p = reinterpret_cast<const uint4 *>(ix.occ + blk);
-    uint4 a = __ldg(p), b = __ldg(p + 1);
-    r.c0 = a.x; r.c1 = a.y; r.c2 = a.z; r.c3 = a.w;
-    r.s0 = (u64)b.x | (u64)b.y << 32; r.s1 = (u64)b.z | (u64)b.w << 32;
+    // one 256-bit load (LDG.E.256 on sm_100a): the block is one 32-byte sector, so one request per rank query
+    u32 a0, a1, a2, a3, b0, b1, b2, b3;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "l"(ix.occ + blk));
+    r.c0 = a0; r.c1 = a1; r.c2 = a2; r.c3 = a3;
+    r.s0 = (u64)b0 | (u64)b1 << 32; r.s1 = (u64)b2 | (u64)b3 << 32;
 #else
     const OccBlock &b = ix.occ[blk];
     r.c0 = b.cnt[0]; r.c1 = b.cnt[1]; r.c2 = b.cnt[2]; r.c3 = b.cnt[3];

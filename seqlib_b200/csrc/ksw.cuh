@@ -28,6 +28,26 @@ struct TextSeq {
     HD int operator[](int i) const { return text_base(*ix, pos + (i64)i * step); }
 };
 
+// the same window with the current 32-base word kept in registers: one load per 32 rows instead of one per row
+struct TextSeqC {
+    const DevIndex *ix; i64 pos; int step;
+    mutable u64 w; mutable i64 wi;
+    HD TextSeqC(const DevIndex *ix_, i64 pos_, int step_) : ix(ix_), pos(pos_), step(step_), w(0), wi(-1) {}
+    HD int operator[](int i) const
+    {
+        i64 p = pos + (i64)i * step;
+        if ((p >> 5) != wi) {
+            wi = p >> 5;
+#if defined(__CUDA_ARCH__)
+            w = __ldg(ix->text + wi);
+#else
+            w = ix->text[wi];
+#endif
+        }
+        return (int)((w >> (2 * (p & 31))) & 3);
+    }
+};
+
 template <class QSeq, class TSeq, class Ctr>
 HD ExtResult extend2(int qlen, const QSeq &query, int tlen, const TSeq &target, const i8 *mat,
                      int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,

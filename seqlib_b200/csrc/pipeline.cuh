@@ -177,10 +177,25 @@ HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const 
     }
     R.n_chains = n; R.n_seeds = ns; R.chain_off = coff; R.seed_off = soff;
     R.frac_rep = (float)l_rep / len;
-    if (B.work) {       // query bases left to extend, summed over the seeds that will be tried (scheduling hint only)
+    if (B.work) {
+        // Scheduling hint only (20 bits, sorted descending): the extension kernel runs four reads per warp in lock step
+        // and a row costs what the widest of the four queries costs, so reads are grouped by the column counts of the
+        // first seed chain2aln will extend (left side first, then right), then by the query bases left over all seeds.
         u32 est = 0;
         for (int i = 0; i < ns; ++i) est += (u32)(len - os[i].len);
-        B.work[rid] = est < 0xFFFFFu ? est : 0xFFFFFu;
+        u32 first = 0, second = 0;
+        if (n > 0 && oc[0].n > 0) {
+            const Seed *cs = os + oc[0].head;
+            int best = 0;
+            for (int i = 1; i < oc[0].n; ++i) if (cs[i].score >= cs[best].score) best = i;
+            u32 ql = (u32)cs[best].qbeg, qr = (u32)(len - cs[best].qbeg - cs[best].len);
+            u32 cl = ql ? (ql + 8) >> 3 : 0, cr = qr ? (qr + 8) >> 3 : 0;
+            first = cl ? cl : cr; second = cl ? cr : 0;
+            if (first > 31) first = 31;
+            if (second > 31) second = 31;
+        }
+        est >>= 2;
+        B.work[rid] = first << 15 | second << 10 | (est < 1023u ? est : 1023u);
     }
 }
 

@@ -53,9 +53,10 @@ HD void extend_lean(const DevIndex &ix, u64 a, u64 o, u64 s, int c, u64 &na, u64
     const u32 dk = k >= ix.primary, dl = l >= ix.primary;
     const u64 kk = k - dk, ll = l - dl;
     const u64 bk = kk >> 6, bl = ll >> 6;
+    // both gathers are issued before either is used, unconditionally: when k and l share a block the second request
+    // merges with the first in L1, whereas a predicated second load would have to wait for the first to land
     OccLoad b1 = load_block(ix, bk);
-    OccLoad b2 = b1;
-    if (bl != bk) b2 = load_block(ix, bl);
+    OccLoad b2 = load_block(ix, bl);
     ctr.occ_blocks += bl != bk ? 2 : 1;
     const int rk = (int)(kk & 63), rl = (int)(ll & 63);          // ranks inside the block, minus one
     const u64 mk = (2ull << rk) - 1, ml = (2ull << rl) - 1;      // rk == 63: 2<<63 wraps to 0, minus 1 = all ones

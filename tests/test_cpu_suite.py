@@ -191,3 +191,46 @@ def test_c_restatement_vs_live_reference_random():
     exp, _ = pyref.align(ridx, (r, off), opt, ids)
     got = pyoracle.align(v, (r, off), opt, ids)
     assert parity.compare_results(got, exp) == []
+
+
+def _emul_lib():
+    """tests/hostsim/{group,reg}_emul.cpp: lock-step CPU emulations of the lane-cooperative DP kernels."""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "hostsim", "libemul.so")
+    srcs = [os.path.join(here, "hostsim", f) for f in ("group_emul.cpp", "reg_emul.cpp")]
+    csrc = os.path.join(here, "..", "seqlib_b200", "csrc")
+    deps = srcs + [os.path.join(csrc, f) for f in ("ksw.cuh", "ksw_reg.cuh", "common.cuh", "fmindex.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", so] + srcs)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("fn,G", [("reg_emul_check", 8), ("reg_emul_check", 4), ("group_emul_check", 8)])
+def test_lane_cooperative_extend_equals_scalar(fn, G):
+    """The lane-cooperative ksw_extend2 schemes (registers: ksw_reg.cuh, shared memory: ksw_group.cuh), emulated in
+    lock step on the CPU with the kernels' own phase functions, give the scalar recurrence's six outputs and cell
+    count on config-3 shaped pairs and on mixed shapes (short queries, unrelated targets, narrow bands, z-drop)."""
+    import ctypes as C
+    L = _emul_lib()
+    mat = np.array(list(_opt_default().mat), dtype=np.int8)
+    sets = []
+    j, q, t = cases.c3_tuples_fast(6000)
+    sets.append((j, q, t, 100))
+    j, q, t = cases.mixed_tuples(30000)
+    q = np.minimum(q, 3).astype(np.uint8)        # the register scheme is used on the 2-bit reference text and N-free reads only
+    for zd in (100, 0, 20):
+        sel = j[j["zdrop"] == zd]
+        sets.append((sel, q, t, zd))
+    for jobs, qp, tp, zd in sets:
+        n = len(jobs)
+        ql = np.ascontiguousarray(jobs["qlen"], dtype=np.int32); tl = np.ascontiguousarray(jobs["tlen"], dtype=np.int32)
+        qo = np.ascontiguousarray(jobs["q_off"], dtype=np.int64); to = np.ascontiguousarray(jobs["t_off"], dtype=np.int64)
+        ws = np.ascontiguousarray(jobs["w"], dtype=np.int32); h0 = np.ascontiguousarray(jobs["h0"], dtype=np.int32)
+        first = C.c_long(-1)
+        bad = getattr(L, fn)(C.c_int(G), C.c_long(n), ql.ctypes.data_as(C.c_void_p), tl.ctypes.data_as(C.c_void_p), qo.ctypes.data_as(C.c_void_p),
+                             to.ctypes.data_as(C.c_void_p), qp.ctypes.data_as(C.c_void_p), tp.ctypes.data_as(C.c_void_p), ws.ctypes.data_as(C.c_void_p),
+                             h0.ctypes.data_as(C.c_void_p), mat.ctypes.data_as(C.c_void_p), C.c_int(6), C.c_int(1), C.c_int(6), C.c_int(1), C.c_int(5),
+                             C.c_int(zd), C.byref(first))
+        assert bad == 0, (fn, G, zd, first.value)
