@@ -247,6 +247,82 @@ int b200_ksw_extend2_batch(int64_t n, const b200_ext_job_t *jobs,
                            const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
                            b200_ext_out_t *out, uint64_t *cells, float *kernel_ms);
 
+/* ------------------------------------------------------------------ */
+/* fermi-lite half: k-mer counting, error correction, unique filter   */
+/*                                         */
+/* ------------------------------------------------------------------ */
+
+/* == fseq1_t (fermi-lite/fml.h:8-11): NUL-terminated, malloc'd strings. */
+typedef struct b200_fseq1 {
+    int32_t l_seq;
+    char *seq, *qual;
+} b200_fseq1_t;
+
+/* == magopt_t (fermi-lite/fml.h:17-20) */
+typedef struct b200_magopt {
+    int flag, min_ovlp, min_elen, min_ensr, min_insr, max_bdist, max_bdiff, max_bvtx, min_merge_len, trim_len, trim_depth;
+    float min_dratio1, max_bcov, max_bfrac;
+} b200_magopt_t;
+
+/* == fml_opt_t (fermi-lite/fml.h:22-29) */
+typedef struct b200_fml_opt {
+    int n_threads;
+    int ec_k;
+    int min_cnt, max_cnt;
+    int min_asm_ovlp;
+    int min_merge_len;
+    b200_magopt_t mag_opt;
+} b200_fml_opt_t;
+
+/* replaces fml_opt_init (fermi-lite/misc.c:31-41) + mag_init_opt (fermi-lite/mag.c:539-557). */
+void b200_fml_opt_init(b200_fml_opt_t *opt);
+/* replaces fml_opt_adjust (fermi-lite/misc.c:43-54); only the read lengths are looked at. */
+void b200_fml_opt_adjust(b200_fml_opt_t *opt, int n_seqs, const b200_fseq1_t *seqs);
+void b200_fml_opt_adjust_lens(b200_fml_opt_t *opt, int64_t n_seqs, int64_t tot_len);
+
+/* replaces fml_correct (fermi-lite/bfc.c:568-571): count ec_k-mers of all reads, then correct every read
+ * IN PLACE (changed bases lower case, qualities recoded, bfc_ec1 at fermi-lite/bfc.c:401-466).
+ * *kcov receives the value fml_correct returns.  ec_k <= 0 leaves the reads untouched and reports 255
+ * (what the reference's undefined shifts amount to on x86-64). */
+int b200_fml_correct(const b200_fml_opt_t *opt, int n, b200_fseq1_t *seqs, float *kcov);
+/* replaces fml_fltuniq (fermi-lite/bfc.c:573-576): trims every read to its longest run of min_asm_ovlp-mers
+ * present in the count table; dropped reads are free()d and get l_seq = 0, seq = qual = NULL like the reference. */
+int b200_fml_fltuniq(const b200_fml_opt_t *opt, int n, b200_fseq1_t *seqs, float *kcov);
+
+/* The same two calls on flat pools (what the wrappers above marshal into): read i occupies
+ * [off[i], off[i+1]) of seqs (and of quals unless quals == NULL).  The pools are rewritten in place;
+ * len_out[i] receives the new length (flt_uniq: the kept run now starts at off[i]; 0 = dropped). */
+int b200_fml_correct_flat(const b200_fml_opt_t *opt, int flt_uniq, int64_t n, char *seqs, char *quals,
+                          const int64_t *off, int32_t *len_out, float *kcov);
+
+/* k-mer count table: replaces fml_count (fermi-lite/bfc.c:86-99) / bfc_ch_t (fermi-lite/htab.c). */
+typedef struct b200_kmer_table b200_kmer_table_t;
+int b200_fml_count(int64_t n, const char *seqs, const char *quals, const int64_t *off,
+                   int k, int q, int l_pre, b200_kmer_table_t **out);
+/* replaces bfc_ch_hist (fermi-lite/htab.c:104-127): returns the mode through *mode (-1 if none). */
+int b200_kmer_table_hist(const b200_kmer_table_t *tab, uint64_t cnt[256], uint64_t high[64], int *mode);
+/* replaces bfc_ch_count (fermi-lite/htab.c:95-102): distinct keys. */
+int64_t b200_kmer_table_size(const b200_kmer_table_t *tab);
+/* replaces bfc_ch_kmer_occ (fermi-lite/htab.c:85-93) for a batch of k-mers given as ASCII (n * k bytes);
+ * occ[i] = -1 if absent, else high << 8 | total. */
+int b200_kmer_table_lookup(const b200_kmer_table_t *tab, int64_t n, const char *kmers, int32_t *occ);
+/* replaces kmer_correct (fermi-lite/bfc.c:556-566) as BFC::ErrorCorrect drives it (src/BFC.cpp:221-262):
+ * corrects (or, with flt_uniq, trims) reads against an existing table with explicit min_cov / mode. */
+int b200_kmer_correct_flat(const b200_kmer_table_t *tab, int min_cov, int mode, int flt_uniq, int64_t n,
+                           char *seqs, char *quals, const int64_t *off, int32_t *len_out);
+void b200_kmer_table_destroy(b200_kmer_table_t *tab);
+
+/* Device timings (ms) and work counters of the last fermi call on this thread. */
+typedef struct b200_fml_stats {
+    float ms_count, ms_table, ms_ec, ms_flt, ms_total;
+    uint64_t n_kmers, n_distinct, table_bytes;
+    uint64_t n_lookups;      /* count-table probes issued by the correction kernel (16 B each) */
+    uint64_t n_spill;        /* reads re-run with the large scratch                            */
+    uint64_t ec_codes[8];    /* reads per ecstat_t.ec_code (fermi-lite/bfc.h:23-35), [6] = none */
+    int n_launches;
+} b200_fml_stats_t;
+int b200_fml_last_stats(b200_fml_stats_t *out);
+
 /* Device selection for multi-GPU processes (one process per GPU). */
 int b200_set_device(int ordinal);
 int b200_device_count(void);

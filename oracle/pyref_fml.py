@@ -1,0 +1,88 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/_ref/libseqref_fml.so = the reference's unmodified
+fermi-lite C compiled from the mount (oracle/Makefile) behind the flat-buffer driver oracle/refdrv_fml.c.
+
+Imported only by tests/, tests/golden/make_golden_fml.py and bench.py's cpu_baseline / --impl reference legs.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from seqlib_b200.abi import FmlOpt
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_FML_SO = os.path.join(_HERE, "_ref", "libseqref_fml.so")
+_lib = None
+
+
+def have_ref():
+    return os.path.exists(_FML_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_FML_SO)
+        L.refdrv_fml_opt_init.argtypes = [C.POINTER(FmlOpt)]
+        L.refdrv_fml_opt_size.restype = C.c_int
+        L.refdrv_fml_correct.restype = C.c_float
+        L.refdrv_fml_correct.argtypes = [C.POINTER(FmlOpt), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.refdrv_fml_count_hist.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.POINTER(C.c_int64)]
+        L.refdrv_fml_kmer_occ.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_int64, C.c_void_p, C.c_void_p]
+        L.refdrv_fml_assemble.restype = C.c_int
+        L.refdrv_fml_assemble.argtypes = [C.POINTER(FmlOpt), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_double)]
+        L.refdrv_fml_free.argtypes = [C.c_void_p]
+        assert L.refdrv_fml_opt_size() == C.sizeof(FmlOpt)
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_opt():
+    o = FmlOpt()
+    lib().refdrv_fml_opt_init(C.byref(o))
+    return o
+
+
+def correct_flat(opt, seqs, quals, off, flt_uniq=False, adjust=False):
+    """fml_correct / fml_fltuniq of the reference.  Returns (seqs, quals, lens, kcov, seconds)."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    quals = None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    n = len(off) - 1
+    so = seqs.copy()
+    qo = None if quals is None else quals.copy()
+    lens = np.zeros(max(n, 1), dtype=np.int32)
+    sec = C.c_double(0)
+    kcov = lib().refdrv_fml_correct(C.byref(opt), int(adjust), int(bool(flt_uniq)), n, _p(seqs), _p(quals), _p(off),
+                                    _p(so), _p(qo), _p(lens), C.byref(sec))
+    return so, qo, lens[:n], kcov, sec.value
+
+
+def count_hist(seqs, quals, off, k, q=20, l_pre=20):
+    """fml_count + bfc_ch_hist of the reference: (cnt[256], high[64], mode, n_distinct)."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    quals = None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    h = np.zeros(320, dtype=np.uint64)
+    nd = C.c_int64(0)
+    mode = lib().refdrv_fml_count_hist(len(off) - 1, _p(seqs), _p(quals), _p(off), k, q, l_pre, _p(h), C.byref(nd))
+    return h[:256].copy(), h[256:].copy(), mode, nd.value
+
+
+def kmer_occ(seqs, quals, off, k, kmers, q=20, l_pre=20):
+    """bfc_ch_kmer_occ of the reference for a list of k-long strings."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    quals = None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    pool = np.frombuffer(b"".join(x.encode() if isinstance(x, str) else x for x in kmers), dtype=np.uint8).copy()
+    occ = np.zeros(max(len(kmers), 1), dtype=np.int32)
+    lib().refdrv_fml_kmer_occ(len(off) - 1, _p(seqs), _p(quals), _p(off), k, q, l_pre, len(kmers), _p(pool), _p(occ))
+    return occ[:len(kmers)]

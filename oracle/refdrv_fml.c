@@ -13,6 +13,11 @@
 #include <stdint.h>
 #include <time.h>
 #include "fml.h"
+#include "htab.h"
+#include "kmer.h"
+
+extern unsigned char seq_nt6_table[256];
+struct bfc_ch_s *fml_count(int n, const fseq1_t *seq, int k, int q, int l_pre, int n_threads);
 
 static double now_s(void)
 {
@@ -90,6 +95,48 @@ int refdrv_fml_assemble(const fml_opt_t *opt, int n, const char *seqs, const cha
 	free(s);
 	*utg_off = uo; *utg_seq = us; *utg_cov = uc; *utg_nsr = nsr;
 	return n_utg;
+}
+
+static void free_seqs(int n, fseq1_t *s)
+{
+	int i;
+	for (i = 0; i < n; ++i) { free(s[i].seq); free(s[i].qual); }
+	free(s);
+}
+
+/* fml_count (fermi-lite/bfc.c:86-99) + bfc_ch_hist (fermi-lite/htab.c:104-127): hist[0..255] totals,
+ * hist[256..319] high-quality counts; returns the mode. */
+int refdrv_fml_count_hist(int n, const char *seqs, const char *quals, const int64_t *off, int k, int q, int l_pre,
+                          uint64_t *hist, int64_t *n_distinct)
+{
+	fseq1_t *s = mk_seqs(n, seqs, quals, off);
+	bfc_ch_t *ch = fml_count(n, s, k, q, l_pre, 1);
+	int mode = bfc_ch_hist(ch, hist, hist + 256);
+	if (n_distinct) *n_distinct = (int64_t)bfc_ch_count(ch);
+	bfc_ch_destroy(ch);
+	free_seqs(n, s);
+	return mode;
+}
+
+/* bfc_ch_kmer_occ (fermi-lite/htab.c:85-93) for n_q ASCII k-mers against the table of the given reads. */
+void refdrv_fml_kmer_occ(int n, const char *seqs, const char *quals, const int64_t *off, int k, int q, int l_pre,
+                         int64_t n_q, const char *kmers, int32_t *occ)
+{
+	fseq1_t *s = mk_seqs(n, seqs, quals, off);
+	bfc_ch_t *ch = fml_count(n, s, k, q, l_pre, 1);
+	int64_t i; int j;
+	for (i = 0; i < n_q; ++i) {
+		bfc_kmer_t x = {{0, 0, 0, 0}};
+		int ok = 1;
+		for (j = 0; j < k; ++j) {
+			int c = seq_nt6_table[(uint8_t)kmers[i * k + j]] - 1;
+			if (c > 3) { ok = 0; break; }
+			bfc_kmer_append(k, x.x, c);
+		}
+		occ[i] = ok ? bfc_ch_kmer_occ(ch, &x) : -1;
+	}
+	bfc_ch_destroy(ch);
+	free_seqs(n, s);
 }
 
 void refdrv_fml_free(void *p) { free(p); }

@@ -142,3 +142,48 @@ class Results:
 
     def md_of(self, h):
         return self.md[h["md_off"]:h["md_off"] + h["md_len"]].decode()
+
+
+# ---------------------------------------------------------------------------------------------------- fermi-lite half
+class MagOpt(C.Structure):
+    """b200_magopt_t == magopt_t (fermi-lite/fml.h:17-20)."""
+    _fields_ = [(n, C.c_int) for n in ("flag", "min_ovlp", "min_elen", "min_ensr", "min_insr", "max_bdist", "max_bdiff",
+                                        "max_bvtx", "min_merge_len", "trim_len", "trim_depth")] + \
+               [(n, C.c_float) for n in ("min_dratio1", "max_bcov", "max_bfrac")]
+
+
+class FmlOpt(C.Structure):
+    """b200_fml_opt_t == fml_opt_t (fermi-lite/fml.h:22-29)."""
+    _fields_ = [("n_threads", C.c_int), ("ec_k", C.c_int), ("min_cnt", C.c_int), ("max_cnt", C.c_int),
+                ("min_asm_ovlp", C.c_int), ("min_merge_len", C.c_int), ("mag_opt", MagOpt)]
+
+
+class Fseq1(C.Structure):
+    """b200_fseq1_t == fseq1_t (fermi-lite/fml.h:8-11)."""
+    _fields_ = [("l_seq", C.c_int32), ("seq", C.c_void_p), ("qual", C.c_void_p)]
+
+
+class FmlStats(C.Structure):
+    _fields_ = [("ms_count", C.c_float), ("ms_table", C.c_float), ("ms_ec", C.c_float), ("ms_flt", C.c_float),
+                ("ms_total", C.c_float), ("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64), ("table_bytes", C.c_uint64),
+                ("n_lookups", C.c_uint64), ("n_spill", C.c_uint64), ("ec_codes", C.c_uint64 * 8), ("n_launches", C.c_int)]
+
+
+def pack_reads_quals(reads, quals=None):
+    """(seqs u8, quals u8 | None, off int64) for lists of str/bytes; quals=None: no qualities."""
+    s, off = pack_reads(reads)
+    if quals is None:
+        return s, None, off
+    q, qoff = pack_reads(quals)
+    assert np.array_equal(off, qoff), "sequence / quality length mismatch"
+    return s, q, off
+
+
+def unpack_reads(pool, off, lens=None):
+    """Pool + offsets (+ new lengths) -> list[bytes]."""
+    b = pool.tobytes()
+    out = []
+    for i in range(len(off) - 1):
+        ln = int(off[i + 1] - off[i]) if lens is None else int(lens[i])
+        out.append(b[int(off[i]):int(off[i]) + ln])
+    return out

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from .abi import (MemOpt, Contig, IndexView, ResultsView, Results, StageStats, INTV_DTYPE, EXT_JOB_DTYPE, EXT_OUT_DTYPE,
-                  np_from_ptr, pack_reads)
+                  np_from_ptr, pack_reads, FmlOpt, Fseq1, FmlStats)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libseqlib_b200.so")
@@ -23,6 +23,9 @@ EXPORTS = [
     "b200_index_l_pac", "b200_mem_align_batch", "b200_results_view", "b200_results_free", "b200_batch_create",
     "b200_batch_run", "b200_batch_fetch", "b200_batch_destroy", "b200_last_stats", "b200_debug_collect_intv",
     "b200_ksw_extend2_batch", "b200_set_device", "b200_device_count",
+    "b200_fml_opt_init", "b200_fml_opt_adjust", "b200_fml_opt_adjust_lens", "b200_fml_correct", "b200_fml_fltuniq",
+    "b200_fml_correct_flat", "b200_fml_count", "b200_kmer_table_hist", "b200_kmer_table_size", "b200_kmer_table_lookup",
+    "b200_kmer_correct_flat", "b200_kmer_table_destroy", "b200_fml_last_stats",
 ]
 
 
@@ -67,6 +70,21 @@ def lib():
         L.b200_ksw_extend2_batch.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
         L.b200_set_device.argtypes = [C.c_int]
+        L.b200_fml_opt_init.argtypes = [C.POINTER(FmlOpt)]
+        L.b200_fml_opt_adjust.argtypes = [C.POINTER(FmlOpt), C.c_int, C.POINTER(Fseq1)]
+        L.b200_fml_opt_adjust_lens.argtypes = [C.POINTER(FmlOpt), C.c_int64, C.c_int64]
+        L.b200_fml_correct.argtypes = [C.POINTER(FmlOpt), C.c_int, C.POINTER(Fseq1), C.POINTER(C.c_float)]
+        L.b200_fml_fltuniq.argtypes = [C.POINTER(FmlOpt), C.c_int, C.POINTER(Fseq1), C.POINTER(C.c_float)]
+        L.b200_fml_correct_flat.argtypes = [C.POINTER(FmlOpt), C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_float)]
+        L.b200_fml_count.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.b200_kmer_table_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.b200_kmer_table_size.restype = C.c_int64
+        L.b200_kmer_table_size.argtypes = [C.c_void_p]
+        L.b200_kmer_table_lookup.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.b200_kmer_correct_flat.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200_kmer_table_destroy.argtypes = [C.c_void_p]
+        L.b200_fml_last_stats.argtypes = [C.POINTER(FmlStats)]
         _lib = L
     return _lib
 
@@ -286,3 +304,82 @@ def ksw_extend2_batch(jobs, qpool, tpool, mat, o_del=6, e_del=1, o_ins=6, e_ins=
     _check(lib().b200_ksw_extend2_batch(len(jobs), _p(jobs), _p(qpool), len(qpool), _p(tpool), len(tpool), _p(mat),
                                         o_del, e_del, o_ins, e_ins, _p(out), C.byref(cells), C.byref(ms)))
     return out, cells.value, ms.value
+
+
+# ---------------------------------------------------------------------------------------------------- fermi-lite half
+def fml_default_opt():
+    o = FmlOpt()
+    lib().b200_fml_opt_init(C.byref(o))
+    return o
+
+
+def fml_opt_adjust(opt, n_seqs, tot_len):
+    lib().b200_fml_opt_adjust_lens(C.byref(opt), int(n_seqs), int(tot_len))
+    return opt
+
+
+def fml_correct_flat(opt, seqs, quals, off, flt_uniq=False):
+    """b200_fml_correct_flat on numpy pools.  Returns (seqs, quals, lens, kcov); the input arrays are not modified."""
+    seqs = np.array(seqs, dtype=np.uint8, copy=True)
+    quals = None if quals is None else np.array(quals, dtype=np.uint8, copy=True)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    n = len(off) - 1
+    lens = np.zeros(max(n, 1), dtype=np.int32)
+    kcov = C.c_float(0)
+    _check(lib().b200_fml_correct_flat(C.byref(opt), int(bool(flt_uniq)), n, _p(seqs), _p(quals), _p(off), _p(lens), C.byref(kcov)))
+    return seqs, quals, lens[:n], kcov.value
+
+
+def fml_last_stats():
+    st = FmlStats()
+    _check(lib().b200_fml_last_stats(C.byref(st)))
+    d = {k: getattr(st, k) for k, _ in FmlStats._fields_ if k != "ec_codes"}
+    d["ec_codes"] = list(st.ec_codes)
+    return d
+
+
+class KmerTable:
+    """b200_kmer_table_t: the device-resident k-mer count table (bfc_ch_t)."""
+
+    def __init__(self, seqs, quals, off, k, q=20, l_pre=20):
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        quals = None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        h = C.c_void_p()
+        _check(lib().b200_fml_count(len(off) - 1, _p(seqs), _p(quals), _p(off), k, q, l_pre, C.byref(h)))
+        self.h, self.k = h, k
+
+    def hist(self):
+        cnt = np.zeros(256, dtype=np.uint64)
+        high = np.zeros(64, dtype=np.uint64)
+        mode = C.c_int(0)
+        _check(lib().b200_kmer_table_hist(self.h, _p(cnt), _p(high), C.byref(mode)))
+        return cnt, high, mode.value
+
+    def size(self):
+        return lib().b200_kmer_table_size(self.h)
+
+    def lookup(self, kmers):
+        """kmers: list of k-long strings -> int32 occ (-1 absent, else high << 8 | total)."""
+        pool, off = pack_reads(kmers)
+        assert len(pool) == len(kmers) * self.k
+        occ = np.zeros(max(len(kmers), 1), dtype=np.int32)
+        _check(lib().b200_kmer_table_lookup(self.h, len(kmers), _p(pool), _p(occ)))
+        return occ[:len(kmers)]
+
+    def correct(self, seqs, quals, off, min_cov, mode, flt_uniq=False):
+        seqs = np.array(seqs, dtype=np.uint8, copy=True)
+        quals = None if quals is None else np.array(quals, dtype=np.uint8, copy=True)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        n = len(off) - 1
+        lens = np.zeros(max(n, 1), dtype=np.int32)
+        _check(lib().b200_kmer_correct_flat(self.h, min_cov, mode, int(bool(flt_uniq)), n, _p(seqs), _p(quals), _p(off), _p(lens)))
+        return seqs, quals, lens[:n]
+
+    def close(self):
+        if self.h:
+            lib().b200_kmer_table_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

@@ -124,3 +124,47 @@ def mixed_tuples(n, seed=11):
     jobs["zdrop"] = rng.choice([100, 0, 20], n)
     jobs["h0"] = rng.integers(1, 160, n)
     return jobs, qp, tp
+
+
+# ---------------------------------------------------------------------------------------------------- fermi-lite half
+def fml_reads(n, region=20000, read_len=150, err=0.01, seed=0x5EED0004, junk=0.03, n_frac=0.01, short_frac=0.01, ragged=True):
+    """Assembly-shaped reads (SURVEY 8d, config 4 at reduced scale): n reads drawn from a random `region`-bp sequence, both
+    strands, `err` substitutions; erroneous bases mostly get a low quality; plus the edge cases the reference code
+    branches on: unrelated reads (no solid k-mer; dropped by fml_fltuniq), reads with N (skipped k-mers, ECCODE_MANY_N when
+    > 5 %), reads shorter than k, ragged lengths.  Returns (seqs u8 pool, quals u8 pool, off)."""
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, region, dtype=np.uint8)
+    comp = np.array([3, 2, 1, 0], dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs, quals = [], []
+    for i in range(n):
+        ln = read_len
+        u = rng.random()
+        if ragged and u < 0.15:
+            ln = int(rng.integers(read_len // 2, read_len + 1))
+        if u > 1 - short_frac:
+            ln = int(rng.integers(1, 40))
+        if rng.random() < junk:
+            s = rng.integers(0, 4, ln, dtype=np.uint8)
+            q = np.full(ln, ord("I"), dtype=np.uint8)
+        else:
+            p = int(rng.integers(0, region - ln + 1))
+            s = ref[p:p + ln].copy()
+            if rng.random() < 0.5:
+                s = comp[s[::-1]]
+            q = rng.choice(np.frombuffer(b"II??5", dtype=np.uint8), ln)
+            e = rng.random(ln) < err
+            s[e] = (s[e] + rng.integers(1, 4, int(e.sum()), dtype=np.uint8)) & 3
+            lowq = e & (rng.random(ln) < 0.7)
+            q[lowq] = ord("(")
+        a = acgt[s]
+        if rng.random() < n_frac:
+            k = 1 if rng.random() < 0.6 else max(1, ln // 8)
+            a[rng.integers(0, ln, k)] = ord("N")
+        if rng.random() < 0.02:
+            a = np.frombuffer(a.tobytes().lower(), dtype=np.uint8).copy()
+        seqs.append(a)
+        quals.append(q)
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    return np.concatenate(seqs), np.concatenate(quals), off
