@@ -86,3 +86,44 @@ def kmer_occ(seqs, quals, off, k, kmers, q=20, l_pre=20):
     occ = np.zeros(max(len(kmers), 1), dtype=np.int32)
     lib().refdrv_fml_kmer_occ(len(off) - 1, _p(seqs), _p(quals), _p(off), k, q, l_pre, len(kmers), _p(pool), _p(occ))
     return occ[:len(kmers)]
+
+
+def bwt(seqs, off, queries=None):
+    """fml_seq2fmi of the reference, decoded: (bwt symbols u8 0..5, cnt[7], mcnt[7], (ranks[nq,6], sym[nq]) for rld_rank1a queries)."""
+    L = lib()
+    L.refdrv_fml_bwt.restype = C.c_int64
+    L.refdrv_fml_bwt.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    q = np.ascontiguousarray(queries if queries is not None else np.zeros(0), dtype=np.uint64)
+    ranks = np.zeros((max(len(q), 1), 6), dtype=np.uint64)
+    sym = np.zeros(max(len(q), 1), dtype=np.int32)
+    cnt = np.zeros(7, dtype=np.uint64)
+    mcnt = np.zeros(7, dtype=np.uint64)
+    p = C.c_void_p()
+    n = L.refdrv_fml_bwt(len(off) - 1, _p(seqs), _p(off), C.byref(p), _p(cnt), _p(mcnt), len(q), _p(q), _p(ranks), _p(sym))
+    out = np.zeros(0, dtype=np.uint8)
+    if n:
+        out = np.frombuffer((C.c_char * n).from_address(p.value), dtype=np.uint8, count=n).copy()
+        L.refdrv_fml_free(p)
+    return out, cnt, mcnt, (ranks[:len(q)], sym[:len(q)])
+
+
+def mag_text(opt, stage, kcov, seqs, off):
+    """fml_seq2fmi + fml_fmi2mag (+ fml_mag_clean for stage 1) of the reference as mag_g_print text."""
+    L = lib()
+    L.refdrv_fml_mag_text.restype = C.c_void_p
+    L.refdrv_fml_mag_text.argtypes = [C.POINTER(FmlOpt), C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    ln = C.c_int64(0)
+    rd = C.c_float(0)
+    sec = C.c_double(0)
+    p = L.refdrv_fml_mag_text(C.byref(opt), stage, kcov, len(off) - 1, _p(seqs), _p(off), C.byref(ln), C.byref(rd), C.byref(sec))
+    if not p:
+        return "", 0.0, sec.value
+    txt = C.string_at(p, ln.value).decode()
+    L.refdrv_fml_free(p)
+    return txt, rd.value, sec.value

@@ -15,6 +15,9 @@
 #include "fml.h"
 #include "htab.h"
 #include "kmer.h"
+#include "rld0.h"
+#include "mag.h"
+#include "kstring.h"
 
 extern unsigned char seq_nt6_table[256];
 struct bfc_ch_s *fml_count(int n, const fseq1_t *seq, int k, int q, int l_pre, int n_threads);
@@ -137,6 +140,108 @@ void refdrv_fml_kmer_occ(int n, const char *seqs, const char *quals, const int64
 	}
 	bfc_ch_destroy(ch);
 	free_seqs(n, s);
+}
+
+/* fml_seq2fmi (fermi-lite/misc.c:65-128) on the given reads, then the whole BWT decoded run by run (rld_dec):
+ * *bwt = malloc'd array of symbols 0..5 ($ACGTN), cnt[0..6] = e->cnt (cumulative), returns the BWT length.
+ * n_q rank queries: for each q[i], sym[i] = rld_rank1a(e, q[i], &ranks[6*i]). */
+int64_t refdrv_fml_bwt(int n, const char *seqs, const int64_t *off, uint8_t **bwt, uint64_t *cnt, uint64_t *mcnt,
+                       int64_t n_q, const uint64_t *q, uint64_t *ranks, int32_t *sym)
+{
+	fml_opt_t opt;
+	fseq1_t *s = mk_seqs(n, seqs, 0, off);
+	rld_t *e;
+	rlditr_t itr;
+	int64_t tot, l, z = 0, i;
+	int c = 0;
+	fml_opt_init(&opt);
+	e = fml_seq2fmi(&opt, n, s);
+	free_seqs(n, s);
+	*bwt = 0;
+	if (e == 0) return 0;
+	tot = e->mcnt[0];
+	*bwt = malloc(tot + 1);
+	rld_itr_init(e, &itr, 0);
+	while ((l = rld_dec(e, &itr, &c, 0)) > 0) { memset(*bwt + z, c, l); z += l; }
+	for (i = 0; i <= 6; ++i) cnt[i] = e->cnt[i], mcnt[i] = e->mcnt[i];
+	for (i = 0; i < n_q; ++i) sym[i] = rld_rank1a(e, q[i], ranks + 6 * i);
+	rld_destroy(e);
+	return z;
+}
+
+static char *mag_text(const mag_t *g, int64_t *len)
+{
+	kstring_t out = {0, 0, 0}, all = {0, 0, 0};
+	size_t i;
+	for (i = 0; i < g->v.n; ++i) {
+		if (g->v.a[i].len < 0) continue;
+		mag_v_write(&g->v.a[i], &out);
+		if (g->v.a[i].len > 0) kputsn(out.s, out.l, &all);
+	}
+	free(out.s);
+	if (all.s == 0) { all.s = calloc(1, 1); }
+	*len = all.l;
+	return all.s;
+}
+
+/* The assembly half of fml_assemble (fermi-lite/misc.c:291-300) on reads that are already corrected / filtered:
+ * fml_seq2fmi, fml_fmi2mag, [fml_mag_clean with min_ensr/min_insr derived from kcov], dumped in mag_g_print's text
+ * format (fermi-lite/mag.c:151-176).  stage 0: graph straight out of fml_fmi2mag; stage 1: after fml_mag_clean. */
+char *refdrv_fml_mag_text(const fml_opt_t *opt0, int stage, float kcov, int n, const char *seqs, const int64_t *off,
+                          int64_t *text_len, float *rdist, double *seconds)
+{
+	fml_opt_t opt = *opt0;
+	fseq1_t *s = mk_seqs(n, seqs, 0, off);
+	rld_t *e;
+	mag_t *g;
+	char *txt;
+	double t0 = now_s();
+	fml_opt_adjust(&opt, n, s);
+	e = fml_seq2fmi(&opt, n, s);
+	free_seqs(n, s);
+	*text_len = 0;
+	if (e == 0) return 0;
+	g = fml_fmi2mag(&opt, e);
+	if (rdist) *rdist = g->rdist;
+	if (stage >= 100) { /* debugging aid: the first (stage - 100) passes of fml_mag_clean / mag_g_clean (fermi-lite/mag.c:559-583) */
+		extern int mag_g_rm_vint(mag_t *g, int min_len, int min_nsr, int min_ovlp);
+		magopt_t o_; const magopt_t *o = &o_;
+		int left = stage - 100, j;
+		opt.mag_opt.min_ensr = opt.mag_opt.min_ensr > kcov * .1 ? opt.mag_opt.min_ensr : (int)(kcov * .1 + .499);
+		opt.mag_opt.min_ensr = opt.mag_opt.min_ensr < opt0->max_cnt ? opt.mag_opt.min_ensr : opt0->max_cnt;
+		opt.mag_opt.min_ensr = opt.mag_opt.min_ensr > opt0->min_cnt ? opt.mag_opt.min_ensr : opt0->min_cnt;
+		opt.mag_opt.min_insr = opt.mag_opt.min_ensr - 1;
+		o_ = opt.mag_opt; o_.min_merge_len = opt.min_merge_len;
+#define STEP(x) do { if (left-- > 0) { x; } } while (0)
+		STEP(mag_g_merge(g, 1, opt.min_merge_len));
+		for (j = 2; j <= o->min_ensr; ++j) STEP(mag_g_rm_vext(g, o->min_elen, j));
+		STEP(mag_g_merge(g, 0, o->min_merge_len));
+		STEP(mag_g_rm_edge(g, g->min_ovlp, o->min_dratio1, o->min_elen, o->min_ensr));
+		STEP(mag_g_merge(g, 1, o->min_merge_len));
+		for (j = 2; j <= o->min_ensr; ++j) STEP(mag_g_rm_vext(g, o->min_elen, j));
+		STEP(mag_g_merge(g, 0, o->min_merge_len));
+		STEP(mag_g_pop_open(g, o->min_elen));
+		STEP(mag_g_pop_simple(g, o->max_bcov, o->max_bfrac, o->min_merge_len, o->max_bdiff, 0));
+		STEP(mag_g_rm_vint(g, o->min_elen, o->min_insr, g->min_ovlp));
+		STEP(mag_g_rm_edge(g, g->min_ovlp, o->min_dratio1, o->min_elen, o->min_ensr));
+		STEP(mag_g_merge(g, 1, o->min_merge_len));
+		STEP(mag_g_rm_vext(g, o->min_elen, o->min_ensr));
+		STEP(mag_g_merge(g, 0, o->min_merge_len));
+		STEP(mag_g_pop_open(g, o->min_elen));
+		STEP(mag_g_rm_vext(g, o->min_elen, o->min_ensr));
+		STEP(mag_g_merge(g, 0, o->min_merge_len));
+#undef STEP
+	} else if (stage >= 1) {
+		opt.mag_opt.min_ensr = opt.mag_opt.min_ensr > kcov * .1 ? opt.mag_opt.min_ensr : (int)(kcov * .1 + .499);
+		opt.mag_opt.min_ensr = opt.mag_opt.min_ensr < opt0->max_cnt ? opt.mag_opt.min_ensr : opt0->max_cnt;
+		opt.mag_opt.min_ensr = opt.mag_opt.min_ensr > opt0->min_cnt ? opt.mag_opt.min_ensr : opt0->min_cnt;
+		opt.mag_opt.min_insr = opt.mag_opt.min_ensr - 1;
+		fml_mag_clean(&opt, g);
+	}
+	if (seconds) *seconds = now_s() - t0;
+	txt = mag_text(g, text_len);
+	fml_mag_destroy(g);
+	return txt;
 }
 
 void refdrv_fml_free(void *p) { free(p); }
