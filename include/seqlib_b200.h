@@ -312,9 +312,65 @@ int b200_kmer_correct_flat(const b200_kmer_table_t *tab, int min_cov, int mode, 
                            char *seqs, char *quals, const int64_t *off, int32_t *len_out);
 void b200_kmer_table_destroy(b200_kmer_table_t *tab);
 
+/* ------------------------------------------------------------------ */
+/* fermi-lite half: FMD-index, unitig graph, cleaning, unitigs        */
+/*                                         */
+/* ------------------------------------------------------------------ */
+
+/* == fml_ovlp_t / fml_utg_t (fermi-lite/fml.h:34-46) */
+typedef struct b200_utg_ovlp {
+    uint32_t len:31, from:1;
+    uint32_t id:31, to:1;
+} b200_utg_ovlp_t;
+typedef struct b200_utg {
+    int32_t len;
+    int32_t nsr;
+    char *seq;
+    char *cov;
+    int n_ovlp[2];
+    b200_utg_ovlp_t *ovlp;
+} b200_utg_t;
+
+typedef struct b200_utgs b200_utgs_t;
+
+/* replaces fml_assemble (fermi-lite/misc.c:280-302) on flat pools: fml_opt_adjust, fml_correct (ec_k >= 0),
+ * fml_fltuniq, fml_seq2fmi, fml_fmi2mag, fml_mag_clean with min_ensr/min_insr derived from kcov, fml_mag2utg.
+ * The caller's pools are NOT modified (the reference leaves its reads in an unspecified state).  *out may be
+ * an empty set (the reference returns NULL when every read was filtered out). */
+int b200_fml_assemble_flat(const b200_fml_opt_t *opt, int64_t n, const char *seqs, const char *quals,
+                           const int64_t *off, b200_utgs_t **out);
+/* the assembly half alone, as FermiAssembler::DirectAssemble drives it (src/FermiAssembler.cpp:24-39):
+ * fml_seq2fmi + fml_fmi2mag + fml_mag_clean(opt as given) + fml_mag2utg on reads taken as they are. */
+int b200_fml_seqs2utg_flat(const b200_fml_opt_t *opt, int64_t n, const char *seqs, const int64_t *off,
+                           b200_utgs_t **out);
+/* fseq1_t form of fml_assemble; *utg is a malloc'd fml_utg_t-compatible array released by b200_fml_utg_destroy
+ * (== fml_utg_destroy, fermi-lite/misc.c:267-276). */
+int b200_fml_assemble(const b200_fml_opt_t *opt, int n_seqs, const b200_fseq1_t *seqs, int *n_utg, b200_utg_t **utg);
+void b200_fml_utg_destroy(int n_utg, b200_utg_t *utg);
+
+int b200_utgs_view(const b200_utgs_t *u, int *n_utg, const b200_utg_t **utg);   /* pointers owned by the handle */
+void b200_utgs_free(b200_utgs_t *u);
+
+/* Stage dumps for parity tests.
+ * b200_fmd_*: the FMD-index (replaces fml_seq2fmi -> rld_t, fermi-lite/misc.c:65-128): the BWT as one symbol per
+ * byte (0..5 = $ACGTN), cnt[7] / mcnt[7] like rld_t, and rld_rank1a (fermi-lite/rld0.c:402-421) for a batch. */
+typedef struct b200_fmd b200_fmd_t;
+int b200_fmd_build(int64_t n, const char *seqs, const int64_t *off, b200_fmd_t **out);
+int64_t b200_fmd_len(const b200_fmd_t *f);
+int b200_fmd_info(const b200_fmd_t *f, uint64_t cnt[7], uint64_t mcnt[7]);
+int b200_fmd_bwt(const b200_fmd_t *f, uint8_t *bwt);
+int b200_fmd_rank1a(const b200_fmd_t *f, int64_t n_q, const uint64_t *q, uint64_t *ranks /* 6 per query */, int32_t *sym);
+void b200_fmd_destroy(b200_fmd_t *f);
+/* the unitig graph in mag_g_print's text format (fermi-lite/mag.c:151-194): stage 0 = out of fml_fmi2mag
+ * (fermi-lite/unitig.c:406-455), stage 1 = after fml_mag_clean with opt as given; *text is malloc'd. */
+int b200_fml_mag_text(const b200_fml_opt_t *opt, int stage, int64_t n, const char *seqs, const int64_t *off,
+                      char **text, int64_t *text_len, float *rdist);
+
 /* Device timings (ms) and work counters of the last fermi call on this thread. */
 typedef struct b200_fml_stats {
     float ms_count, ms_table, ms_ec, ms_flt, ms_total;
+    float ms_fmd, ms_nodes, ms_walk_host, ms_clean_host;   /* index build, overlap records (device); walk, cleaning (host) */
+    uint64_t fmd_symbols, n_strings, n_vertices, n_utg;
     uint64_t n_kmers, n_distinct, table_bytes;
     uint64_t n_lookups;      /* count-table probes issued by the correction kernel (16 B each) */
     uint64_t n_spill;        /* reads re-run with the large scratch                            */

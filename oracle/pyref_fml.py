@@ -34,7 +34,7 @@ def lib():
         L.refdrv_fml_assemble.restype = C.c_int
         L.refdrv_fml_assemble.argtypes = [C.POINTER(FmlOpt), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                          C.POINTER(C.c_double)]
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_double)]
         L.refdrv_fml_free.argtypes = [C.c_void_p]
         assert L.refdrv_fml_opt_size() == C.sizeof(FmlOpt)
         _lib = L
@@ -127,3 +127,33 @@ def mag_text(opt, stage, kcov, seqs, off):
     txt = C.string_at(p, ln.value).decode()
     L.refdrv_fml_free(p)
     return txt, rd.value, sec.value
+
+
+def assemble(opt, seqs, quals, off):
+    """fml_assemble of the reference: (list of dicts like seqlib_b200.abi.utgs_to_py, seconds)."""
+    L = lib()
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    quals = None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    ps = [C.c_void_p() for _ in range(6)]
+    sec = C.c_double(0)
+    n = L.refdrv_fml_assemble(C.byref(opt), len(off) - 1, _p(seqs), _p(quals), _p(off), *[C.byref(p) for p in ps], C.byref(sec))
+    out = []
+    if n >= 0 and ps[0].value:
+        uo = np.frombuffer((C.c_char * (8 * (n + 1))).from_address(ps[0].value), dtype=np.int64).copy()
+        tot = int(uo[-1])
+        us = C.string_at(ps[1].value, tot)
+        uc = C.string_at(ps[2].value, tot)
+        nsr = np.frombuffer((C.c_char * (4 * max(n, 1))).from_address(ps[3].value), dtype=np.int32).copy()
+        nv = np.frombuffer((C.c_char * (8 * max(n, 1))).from_address(ps[4].value), dtype=np.int32).copy()
+        no = int(nv[:2 * n].sum())
+        ov = np.frombuffer((C.c_char * (16 * max(no, 1))).from_address(ps[5].value), dtype=np.int32).copy().reshape(-1, 4)
+        k = 0
+        for i in range(n):
+            m = int(nv[2 * i] + nv[2 * i + 1])
+            out.append(dict(seq=us[uo[i]:uo[i + 1]], cov=uc[uo[i]:uo[i + 1]], nsr=int(nsr[i]), n_ovlp=(int(nv[2 * i]), int(nv[2 * i + 1])),
+                            ovlp=[tuple(int(x) for x in ov[k + j]) for j in range(m)]))
+            k += m
+        for p in ps:
+            L.refdrv_fml_free(p)
+    return out, sec.value

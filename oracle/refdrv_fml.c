@@ -74,7 +74,8 @@ float refdrv_fml_correct(const fml_opt_t *opt0, int adjust, int flt_uniq, int n,
 /* fml_assemble (fermi-lite/misc.c:280-302).  Returns the unitigs flattened:
  * utg_off[n_utg+1] into one char pool (sequence) and one cov pool, nsr[]. */
 int refdrv_fml_assemble(const fml_opt_t *opt, int n, const char *seqs, const char *quals, const int64_t *off,
-                        int64_t **utg_off, char **utg_seq, char **utg_cov, int32_t **utg_nsr, double *seconds)
+                        int64_t **utg_off, char **utg_seq, char **utg_cov, int32_t **utg_nsr,
+                        int32_t **utg_novlp /* 2 per unitig */, int32_t **utg_ovlp /* len, from, id, to per overlap */, double *seconds)
 {
 	fseq1_t *s = mk_seqs(n, seqs, quals, off);
 	int n_utg = 0, i;
@@ -91,6 +92,17 @@ int refdrv_fml_assemble(const fml_opt_t *opt, int n, const char *seqs, const cha
 		memcpy(us + uo[i], u[i].seq, u[i].len);
 		memcpy(uc + uo[i], u[i].cov, u[i].len);
 		nsr[i] = u[i].nsr;
+	}
+	{
+		int64_t no = 0, k = 0; int j;
+		int32_t *nv = calloc(n_utg ? 2 * n_utg : 1, 4), *ov;
+		for (i = 0; i < n_utg; ++i) { nv[2*i] = u[i].n_ovlp[0]; nv[2*i+1] = u[i].n_ovlp[1]; no += u[i].n_ovlp[0] + u[i].n_ovlp[1]; }
+		ov = calloc(no ? 4 * no : 1, 4);
+		for (i = 0; i < n_utg; ++i)
+			for (j = 0; j < u[i].n_ovlp[0] + u[i].n_ovlp[1]; ++j, ++k) {
+				ov[4*k] = u[i].ovlp[j].len; ov[4*k+1] = u[i].ovlp[j].from; ov[4*k+2] = u[i].ovlp[j].id; ov[4*k+3] = u[i].ovlp[j].to;
+			}
+		*utg_novlp = nv; *utg_ovlp = ov;
 	}
 	fml_utg_destroy(n_utg, u);
 	/* in this fork fml_assemble does not free the reads (fermi-lite/misc.c:85-102) */

@@ -165,7 +165,9 @@ class Fseq1(C.Structure):
 
 class FmlStats(C.Structure):
     _fields_ = [("ms_count", C.c_float), ("ms_table", C.c_float), ("ms_ec", C.c_float), ("ms_flt", C.c_float),
-                ("ms_total", C.c_float), ("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64), ("table_bytes", C.c_uint64),
+                ("ms_total", C.c_float), ("ms_fmd", C.c_float), ("ms_nodes", C.c_float), ("ms_walk_host", C.c_float),
+                ("ms_clean_host", C.c_float), ("fmd_symbols", C.c_uint64), ("n_strings", C.c_uint64), ("n_vertices", C.c_uint64),
+                ("n_utg", C.c_uint64), ("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64), ("table_bytes", C.c_uint64),
                 ("n_lookups", C.c_uint64), ("n_spill", C.c_uint64), ("ec_codes", C.c_uint64 * 8), ("n_launches", C.c_int)]
 
 
@@ -186,4 +188,26 @@ def unpack_reads(pool, off, lens=None):
     for i in range(len(off) - 1):
         ln = int(off[i + 1] - off[i]) if lens is None else int(lens[i])
         out.append(b[int(off[i]):int(off[i]) + ln])
+    return out
+
+
+class UtgOvlp(C.Structure):
+    """b200_utg_ovlp_t == fml_ovlp_t (fermi-lite/fml.h:34-37)."""
+    _fields_ = [("len", C.c_uint32, 31), ("from_", C.c_uint32, 1), ("id", C.c_uint32, 31), ("to", C.c_uint32, 1)]
+
+
+class Utg(C.Structure):
+    """b200_utg_t == fml_utg_t (fermi-lite/fml.h:39-46)."""
+    _fields_ = [("len", C.c_int32), ("nsr", C.c_int32), ("seq", C.c_void_p), ("cov", C.c_void_p),
+                ("n_ovlp", C.c_int * 2), ("ovlp", C.POINTER(UtgOvlp))]
+
+
+def utgs_to_py(n, arr):
+    """fml_utg_t array -> list of dicts (seq, cov, nsr, ovlp[(len, from, id, to)])."""
+    out = []
+    for i in range(n):
+        u = arr[i]
+        no = u.n_ovlp[0] + u.n_ovlp[1]
+        out.append(dict(seq=C.string_at(u.seq, u.len), cov=C.string_at(u.cov, u.len), nsr=u.nsr, n_ovlp=(u.n_ovlp[0], u.n_ovlp[1]),
+                        ovlp=[(u.ovlp[j].len, u.ovlp[j].from_, u.ovlp[j].id, u.ovlp[j].to) for j in range(no)]))
     return out

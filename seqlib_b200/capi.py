@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from .abi import (MemOpt, Contig, IndexView, ResultsView, Results, StageStats, INTV_DTYPE, EXT_JOB_DTYPE, EXT_OUT_DTYPE,
-                  np_from_ptr, pack_reads, FmlOpt, Fseq1, FmlStats)
+                  np_from_ptr, pack_reads, FmlOpt, Fseq1, FmlStats, Utg, utgs_to_py)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libseqlib_b200.so")
@@ -26,6 +26,9 @@ EXPORTS = [
     "b200_fml_opt_init", "b200_fml_opt_adjust", "b200_fml_opt_adjust_lens", "b200_fml_correct", "b200_fml_fltuniq",
     "b200_fml_correct_flat", "b200_fml_count", "b200_kmer_table_hist", "b200_kmer_table_size", "b200_kmer_table_lookup",
     "b200_kmer_correct_flat", "b200_kmer_table_destroy", "b200_fml_last_stats",
+    "b200_fml_assemble_flat", "b200_fml_seqs2utg_flat", "b200_fml_assemble", "b200_fml_utg_destroy", "b200_utgs_view",
+    "b200_utgs_free", "b200_fmd_build", "b200_fmd_len", "b200_fmd_info", "b200_fmd_bwt", "b200_fmd_rank1a", "b200_fmd_destroy",
+    "b200_fml_mag_text",
 ]
 
 
@@ -85,6 +88,21 @@ def lib():
         L.b200_kmer_correct_flat.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b200_kmer_table_destroy.argtypes = [C.c_void_p]
         L.b200_fml_last_stats.argtypes = [C.POINTER(FmlStats)]
+        L.b200_fml_assemble_flat.argtypes = [C.POINTER(FmlOpt), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.b200_fml_seqs2utg_flat.argtypes = [C.POINTER(FmlOpt), C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.b200_fml_assemble.argtypes = [C.POINTER(FmlOpt), C.c_int, C.POINTER(Fseq1), C.POINTER(C.c_int), C.POINTER(C.POINTER(Utg))]
+        L.b200_fml_utg_destroy.argtypes = [C.c_int, C.POINTER(Utg)]
+        L.b200_utgs_view.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.POINTER(Utg))]
+        L.b200_utgs_free.argtypes = [C.c_void_p]
+        L.b200_fmd_build.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.b200_fmd_len.restype = C.c_int64
+        L.b200_fmd_len.argtypes = [C.c_void_p]
+        L.b200_fmd_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200_fmd_bwt.argtypes = [C.c_void_p, C.c_void_p]
+        L.b200_fmd_rank1a.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b200_fmd_destroy.argtypes = [C.c_void_p]
+        L.b200_fml_mag_text.argtypes = [C.POINTER(FmlOpt), C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -379,6 +397,83 @@ class KmerTable:
     def close(self):
         if self.h:
             lib().b200_kmer_table_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def _utgs_out(h):
+    n = C.c_int(0)
+    arr = C.POINTER(Utg)()
+    _check(lib().b200_utgs_view(h, C.byref(n), C.byref(arr)))
+    out = utgs_to_py(n.value, arr)
+    lib().b200_utgs_free(h)
+    return out
+
+
+def fml_assemble_flat(opt, seqs, quals, off):
+    """b200_fml_assemble_flat: list of unitig dicts (seq, cov, nsr, n_ovlp, ovlp)."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    quals = None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    h = C.c_void_p()
+    _check(lib().b200_fml_assemble_flat(C.byref(opt), len(off) - 1, _p(seqs), _p(quals), _p(off), C.byref(h)))
+    return _utgs_out(h)
+
+
+def fml_seqs2utg_flat(opt, seqs, off):
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    h = C.c_void_p()
+    _check(lib().b200_fml_seqs2utg_flat(C.byref(opt), len(off) - 1, _p(seqs), _p(off), C.byref(h)))
+    return _utgs_out(h)
+
+
+def fml_mag_text(opt, stage, seqs, off):
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    p = C.c_void_p()
+    ln = C.c_int64(0)
+    rd = C.c_float(0)
+    _check(lib().b200_fml_mag_text(C.byref(opt), stage, len(off) - 1, _p(seqs), _p(off), C.byref(p), C.byref(ln), C.byref(rd)))
+    txt = C.string_at(p, ln.value).decode() if p.value else ""
+    if p.value:
+        C.CDLL(None).free(p)
+    return txt, rd.value
+
+
+class Fmd:
+    """b200_fmd_t: device-resident FMD-index of a read set."""
+
+    def __init__(self, seqs, off):
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        h = C.c_void_p()
+        _check(lib().b200_fmd_build(len(off) - 1, _p(seqs), _p(off), C.byref(h)))
+        self.h = h
+
+    def info(self):
+        cnt = np.zeros(7, dtype=np.uint64)
+        mcnt = np.zeros(7, dtype=np.uint64)
+        _check(lib().b200_fmd_info(self.h, _p(cnt), _p(mcnt)))
+        return cnt, mcnt
+
+    def bwt(self):
+        out = np.zeros(lib().b200_fmd_len(self.h), dtype=np.uint8)
+        _check(lib().b200_fmd_bwt(self.h, _p(out)))
+        return out
+
+    def rank1a(self, q):
+        q = np.ascontiguousarray(q, dtype=np.uint64)
+        ranks = np.zeros((max(len(q), 1), 6), dtype=np.uint64)
+        sym = np.zeros(max(len(q), 1), dtype=np.int32)
+        _check(lib().b200_fmd_rank1a(self.h, len(q), _p(q), _p(ranks), _p(sym)))
+        return ranks[:len(q)], sym[:len(q)]
+
+    def close(self):
+        if self.h:
+            lib().b200_fmd_destroy(self.h)
             self.h = None
 
     def __del__(self):

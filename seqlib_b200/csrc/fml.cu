@@ -11,10 +11,15 @@
 // load = one 32-byte HBM sector).
 #include <cstring>
 #include <cstdlib>
+#include <ctime>
 #include <cub/cub.cuh>
 #include "engine.cuh"
 #include "bfc.cuh"
 #include "fml_host.h"
+#include "fmd_dev.h"
+#include "unitig.cuh"
+#include "utg_walk.h"
+#include "mag_host.h"
 
 using namespace b200;
 
@@ -24,6 +29,16 @@ struct b200_kmer_table {
     u64 n_kmers = 0, n_distinct = 0;
     uint64_t hist[256], hist_high[64];
     CountTable view() const { CountTable t; t.slots = slots.as<CountSlot>(); t.mask = cap - 1; t.k = k; t.l_pre = l_pre; return t; }
+};
+
+struct b200_fmd {             // device-resident FMD-index (rld_t)
+    b200::FmdDevice F;
+};
+
+struct b200_utgs {            // fml_utg_t[] as one handle
+    std::vector<b200::MagUtg> utg;
+    std::vector<b200_utg_t> view;
+    std::vector<std::vector<b200_utg_ovlp_t>> ovlp;
 };
 
 namespace b200 {
@@ -180,6 +195,63 @@ __global__ void __launch_bounds__(256) k_lookup(CountTable tab, i64 n, const cha
     occ[i] = ok ? tab.kmer_occ(x) : -1;
 }
 
+// ------------------------------------------------------------------------------------------------ unitig records
+struct UtgArgs {
+    FmdIndex e; int min_match;
+    UtgNode *node;
+    u8 *seq; UtgNei *nei; UtgMark *mark; u64 seq_cap, nei_cap, mark_cap;
+    unsigned long long *ctr;           // [0] work, [1] seq bytes, [2] nei entries, [3] mark entries, [4] pool overflow, [5] rank queries
+    const u32 *todo; u64 n_todo;
+    u8 *scratch; size_t stride; int cap, s_cap, tmark_cap;
+};
+
+// one string per thread: fm6_retrieve + fm6_get_nei + check_left (unitig.cuh), results bump-allocated into the pools
+__global__ void __launch_bounds__(128) k_utg_nodes(const __grid_constant__ UtgArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    u8 *mine = A.scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.stride;
+    UtgScratch S;
+    utg_scratch_bind(S, mine, A.cap, A.s_cap, A.tmark_cap);
+    const u64 n = A.todo ? A.n_todo : A.e.n_str;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.ctr, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        u64 t = base + lane;
+        if (t < n) {
+            u64 x = A.todo ? (u64)A.todo[t] : t;
+            UtgNode N;
+            utg_node(A.e, A.min_match, x, S, N);
+            N.seq_off = N.nei_off = N.mark_off = 0;
+            if (!(N.flags & UTG_OVERFLOW)) {
+                u64 ns = (u64)(N.len + N.ext_len), nn = (u64)N.n_nei, nm = (u64)(N.n_mark_r + N.n_mark_c);
+                u64 so = ns ? atomicAdd(A.ctr + 1, (unsigned long long)ns) : 0;
+                u64 no = nn ? atomicAdd(A.ctr + 2, (unsigned long long)nn) : 0;
+                u64 mo = nm ? atomicAdd(A.ctr + 3, (unsigned long long)nm) : 0;
+                if (so + ns > A.seq_cap || no + nn > A.nei_cap || mo + nm > A.mark_cap) atomicAdd(A.ctr + 4, 1ull);
+                else {
+                    N.seq_off = so; N.nei_off = no; N.mark_off = mo;
+                    for (u64 i = 0; i < ns; ++i) A.seq[so + i] = S.s[i];
+                    for (u64 i = 0; i < nn; ++i) { UtgNei o; o.x0 = S.nei[i].x[0]; o.x1 = S.nei[i].x[1]; o.x2 = S.nei[i].x[2]; o.ovlp = (i64)S.nei[i].info; A.nei[no + i] = o; }
+                    for (u64 i = 0; i < nm; ++i) A.mark[mo + i] = S.mark[i];
+                }
+            }
+            A.node[x] = N;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fmd_rank(FmdIndex e, i64 n, const u64 *q, u64 *ranks, i32 *sym)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 ok[6];
+    sym[i] = fmd_rank1a(e, q[i], ok);
+    for (int c = 0; c < 6; ++c) ranks[6 * i + c] = ok[c];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct FmlEngine {
     cudaStream_t st = nullptr;
@@ -316,7 +388,7 @@ static void correct_on_device(FmlEngine &E, ReadPool R, const b200_kmer_table *t
     if (flt_uniq) {
         E.d_len.reserve((size_t)n * 4);
         k_flt<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R, tab->view(), bo, E.d_len.as<i32>(), ctr + 1); ++nl;
-        CU_CHECK(cudaMemcpyAsync(len_out, E.d_len.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (len_out) CU_CHECK(cudaMemcpyAsync(len_out, E.d_len.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     } else {
         E.d_codes.reserve((size_t)n);
         EcArgs A;
@@ -360,8 +432,8 @@ static void correct_on_device(FmlEngine &E, ReadPool R, const b200_kmer_table *t
         for (i64 i = 0; i < n; ++i) ++g_fml_stats.ec_codes[codes[i] & 7];
         if (len_out) for (i64 i = 0; i < n; ++i) len_out[i] = (i32)(off[i + 1] - off[i]);
     }
-    CU_CHECK(cudaMemcpyAsync(seqs, R.seq, (size_t)tot, cudaMemcpyDeviceToHost, st));
-    if (quals) CU_CHECK(cudaMemcpyAsync(quals, R.qual, (size_t)tot, cudaMemcpyDeviceToHost, st));
+    if (seqs) CU_CHECK(cudaMemcpyAsync(seqs, R.seq, (size_t)tot, cudaMemcpyDeviceToHost, st));      // null: results stay on the device
+    if (seqs && quals) CU_CHECK(cudaMemcpyAsync(quals, R.qual, (size_t)tot, cudaMemcpyDeviceToHost, st));
     unsigned long long lk = 0;
     CU_CHECK(cudaMemcpyAsync(&lk, ctr + 1, 8, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
@@ -379,6 +451,141 @@ template <class F> static int guarded(F &&f)
     catch (const std::length_error &e) { return fail(B200_ERR_LIMIT, e.what()); }
     catch (const std::invalid_argument &e) { return fail(B200_ERR_ARG, e.what()); }
     catch (const std::exception &e) { return fail(B200_ERR_CUDA, e.what()); }
+}
+
+
+// ------------------------------------------------------------------------------------------------ assembly (host side)
+static double now_ms()
+{
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// per-string overlap records of an index -> host pools
+struct NodeHost {
+    std::vector<UtgNode> node; std::vector<u8> seq; std::vector<UtgNei> nei; std::vector<UtgMark> mark;
+};
+
+static void utg_nodes_on_device(FmlEngine &E, const FmdDevice &F, int min_match, int maxlen, NodeHost &H)
+{
+    cudaStream_t st = E.st;
+    int &nl = g_fml_stats.n_launches;
+    const u64 n_str = F.idx.n_str;
+    H.node.assign(n_str, UtgNode());
+    if (n_str == 0) return;
+    DevBuf d_node, d_seq, d_nei, d_mark, d_todo;
+    d_node.reserve(n_str * sizeof(UtgNode));
+    u64 seq_cap = 2 * F.idx.n + 1024, nei_cap = 4 * n_str + 4096, mark_cap = 4 * n_str + 4096;
+    E.d_ctr.reserve(64);
+    unsigned long long *ctr = E.d_ctr.as<unsigned long long>();
+    for (int attempt = 0;; ++attempt) {
+        if (attempt > 6) throw std::length_error("unitig record pools keep overflowing");
+        d_seq.reserve(seq_cap); d_nei.reserve(nei_cap * sizeof(UtgNei)); d_mark.reserve(mark_cap * sizeof(UtgMark));
+        UtgArgs A;
+        A.e = F.idx; A.min_match = min_match; A.node = d_node.as<UtgNode>();
+        A.seq = d_seq.as<u8>(); A.nei = d_nei.as<UtgNei>(); A.mark = d_mark.as<UtgMark>();
+        A.seq_cap = seq_cap; A.nei_cap = nei_cap; A.mark_cap = mark_cap; A.ctr = ctr;
+        A.todo = nullptr; A.n_todo = 0;
+        A.cap = 2 * maxlen + 64; A.s_cap = 2 * maxlen + 32; A.tmark_cap = 64;
+        A.stride = (utg_scratch_bytes(A.cap, A.s_cap, A.tmark_cap) + 15) & ~(size_t)15;
+        const int threads = 128;
+        int blocks = (int)std::min<u64>((n_str + threads - 1) / threads, (u64)E.sm_count * 8);
+        E.d_scratch.reserve((size_t)blocks * threads * A.stride);
+        A.scratch = E.d_scratch.as<u8>();
+        CU_CHECK(cudaMemsetAsync(ctr, 0, 64, st));
+        k_utg_nodes<<<blocks, threads, 0, st>>>(A); ++nl;
+        unsigned long long c[8];
+        CU_CHECK(cudaMemcpyAsync(c, ctr, 64, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaMemcpyAsync(H.node.data(), d_node.p, n_str * sizeof(UtgNode), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+        CU_CHECK(cudaGetLastError());
+        // strings whose scratch overflowed: same kernel, few threads, large scratch
+        std::vector<u32> todo;
+        for (u64 x = 0; x < n_str; ++x) if (H.node[x].flags & UTG_OVERFLOW) todo.push_back((u32)x);
+        for (int round = 0; !todo.empty(); ++round) {
+            if (round > 3) throw std::length_error("unitig record scratch keeps overflowing");
+            UtgArgs B = A;
+            B.cap = (16 * maxlen + 4096) << (2 * round); B.s_cap = 2 * maxlen + 32; B.tmark_cap = 4096 << (2 * round);
+            B.stride = (utg_scratch_bytes(B.cap, B.s_cap, B.tmark_cap) + 15) & ~(size_t)15;
+            int sb = (int)std::min<size_t>((todo.size() + 31) / 32, 32);
+            E.d_scratch.reserve((size_t)sb * 32 * B.stride);
+            B.scratch = E.d_scratch.as<u8>();
+            d_todo.reserve(todo.size() * 4);
+            CU_CHECK(cudaMemcpyAsync(d_todo.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
+            CU_CHECK(cudaMemsetAsync(ctr, 0, 8, st));
+            B.todo = d_todo.as<u32>(); B.n_todo = todo.size();
+            k_utg_nodes<<<sb, 32, 0, st>>>(B); ++nl;
+            CU_CHECK(cudaMemcpyAsync(c, ctr, 64, cudaMemcpyDeviceToHost, st));
+            CU_CHECK(cudaMemcpyAsync(H.node.data(), d_node.p, n_str * sizeof(UtgNode), cudaMemcpyDeviceToHost, st));
+            CU_CHECK(cudaStreamSynchronize(st));
+            CU_CHECK(cudaGetLastError());
+            std::vector<u32> next;
+            for (u32 x : todo) if (H.node[x].flags & UTG_OVERFLOW) next.push_back(x);
+            todo.swap(next);
+            g_fml_stats.n_spill += B.n_todo;
+        }
+        if (c[4]) {          // a pool was too small: grow to what was asked for and run again
+            seq_cap = std::max<u64>(seq_cap, c[1] + 1024); nei_cap = std::max<u64>(nei_cap, 2 * c[2] + 1024); mark_cap = std::max<u64>(mark_cap, 2 * c[3] + 1024);
+            continue;
+        }
+        H.seq.resize(c[1]); H.nei.resize(c[2]); H.mark.resize(c[3]);
+        if (c[1]) CU_CHECK(cudaMemcpyAsync(H.seq.data(), d_seq.p, c[1], cudaMemcpyDeviceToHost, st));
+        if (c[2]) CU_CHECK(cudaMemcpyAsync(H.nei.data(), d_nei.p, c[2] * sizeof(UtgNei), cudaMemcpyDeviceToHost, st));
+        if (c[3]) CU_CHECK(cudaMemcpyAsync(H.mark.data(), d_mark.p, c[3] * sizeof(UtgMark), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+        break;
+    }
+}
+
+// fml_seq2fmi + fml_fmi2mag over reads resident on the device; g receives the graph as fml_fmi2mag returns it
+static bool mag_from_device_reads(FmlEngine &E, ReadPool R, const i32 *d_len, int maxlen, const b200_fml_opt_t &opt, FmdDevice &F, Mag &g)
+{
+    CU_CHECK(cudaStreamSynchronize(E.st));
+    CU_CHECK(cudaEventRecord(E.ev[4], 0));
+    fmd_build_device(F, R.seq, R.off, d_len, R.n, E.st);
+    CU_CHECK(cudaEventRecord(E.ev[5], 0));
+    CU_CHECK(cudaEventSynchronize(E.ev[5]));
+    g_fml_stats.ms_fmd = ms_between(E.ev[4], E.ev[5]);
+    g_fml_stats.fmd_symbols = F.idx.n; g_fml_stats.n_strings = F.idx.n_str;
+    g.v.clear();
+    if (F.idx.n == 0) return false;          // fml_seq2fmi returned NULL
+    NodeHost H;
+    CU_CHECK(cudaEventRecord(E.ev[4], E.st));
+    utg_nodes_on_device(E, F, opt.min_asm_ovlp, maxlen, H);
+    CU_CHECK(cudaEventRecord(E.ev[5], E.st));
+    CU_CHECK(cudaEventSynchronize(E.ev[5]));
+    g_fml_stats.ms_nodes = ms_between(E.ev[4], E.ev[5]);
+    double t0 = now_ms();
+    UtgPools P; P.node = H.node.data(); P.n_str = F.idx.n_str; P.seq = H.seq.data(); P.nei = H.nei.data(); P.mark = H.mark.data();
+    utg_walk_all(P, opt.min_asm_ovlp, opt.min_merge_len, g);
+    g_fml_stats.ms_walk_host = (float)(now_ms() - t0);
+    g_fml_stats.n_vertices = g.v.size();
+    return true;
+}
+
+static b200_utgs *utgs_from_mag(const Mag &g)
+{
+    b200_utgs *U = new b200_utgs();
+    U->utg = g.to_utg();
+    U->view.resize(U->utg.size()); U->ovlp.resize(U->utg.size());
+    for (size_t i = 0; i < U->utg.size(); ++i) {
+        MagUtg &m = U->utg[i];
+        b200_utg_t &v = U->view[i];
+        v.len = (int32_t)m.seq.size(); v.nsr = m.nsr;
+        v.seq = &m.seq[0]; v.cov = &m.cov[0];          // std::string keeps the terminating NUL
+        v.n_ovlp[0] = m.n_ovlp[0]; v.n_ovlp[1] = m.n_ovlp[1];
+        for (const MagUtgOvlp &o : m.ovlp) { b200_utg_ovlp_t t; t.len = o.len; t.from = (uint32_t)o.from; t.id = o.id; t.to = (uint32_t)o.to; U->ovlp[i].push_back(t); }
+        v.ovlp = U->ovlp[i].empty() ? nullptr : U->ovlp[i].data();
+    }
+    return U;
+}
+
+static int host_maxlen(i64 n, const i64 *off)
+{
+    i64 m = 1;
+    for (i64 i = 0; i < n; ++i) m = std::max(m, off[i + 1] - off[i]);
+    if (m >= (1 << 24)) throw std::length_error("read longer than 2^24 bases");
+    return (int)m;
 }
 
 } // namespace b200
@@ -567,5 +774,235 @@ static int fseq_call(const b200_fml_opt_t *opt, int flt_uniq, int n, b200_fseq1_
 
 int b200_fml_correct(const b200_fml_opt_t *opt, int n, b200_fseq1_t *seqs, float *kcov) { return fseq_call(opt, 0, n, seqs, kcov); }
 int b200_fml_fltuniq(const b200_fml_opt_t *opt, int n, b200_fseq1_t *seqs, float *kcov) { return fseq_call(opt, 1, n, seqs, kcov); }
+
+
+// ------------------------------------------------------------------------------------------------ assembly entry points
+int b200_fmd_build(int64_t n, const char *seqs, const int64_t *off, b200_fmd_t **out)
+{
+    if (!out || n < 0 || (n > 0 && (!seqs || !off))) return fail(B200_ERR_ARG, "b200_fmd_build: bad arguments");
+    *out = nullptr;
+    return guarded([&]() {
+        FmlEngine &E = fml_engine();
+        int64_t zero[1] = {0};
+        ReadPool R = upload_reads(E, n, seqs, nullptr, n > 0 ? off : zero);
+        host_maxlen(n, n > 0 ? off : zero);
+        CU_CHECK(cudaStreamSynchronize(E.st));
+        b200_fmd *f = new b200_fmd();
+        try { fmd_build_device(f->F, R.seq, R.off, nullptr, n, E.st); } catch (...) { delete f; throw; }
+        *out = f;
+        return (int)B200_OK;
+    });
+}
+
+int64_t b200_fmd_len(const b200_fmd_t *f) { return f ? (int64_t)f->F.idx.n : 0; }
+
+int b200_fmd_info(const b200_fmd_t *f, uint64_t cnt[7], uint64_t mcnt[7])
+{
+    if (!f) return fail(B200_ERR_ARG, "null index");
+    for (int i = 0; i < 7; ++i) cnt[i] = f->F.idx.cnt[i];
+    mcnt[0] = f->F.idx.n;
+    for (int i = 1; i < 7; ++i) mcnt[i] = f->F.idx.cnt[i] - f->F.idx.cnt[i - 1];
+    return B200_OK;
+}
+
+int b200_fmd_bwt(const b200_fmd_t *f, uint8_t *bwt)
+{
+    if (!f || !bwt) return fail(B200_ERR_ARG, "b200_fmd_bwt: bad arguments");
+    if (f->F.idx.n == 0) return B200_OK;
+    return guarded([&]() {
+        CU_CHECK(cudaMemcpy(bwt, f->F.bwt8.p, f->F.idx.n, cudaMemcpyDeviceToHost));
+        return (int)B200_OK;
+    });
+}
+
+int b200_fmd_rank1a(const b200_fmd_t *f, int64_t n_q, const uint64_t *q, uint64_t *ranks, int32_t *sym)
+{
+    if (!f || n_q < 0 || (n_q > 0 && (!q || !ranks || !sym))) return fail(B200_ERR_ARG, "b200_fmd_rank1a: bad arguments");
+    if (n_q == 0) return B200_OK;
+    if (f->F.idx.n == 0) return fail(B200_ERR_ARG, "empty index");
+    return guarded([&]() {
+        FmlEngine &E = fml_engine();
+        DevBuf dq, dr, ds;
+        dq.reserve(n_q * 8); dr.reserve(n_q * 48); ds.reserve(n_q * 4);
+        CU_CHECK(cudaMemcpyAsync(dq.p, q, n_q * 8, cudaMemcpyHostToDevice, E.st));
+        k_fmd_rank<<<(unsigned)((n_q + 255) / 256), 256, 0, E.st>>>(f->F.idx, n_q, dq.as<u64>(), dr.as<u64>(), ds.as<i32>());
+        CU_CHECK(cudaMemcpyAsync(ranks, dr.p, n_q * 48, cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaMemcpyAsync(sym, ds.p, n_q * 4, cudaMemcpyDeviceToHost, E.st));
+        CU_CHECK(cudaStreamSynchronize(E.st));
+        CU_CHECK(cudaGetLastError());
+        return (int)B200_OK;
+    });
+}
+
+void b200_fmd_destroy(b200_fmd_t *f) { delete f; }
+
+int b200_fml_mag_text(const b200_fml_opt_t *opt, int stage, int64_t n, const char *seqs, const int64_t *off,
+                      char **text, int64_t *text_len, float *rdist)
+{
+    if (!opt || !text || !text_len || n < 0 || (n > 0 && (!seqs || !off))) return fail(B200_ERR_ARG, "b200_fml_mag_text: bad arguments");
+    *text = nullptr; *text_len = 0;
+    return guarded([&]() {
+        FmlEngine &E = fml_engine();
+        memset(&g_fml_stats, 0, sizeof(g_fml_stats));
+        int64_t zero[1] = {0};
+        ReadPool R = upload_reads(E, n, seqs, nullptr, n > 0 ? off : zero);
+        int maxlen = host_maxlen(n, n > 0 ? off : zero);
+        FmdDevice F; Mag g;
+        mag_from_device_reads(E, R, nullptr, maxlen, *opt, F, g);
+        if (rdist) *rdist = g.rdist;
+        if (stage >= 1) g.fml_clean(*opt);
+        std::string t = g.text();
+        char *o = (char *)malloc(t.size() + 1);
+        if (!o) throw std::bad_alloc();
+        memcpy(o, t.data(), t.size()); o[t.size()] = 0;
+        *text = o; *text_len = (int64_t)t.size();
+        return (int)B200_OK;
+    });
+}
+
+int b200_fml_seqs2utg_flat(const b200_fml_opt_t *opt, int64_t n, const char *seqs, const int64_t *off, b200_utgs_t **out)
+{
+    if (!opt || !out || n < 0 || (n > 0 && (!seqs || !off))) return fail(B200_ERR_ARG, "b200_fml_seqs2utg_flat: bad arguments");
+    *out = nullptr;
+    return guarded([&]() {
+        FmlEngine &E = fml_engine();
+        memset(&g_fml_stats, 0, sizeof(g_fml_stats));
+        int64_t zero[1] = {0};
+        ReadPool R = upload_reads(E, n, seqs, nullptr, n > 0 ? off : zero);
+        int maxlen = host_maxlen(n, n > 0 ? off : zero);
+        FmdDevice F; Mag g;
+        mag_from_device_reads(E, R, nullptr, maxlen, *opt, F, g);
+        double t0 = now_ms();
+        g.fml_clean(*opt);
+        g_fml_stats.ms_clean_host = (float)(now_ms() - t0);
+        *out = utgs_from_mag(g);
+        g_fml_stats.n_utg = (*out)->utg.size();
+        return (int)B200_OK;
+    });
+}
+
+int b200_fml_assemble_flat(const b200_fml_opt_t *opt0, int64_t n, const char *seqs, const char *quals, const int64_t *off, b200_utgs_t **out)
+{
+    if (!opt0 || !out || n < 0 || (n > 0 && (!seqs || !off))) return fail(B200_ERR_ARG, "b200_fml_assemble_flat: bad arguments");
+    *out = nullptr;
+    if (n == 0) { *out = new b200_utgs(); return B200_OK; }
+    return guarded([&]() {
+        FmlEngine &E = fml_engine();
+        memset(&g_fml_stats, 0, sizeof(g_fml_stats));
+        b200_fml_opt_t opt = *opt0;
+        uint64_t tot_len = (uint64_t)off[n];
+        b200_fml_opt_adjust_lens(&opt, n, (int64_t)tot_len);
+        if (opt.ec_k > 63 || opt.min_asm_ovlp > 63 || opt.min_asm_ovlp < 1) throw std::length_error("k-mer length outside [1, 63]");
+        int maxlen = host_maxlen(n, off);
+        CU_CHECK(cudaEventRecord(E.ev[0], E.st));
+        ReadPool R = upload_reads(E, n, seqs, quals, off);
+        float kcov = 0; int min_cov = 0;
+        // fml_correct
+        if (opt.ec_k >= 0) {
+            if (opt.ec_k > 0) {
+                BfcOpt bo; bfc_opt_defaults(bo);
+                bo.k = opt.ec_k; bo.l_pre = fml_initial_l_pre(tot_len);
+                b200_kmer_table tab;
+                CU_CHECK(cudaEventRecord(E.ev[1], E.st));
+                count_on_device(E, R, (i64)tot_len, bo.k, bo.q, bo.l_pre, &tab);
+                CU_CHECK(cudaEventRecord(E.ev[2], E.st));
+                bo.l_pre = tab.l_pre;
+                fml_kcov_min_cov(tab.hist, opt.min_cnt, opt.max_cnt, kcov, min_cov);
+                bo.min_cov = min_cov;
+                correct_on_device(E, R, &tab, bo, fml_hist_mode(tab.hist), 0, nullptr, nullptr, off, nullptr);
+                CU_CHECK(cudaEventRecord(E.ev[3], E.st));
+                CU_CHECK(cudaStreamSynchronize(E.st));
+                g_fml_stats.ms_count = ms_between(E.ev[1], E.ev[2]);
+                g_fml_stats.ms_ec = ms_between(E.ev[2], E.ev[3]);
+            }
+        }
+        // fml_fltuniq
+        {
+            BfcOpt bo; bfc_opt_defaults(bo);
+            bo.k = opt.min_asm_ovlp; bo.l_pre = fml_initial_l_pre(tot_len);
+            b200_kmer_table tab;
+            CU_CHECK(cudaEventRecord(E.ev[1], E.st));
+            count_on_device(E, R, (i64)tot_len, bo.k, bo.q, bo.l_pre, &tab);
+            bo.l_pre = tab.l_pre;
+            fml_kcov_min_cov(tab.hist, opt.min_cnt, opt.max_cnt, kcov, min_cov);
+            bo.min_cov = min_cov;
+            correct_on_device(E, R, &tab, bo, fml_hist_mode(tab.hist), 1, nullptr, nullptr, off, nullptr);
+            CU_CHECK(cudaEventRecord(E.ev[2], E.st));
+            CU_CHECK(cudaStreamSynchronize(E.st));
+            g_fml_stats.ms_flt = ms_between(E.ev[1], E.ev[2]);
+        }
+        // fml_seq2fmi + fml_fmi2mag
+        FmdDevice F; Mag g;
+        if (!mag_from_device_reads(E, R, E.d_len.as<i32>(), maxlen, opt, F, g)) { *out = new b200_utgs(); return (int)B200_OK; }
+        // min_ensr / min_insr from kcov (fermi-lite/misc.c:295-298), fml_mag_clean, fml_mag2utg
+        opt.mag_opt.min_ensr = opt.mag_opt.min_ensr > kcov * .1 ? opt.mag_opt.min_ensr : (int)(kcov * .1 + .499);
+        opt.mag_opt.min_ensr = opt.mag_opt.min_ensr < opt0->max_cnt ? opt.mag_opt.min_ensr : opt0->max_cnt;
+        opt.mag_opt.min_ensr = opt.mag_opt.min_ensr > opt0->min_cnt ? opt.mag_opt.min_ensr : opt0->min_cnt;
+        opt.mag_opt.min_insr = opt.mag_opt.min_ensr - 1;
+        double t0 = now_ms();
+        g.fml_clean(opt);
+        g_fml_stats.ms_clean_host = (float)(now_ms() - t0);
+        *out = utgs_from_mag(g);
+        g_fml_stats.n_utg = (*out)->utg.size();
+        CU_CHECK(cudaEventRecord(E.ev[3], E.st));
+        CU_CHECK(cudaStreamSynchronize(E.st));
+        g_fml_stats.ms_total = ms_between(E.ev[0], E.ev[3]);
+        return (int)B200_OK;
+    });
+}
+
+int b200_utgs_view(const b200_utgs_t *u, int *n_utg, const b200_utg_t **utg)
+{
+    if (!u || !n_utg || !utg) return fail(B200_ERR_ARG, "b200_utgs_view: bad arguments");
+    *n_utg = (int)u->view.size();
+    *utg = u->view.empty() ? nullptr : u->view.data();
+    return B200_OK;
+}
+
+void b200_utgs_free(b200_utgs_t *u) { delete u; }
+
+int b200_fml_assemble(const b200_fml_opt_t *opt, int n_seqs, const b200_fseq1_t *s, int *n_utg, b200_utg_t **utg)
+{
+    if (!opt || !n_utg || !utg || n_seqs < 0 || (n_seqs > 0 && !s)) return fail(B200_ERR_ARG, "b200_fml_assemble: bad arguments");
+    *n_utg = 0; *utg = nullptr;
+    std::vector<int64_t> off((size_t)n_seqs + 1, 0);
+    bool has_qual = n_seqs > 0;
+    for (int i = 0; i < n_seqs; ++i) {
+        off[i + 1] = off[i] + (s[i].l_seq > 0 ? s[i].l_seq : 0);
+        if (s[i].l_seq > 0 && !s[i].qual) has_qual = false;
+    }
+    for (int i = 0; i < n_seqs; ++i) if (s[i].l_seq > 0 && !has_qual && s[i].qual) return fail(B200_ERR_LIMIT, "reads with and without qualities in one batch");
+    std::vector<char> seqs((size_t)off[n_seqs] + 1), quals(has_qual ? (size_t)off[n_seqs] + 1 : 0);
+    for (int i = 0; i < n_seqs; ++i) if (s[i].l_seq > 0) {
+        memcpy(seqs.data() + off[i], s[i].seq, s[i].l_seq);
+        if (has_qual) memcpy(quals.data() + off[i], s[i].qual, s[i].l_seq);
+    }
+    b200_utgs_t *U = nullptr;
+    int rc = b200_fml_assemble_flat(opt, n_seqs, seqs.data(), has_qual ? quals.data() : nullptr, off.data(), &U);
+    if (rc != B200_OK) return rc;
+    int n = (int)U->view.size();
+    if (n == 0) { delete U; return B200_OK; }         // the reference returns NULL with *n_utg untouched by the graph code
+    b200_utg_t *a = (b200_utg_t *)calloc(n, sizeof(b200_utg_t));
+    if (!a) { delete U; return fail(B200_ERR_NOMEM, "out of host memory"); }
+    for (int i = 0; i < n; ++i) {
+        const b200_utg_t &v = U->view[i];
+        a[i] = v;
+        a[i].seq = (char *)malloc(v.len + 1); memcpy(a[i].seq, v.seq, v.len); a[i].seq[v.len] = 0;
+        a[i].cov = (char *)malloc(v.len + 1); memcpy(a[i].cov, v.cov, v.len); a[i].cov[v.len] = 0;
+        int no = v.n_ovlp[0] + v.n_ovlp[1];
+        a[i].ovlp = (b200_utg_ovlp_t *)calloc(no ? no : 1, sizeof(b200_utg_ovlp_t));
+        if (no) memcpy(a[i].ovlp, v.ovlp, no * sizeof(b200_utg_ovlp_t));
+    }
+    delete U;
+    *n_utg = n; *utg = a;
+    return B200_OK;
+}
+
+void b200_fml_utg_destroy(int n_utg, b200_utg_t *utg)
+{
+    if (!utg) return;
+    for (int i = 0; i < n_utg; ++i) { free(utg[i].seq); free(utg[i].cov); free(utg[i].ovlp); }
+    free(utg);
+}
 
 } // extern "C"

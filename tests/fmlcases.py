@@ -67,3 +67,41 @@ def compare(got, z):
         elif not np.array_equal(v, e):
             bad.append("%s differs (%d entries)" % (k, int((np.asarray(v) != np.asarray(e)).sum()) if np.shape(v) == np.shape(e) else -1))
     return bad
+
+
+# ---------------------------------------------------------------------------------------------------- assembly half
+def utg_text(utgs):
+    """Unitigs in fml_utg_print's layout (fermi-lite/misc.c:215-246), one canonical text for comparisons."""
+    out = []
+    for i, u in enumerate(utgs):
+        l0 = "".join("%d,%d;" % (o[2] << 1 | o[3], o[0]) for o in u["ovlp"][:u["n_ovlp"][0]]) or "."
+        l1 = "".join("%d,%d;" % (o[2] << 1 | o[3], o[0]) for o in u["ovlp"][u["n_ovlp"][0]:]) or "."
+        out.append("@%d:%d\t%d\t%s\t%s\n%s\n+\n%s\n" % (i << 1, i << 1 | 1, u["nsr"], l0, l1, u["seq"].decode(), u["cov"].decode()))
+    return "".join(out)
+
+
+def filtered_reads(z, off):
+    """The reads as fml_fltuniq leaves them (input of fml_seq2fmi), from a BFC fixture."""
+    fl = z["flt_lens"]
+    foff = np.zeros(len(fl) + 1, dtype=np.int64)
+    foff[1:] = np.cumsum(fl)
+    return z["flt_seqs"], foff
+
+
+def asm_opt_for(opt, tot_len, n, kcov, clean=True):
+    """Options as fml_assemble hands them to fml_fmi2mag / fml_mag_clean (fermi-lite/misc.c:286-298)."""
+    opt.ec_k = adjusted_ec_k(tot_len, 0)
+    opt.mag_opt.min_elen = int(float(tot_len) / n * 2.5 + .499)
+    if clean:
+        me = opt.mag_opt.min_ensr if opt.mag_opt.min_ensr > kcov * .1 else int(kcov * .1 + .499)
+        me = me if me < opt.max_cnt else opt.max_cnt
+        me = me if me > opt.min_cnt else opt.min_cnt
+        opt.mag_opt.min_ensr = me
+        opt.mag_opt.min_insr = me - 1
+    return opt
+
+
+def load_asm(name):
+    z = np.load(os.path.join(GOLD, name + "_asm.npz"))
+    return dict(bwt_md5=str(z["bwt_md5"]), cnt=z["cnt"], mag0=z["mag0"].tobytes().decode(), mag1=z["mag1"].tobytes().decode(),
+                utg=z["utg"].tobytes().decode(), rdist=float(z["rdist"]), rank_q=z["rank_q"], rank_r=z["rank_r"], rank_s=z["rank_s"])
