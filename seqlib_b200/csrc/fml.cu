@@ -744,17 +744,17 @@ static int fseq_call(const b200_fml_opt_t *opt, int flt_uniq, int n, b200_fseq1_
 {
     if (!opt || n < 0 || (n > 0 && !s)) return fail(B200_ERR_ARG, "bad arguments");
     std::vector<int64_t> off((size_t)n + 1, 0);
-    bool has_qual = n > 0;
+    bool has_qual = false;
     for (int i = 0; i < n; ++i) {
         off[i + 1] = off[i] + (s[i].l_seq > 0 ? s[i].l_seq : 0);
-        if (s[i].l_seq > 0 && !s[i].qual) has_qual = false;
+        if (s[i].l_seq > 0 && s[i].qual) has_qual = true;
     }
-    // the reference decides per read whether qualities exist; a batch mixing both kinds is split by the caller
-    for (int i = 0; i < n; ++i) if (s[i].l_seq > 0 && !has_qual && s[i].qual) return fail(B200_ERR_LIMIT, "reads with and without qualities in one batch");
-    std::vector<char> seqs((size_t)off[n] + 1), quals(has_qual ? (size_t)off[n] + 1 : 0);
+    // the reference decides per read whether qualities exist (qual == NULL: every base counts as high quality and no
+    // quality is written back): such reads ride along with a filler above any threshold
+    std::vector<char> seqs((size_t)off[n] + 1), quals(has_qual ? (size_t)off[n] + 1 : 0, '~');
     for (int i = 0; i < n; ++i) if (s[i].l_seq > 0) {
         memcpy(seqs.data() + off[i], s[i].seq, s[i].l_seq);
-        if (has_qual) memcpy(quals.data() + off[i], s[i].qual, s[i].l_seq);
+        if (s[i].qual) memcpy(quals.data() + off[i], s[i].qual, s[i].l_seq);
     }
     std::vector<int32_t> len((size_t)n + 1);
     int rc = b200_fml_correct_flat(opt, flt_uniq, n, seqs.data(), has_qual ? quals.data() : nullptr, off.data(), len.data(), kcov);
@@ -766,7 +766,7 @@ static int fseq_call(const b200_fml_opt_t *opt, int flt_uniq, int n, b200_fseq1_
         }
         if (flt_uniq && len[i] == 0) { free(s[i].seq); free(s[i].qual); s[i].l_seq = 0; s[i].seq = s[i].qual = nullptr; continue; }
         memcpy(s[i].seq, seqs.data() + off[i], len[i]); s[i].seq[len[i]] = 0;
-        if (has_qual) { memcpy(s[i].qual, quals.data() + off[i], len[i]); s[i].qual[len[i]] = 0; }
+        if (s[i].qual) { memcpy(s[i].qual, quals.data() + off[i], len[i]); s[i].qual[len[i]] = 0; }
         s[i].l_seq = len[i];
     }
     return B200_OK;
@@ -966,16 +966,15 @@ int b200_fml_assemble(const b200_fml_opt_t *opt, int n_seqs, const b200_fseq1_t 
     if (!opt || !n_utg || !utg || n_seqs < 0 || (n_seqs > 0 && !s)) return fail(B200_ERR_ARG, "b200_fml_assemble: bad arguments");
     *n_utg = 0; *utg = nullptr;
     std::vector<int64_t> off((size_t)n_seqs + 1, 0);
-    bool has_qual = n_seqs > 0;
+    bool has_qual = false;
     for (int i = 0; i < n_seqs; ++i) {
         off[i + 1] = off[i] + (s[i].l_seq > 0 ? s[i].l_seq : 0);
-        if (s[i].l_seq > 0 && !s[i].qual) has_qual = false;
+        if (s[i].l_seq > 0 && s[i].qual) has_qual = true;
     }
-    for (int i = 0; i < n_seqs; ++i) if (s[i].l_seq > 0 && !has_qual && s[i].qual) return fail(B200_ERR_LIMIT, "reads with and without qualities in one batch");
-    std::vector<char> seqs((size_t)off[n_seqs] + 1), quals(has_qual ? (size_t)off[n_seqs] + 1 : 0);
+    std::vector<char> seqs((size_t)off[n_seqs] + 1), quals(has_qual ? (size_t)off[n_seqs] + 1 : 0, '~');
     for (int i = 0; i < n_seqs; ++i) if (s[i].l_seq > 0) {
         memcpy(seqs.data() + off[i], s[i].seq, s[i].l_seq);
-        if (has_qual) memcpy(quals.data() + off[i], s[i].qual, s[i].l_seq);
+        if (s[i].qual) memcpy(quals.data() + off[i], s[i].qual, s[i].l_seq);
     }
     b200_utgs_t *U = nullptr;
     int rc = b200_fml_assemble_flat(opt, n_seqs, seqs.data(), has_qual ? quals.data() : nullptr, off.data(), &U);

@@ -129,3 +129,51 @@ def test_direct_assemble_and_fseq_entry(capi):
     assert capi.lib().b200_fml_assemble(C.byref(o2), n, arr, C.byref(nu), C.byref(up)) == 0
     assert fmlcases.utg_text(utgs_to_py(nu.value, up)) == gold["utg"]
     capi.lib().b200_fml_utg_destroy(nu.value, up)
+
+
+def _cxx_exe(name):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cxx", name)
+    src = exe + ".cpp"
+    lib = os.path.join(root, "seqlib_b200", "libSeqLibB200.so")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "seqlib_b200", "cxx")])
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(lib)):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "include"), "-o", exe, src,
+                               "-L" + os.path.join(root, "seqlib_b200"), "-lSeqLibB200", "-lseqlib_b200",
+                               "-Wl,-rpath," + os.path.join(root, "seqlib_b200")])
+    return exe
+
+
+def test_cxx_fermi_assembler_and_bfc(capi, tmp_path):
+    """SeqLib::FermiAssembler::PerformAssembly through the C++ drop-in class gives the golden unitigs; the BFC ->
+    DirectAssemble flow of the reference's "correct_and_assemble" test runs and agrees with the flat ABI."""
+    import subprocess
+    exe = _cxx_exe("test_fermi")
+    seqs, quals, off, z = fmlcases.load("fml_mt_2k")
+    gold = fmlcases.load_asm("fml_mt_2k")
+    rs, rq = unpack_reads(seqs, off), unpack_reads(quals, off)
+    tsv = tmp_path / "reads.tsv"
+    with open(tsv, "w") as f:
+        for i, (a, b) in enumerate(zip(rs, rq)):
+            f.write("r%d\t%s\t%s\n" % (i, a.decode(), b.decode()))
+    r = subprocess.run([exe, str(tsv), "assemble"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = [ln for ln in gold["utg"].split("\n")[1::4]]
+    assert r.stdout.split() == want
+    r = subprocess.run([exe, str(tsv), "bfc"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    contigs = r.stdout.split()
+    assert contigs and max(len(c) for c in contigs) > 1000
+    # the same flow on the flat ABI: count + correct with the trained k, then the assembly half with DirectAssemble's options
+    kmer = int(r.stderr.split("kmer ")[1].split()[0])
+    o = capi.fml_default_opt()
+    o.ec_k = kmer
+    cs, cq, _, kcov = capi.fml_correct_flat(o, seqs, quals, off)
+    up = np.frombuffer(cs.tobytes().upper(), dtype=np.uint8)
+    o2 = capi.fml_default_opt()
+    me = o2.mag_opt.min_ensr if o2.mag_opt.min_ensr > kcov * .1 else int(kcov * .1 + .499)
+    o2.mag_opt.min_ensr, o2.mag_opt.min_insr = me, me - 1
+    flat = capi.fml_seqs2utg_flat(o2, up, off)
+    assert [u["seq"].decode() for u in flat] == contigs
