@@ -179,10 +179,10 @@ HD void bfc_opt_defaults(BfcOpt &o)
     o.w_ec = 1; o.w_ec_high = 7; o.w_absent = 3; o.w_absent_high = 1; o.max_path_diff = 15; o.max_heap = 100;
 }
 
-struct EcBase {      // ecbase_t (fermi-lite/bfc.h:86-91)
-    u8 b, q, ob, oq, lcov, hcov;
-    u8 solid_end, high_end;
-    u8 ec, absent;
+struct EcBase {      // ecbase_t (fermi-lite/bfc.h:86-91) packed into 4 bytes; lcov / hcov are 6-bit counters in the reference
+    u8 b : 3, q : 1, ob : 3, oq : 1;
+    u8 lcov, hcov;
+    u8 solid_end : 1, high_end : 1;
 };
 
 enum { BFC_EC_HIST = 5, BFC_EC_HIST_HIGH = 2, BFC_MAX_PATHS = 4 };
@@ -201,9 +201,11 @@ struct EcStack {     // ecstack1_t
     u8 b; EcPenalty pen; u16 cnt;
 };
 
+struct EcHeapKey { int tot_pen, slot; };      // what the binary heap moves around; the 72-byte entry stays put in `pool`
+
 struct EcScratch {
     EcBase *seq; u8 *ec0, *ec1;     // len entries each; of the two corrected copies only the base is ever read back
-    EcHeap *heap; int heap_cap, heap_n;
+    EcHeapKey *heap; EcHeap *pool; u8 *free_; int heap_cap, heap_n, n_free;
     EcStack *stack; int stack_cap, stack_n;
     int heap_hw, stack_hw;          // high-water marks (scratch sizing)
     bool overflow;
@@ -211,15 +213,20 @@ struct EcScratch {
 
 HD size_t ec_scratch_bytes(int maxlen, int heap_cap, int stack_cap)
 {
-    return (((size_t)maxlen * (sizeof(EcBase) + 2) + 15) & ~(size_t)15) + (size_t)heap_cap * sizeof(EcHeap) + (size_t)stack_cap * sizeof(EcStack);
+    return (((size_t)maxlen * (sizeof(EcBase) + 2) + 15) & ~(size_t)15) + (size_t)(heap_cap + 2) * sizeof(EcHeap)
+         + (size_t)(heap_cap + 2) * sizeof(EcHeapKey) + (((size_t)heap_cap + 2 + 15) & ~(size_t)15) + (size_t)stack_cap * sizeof(EcStack);
 }
 
 HD void ec_scratch_bind(EcScratch &s, u8 *p, int maxlen, int heap_cap, int stack_cap)
 {
     s.seq = (EcBase *)p; s.ec0 = (u8 *)(s.seq + maxlen); s.ec1 = s.ec0 + maxlen;     // p is 16-byte aligned
     p += ((size_t)maxlen * (sizeof(EcBase) + 2) + 15) & ~(size_t)15;
-    s.heap = (EcHeap *)p; s.heap_cap = heap_cap; s.heap_n = 0;
-    p += (size_t)heap_cap * sizeof(EcHeap);
+    s.pool = (EcHeap *)p; s.heap_cap = heap_cap; s.heap_n = 0;
+    p += (size_t)(heap_cap + 2) * sizeof(EcHeap);
+    s.heap = (EcHeapKey *)p;
+    p += (size_t)(heap_cap + 2) * sizeof(EcHeapKey);
+    s.free_ = p; s.n_free = 0;
+    p += ((size_t)heap_cap + 2 + 15) & ~(size_t)15;
     s.stack = (EcStack *)p; s.stack_cap = stack_cap; s.stack_n = 0;
     s.heap_hw = s.stack_hw = 0;
     s.overflow = false;
@@ -231,10 +238,10 @@ HD int weighted_penalty(const BfcOpt &o, const EcPenalty &p)
 }
 
 // ks_heapup_ec / ks_heapdown_ec (fermi-lite/ksort.h:125-146) with heap_lt(a, b) = a.tot_pen > b.tot_pen
-HD void ec_heapup(int n, EcHeap *l)
+HD void ec_heapup(int n, EcHeapKey *l)
 {
     int k = n - 1;
-    EcHeap tmp = l[k];
+    EcHeapKey tmp = l[k];
     while (k) {
         int i = (k - 1) >> 1;
         if (tmp.tot_pen > l[i].tot_pen) break;
@@ -243,10 +250,10 @@ HD void ec_heapup(int n, EcHeap *l)
     l[k] = tmp;
 }
 
-HD void ec_heapdown(int i, int n, EcHeap *l)
+HD void ec_heapdown(int i, int n, EcHeapKey *l)
 {
     int k = i;
-    EcHeap tmp = l[i];
+    EcHeapKey tmp = l[i];
     while ((k = (k << 1) + 1) < n) {
         if (k != n - 1 && l[k].tot_pen > l[k + 1].tot_pen) ++k;
         if (l[k].tot_pen > tmp.tot_pen) break;
@@ -263,7 +270,7 @@ HD void ec_seq_conv(const char *s, const char *q, int l, int qthres, EcBase *a)
         c.b = c.ob = (u8)nt6m1((unsigned char)s[i]);
         c.q = c.oq = !q ? 1 : (q[i] - 33 >= qthres ? 1 : 0);
         if (c.b > 3) c.q = c.oq = 0;
-        c.lcov = c.hcov = c.solid_end = c.high_end = c.ec = c.absent = 0;
+        c.lcov = c.hcov = 0; c.solid_end = c.high_end = 0;
         a[i] = c;
     }
 }
@@ -330,6 +337,9 @@ HD int ec_first_kmer(int k, const EcBase *a, int n, int start, Kmer4 &x)
     return i;
 }
 
+// bfc_ec_kcov (fermi-lite/bfc.c:175-196).  The reference bumps lcov / hcov of all k positions under every solid k-mer; the
+// same 6-bit counters come out of one backward sweep with running window sums (positions covered by the k-mers that END in
+// [j, j + k - 1]).
 template <class Tab>
 HD void ec_kcov(int k, int min_occ, EcBase *a, int n, const Tab &ch)
 {
@@ -337,23 +347,23 @@ HD void ec_kcov(int k, int min_occ, EcBase *a, int n, const Tab &ch)
     int l = 0;
     for (int i = 0; i < n; ++i) {
         EcBase &c = a[i];
-        c.high_end = c.solid_end = c.lcov = c.hcov = 0;
+        c.high_end = c.solid_end = 0; c.lcov = c.hcov = 0;
         if (c.b < 4) {
             kmer_append(k, x.x, c.b);
             if (++l >= k) {
                 int r = ch.kmer_occ(x);
                 if (r >= 0) {
                     if ((r >> 8 & 0x3f) >= min_occ + 1) c.high_end = 1;
-                    if ((r & 0xff) >= min_occ) {
-                        c.solid_end = 1;
-                        for (int j = i - k + 1; j <= i; ++j) {      // 6-bit counters in the reference
-                            a[j].lcov = (a[j].lcov + 1) & 63;
-                            a[j].hcov = (a[j].hcov + c.high_end) & 63;
-                        }
-                    }
+                    if ((r & 0xff) >= min_occ) c.solid_end = 1;
                 }
             }
         } else { l = 0; kmer_clear(x); }
+    }
+    int ls = 0, hs = 0;
+    for (int j = n - 1; j >= 0; --j) {
+        if (a[j].solid_end) { ++ls; hs += a[j].high_end; }
+        if (j + k < n && a[j + k].solid_end) { --ls; hs -= a[j + k].high_end; }
+        a[j].lcov = (u8)(ls & 63); a[j].hcov = (u8)(hs & 63);
     }
 }
 
@@ -373,12 +383,13 @@ HD u64 ec_best_island(int k, const EcBase *a, int n)
 // buf_update (fermi-lite/bfc.c:231-263)
 HD void ec_buf_update(const BfcOpt &o, EcScratch &e, const EcHeap &prev, const EcPenalty &pen, int cnt)
 {
-    if (e.stack_n >= e.stack_cap || e.heap_n >= e.heap_cap) { e.overflow = true; return; }
+    if (e.stack_n >= e.stack_cap || e.heap_n >= e.heap_cap || e.n_free == 0) { e.overflow = true; return; }
     EcStack &q = e.stack[e.stack_n++];
     q.parent = prev.k; q.i = prev.i; q.b = pen.b; q.pen = pen;
     q.cnt = cnt > 0 ? (u16)(cnt & 0xff) : 0;
     q.tot_pen = prev.tot_pen + weighted_penalty(o, pen);
-    EcHeap &r = e.heap[e.heap_n++];
+    const int slot = e.free_[--e.n_free];
+    EcHeap &r = e.pool[slot];
     r.i = prev.i + 1;
     r.k = e.stack_n - 1;
     r.x = prev.x;
@@ -392,6 +403,8 @@ HD void ec_buf_update(const BfcOpt &o, EcScratch &e, const EcHeap &prev, const E
     } else for (int t = 0; t < BFC_EC_HIST; ++t) r.ecpos[t] = prev.ecpos[t];
     r.tot_pen = q.tot_pen;
     kmer_append(o.k, r.x.x, pen.b);
+    EcHeapKey hk; hk.tot_pen = r.tot_pen; hk.slot = slot;
+    e.heap[e.heap_n++] = hk;
     ec_heapup(e.heap_n, e.heap);
     if (e.heap_n > e.heap_hw) e.heap_hw = e.heap_n;
     if (e.stack_n > e.stack_hw) e.stack_hw = e.stack_n;
@@ -416,9 +429,13 @@ HD int ec_backtrack(const EcStack *s, int end, int n, u8 *path)
 template <class Tab>
 HD int ec1dir(const BfcOpt &o, const Tab &ch, EcScratch &e, const EcBase *seq, int n, u8 *ec, int start, int end)
 {
-    EcHeap z;
     int i, l, rv = -1, path[BFC_MAX_PATHS], n_paths = 0, min_path = -1, min_path_pen = 0x7fffffff, n_failures = 0;
     e.heap_n = e.stack_n = 0;
+    e.n_free = e.heap_cap + 2;
+    for (i = 0; i < e.n_free; ++i) e.free_[i] = (u8)(e.n_free - 1 - i);      // slot 0 is handed out first
+    int zslot = e.free_[--e.n_free];
+    EcHeap &z0 = e.pool[zslot];
+    EcHeap z;
     z.tot_pen = 0; z.i = 0; z.k = 0; kmer_clear(z.x);
     for (z.i = start, l = 0; z.i < end; ++z.i) {
         int c = seq[z.i].b;
@@ -430,12 +447,17 @@ HD int ec1dir(const BfcOpt &o, const Tab &ch, EcScratch &e, const EcBase *seq, i
     z.k = -1;
     for (i = 0; i < BFC_EC_HIST; ++i) z.ecpos[i] = -1;
     for (i = 0; i < BFC_EC_HIST_HIGH; ++i) z.ecpos_high[i] = -1;
-    e.heap[e.heap_n++] = z;
+    z0 = z;
+    { EcHeapKey hk; hk.tot_pen = 0; hk.slot = zslot; e.heap[e.heap_n++] = hk; }
+    zslot = -1;
     for (i = 0; i < n; ++i) ec[i] = seq[i].b;
     for (;;) {
         int stop = 0;
+        if (zslot >= 0) e.free_[e.n_free++] = (u8)zslot;        // the entry popped last round is no longer referenced
+        zslot = -1;
         if (e.heap_n == 0) { rv = -2; break; }
-        z = e.heap[0];
+        zslot = e.heap[0].slot;
+        z = e.pool[zslot];
         e.heap[0] = e.heap[--e.heap_n];
         ec_heapdown(0, e.heap_n, e.heap);
         if (min_path >= 0 && z.tot_pen > min_path_pen + o.max_path_diff) break;

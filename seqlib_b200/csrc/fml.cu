@@ -167,6 +167,28 @@ __global__ void __launch_bounds__(128) k_ec(const __grid_constant__ EcArgs A)
     if (lane == 0) atomicAdd(A.lookups, x);
 }
 
+// Scheduling key of a read for k_ec: reads whose k-mers are all solid walk the "fixed" fast path (one probe per base), every
+// non-solid k-mer opens a search.  Warps that get reads of similar difficulty diverge less, and the hardest reads go first so
+// they do not form the tail of the launch.  (Purely an ordering: k_ec recomputes everything it needs.)
+__global__ void __launch_bounds__(256) k_ec_difficulty(ReadPool R, CountTable tab, int min_cov, u32 *key, u32 *idx)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n) return;
+    i64 b = R.off[i];
+    int len = (int)(R.off[i + 1] - b), l = 0, bad = 0;
+    const char *s = R.seq + b;
+    Kmer4 x; kmer_clear(x);
+    for (int j = 0; j < len; ++j) {
+        int c = nt6m1((unsigned char)s[j]);
+        if (c < 4) {
+            kmer_append(tab.k, x.x, c);
+            if (++l >= tab.k) { int r = tab.kmer_occ(x); if (r < 0 || (r & 0xff) < min_cov) ++bad; }
+        } else { l = 0; kmer_clear(x); bad += tab.k; }
+    }
+    key[i] = ~(u32)bad;          // ascending sort -> most non-solid k-mers first
+    idx[i] = (u32)i;
+}
+
 __global__ void __launch_bounds__(256) k_flt(ReadPool R, CountTable tab, BfcOpt opt, i32 *len_out, unsigned long long *lookups)
 {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,7 +279,7 @@ struct FmlEngine {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[6];
     int sm_count = 0;
-    DevBuf d_seq, d_qual, d_off, d_cnt, d_recoff, d_lo[2], d_hi[2], d_flags, d_starts, d_tmp, d_hist, d_len, d_codes, d_scratch, d_ctr, d_todo;
+    DevBuf d_seq, d_qual, d_off, d_cnt, d_recoff, d_lo[2], d_hi[2], d_flags, d_starts, d_tmp, d_hist, d_len, d_codes, d_scratch, d_ctr, d_todo, d_order[2];
     bool ready = false;
     void init()
     {
@@ -400,6 +422,15 @@ static void correct_on_device(FmlEngine &E, ReadPool R, const b200_kmer_table *t
         E.d_scratch.reserve((size_t)blocks * threads * A.scratch_stride);
         A.scratch = E.d_scratch.as<u8>();
         A.todo = nullptr; A.n_todo = 0; A.codes = E.d_codes.as<u8>(); A.work = ctr; A.lookups = ctr + 1;
+        if (n >= 4096 && n < (1ll << 31)) {       // order the reads by difficulty (see k_ec_difficulty)
+            E.d_cnt.reserve((size_t)n * 4); E.d_starts.reserve((size_t)n * 4); E.d_order[0].reserve((size_t)n * 4); E.d_order[1].reserve((size_t)n * 4);
+            k_ec_difficulty<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R, A.tab, bo.min_cov, E.d_cnt.as<u32>(), E.d_order[0].as<u32>()); ++nl;
+            size_t tb = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, E.d_cnt.as<u32>(), E.d_starts.as<u32>(), E.d_order[0].as<u32>(), E.d_order[1].as<u32>(), (int)n, 0, 32, st);
+            E.d_tmp.reserve(tb);
+            cub::DeviceRadixSort::SortPairs(E.d_tmp.p, tb, E.d_cnt.as<u32>(), E.d_starts.as<u32>(), E.d_order[0].as<u32>(), E.d_order[1].as<u32>(), (int)n, 0, 32, st); ++nl;
+            A.todo = E.d_order[1].as<u32>(); A.n_todo = n;
+        }
         k_ec<<<blocks, threads, 0, st>>>(A); ++nl;
         std::vector<u8> codes((size_t)n);
         CU_CHECK(cudaMemcpyAsync(codes.data(), E.d_codes.p, (size_t)n, cudaMemcpyDeviceToHost, st));

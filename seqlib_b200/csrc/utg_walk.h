@@ -26,7 +26,7 @@ struct UtgWalker {
     // state of the walk in progress (aux_t + the kstrings of thrdat_t)
     std::string s, cov;
     std::vector<MagEdge> nei;           // copy_nei's view of a->nei: (x[0], info)
-    u64 last_nei_x1 = 0, last_nei_x2 = 0;
+    std::vector<int> dcov;              // pending coverage increments of the current direction, as a difference array
 
     UtgWalker(const UtgPools &p, int mm, int mml) : P(p), min_match(mm), min_merge_len(mml)
     {
@@ -71,12 +71,25 @@ struct UtgWalker {
             set_bits(nn[0].x0, nn[0].x1, nn[0].x2);
             ++n_reads;
             s.append((const char *)(P.seq + N.seq_off + N.len), (size_t)N.ext_len);
-            for (int i = rbeg; i < ori_l; ++i) if (cov[i] != '~') ++cov[i];
+            // the reference bumps cov[rbeg, ori_l) by one, saturating at '~': saturating adds commute, so the bumps are
+            // collected as a difference array and applied once per direction (flush_cov)
+            dcov.resize(s.size() + 1, 0);
+            ++dcov[rbeg]; --dcov[ori_l];
             cov.append((size_t)N.ext_len, '"');
             beg = rbeg; ori_l = (int)s.size();
             cur = nn[0].x1;
         }
+        flush_cov();
         return n_reads;
+    }
+    void flush_cov()
+    {
+        int run = 0;
+        for (size_t i = 0; i < dcov.size() && i < cov.size(); ++i) {
+            run += dcov[i];
+            if (run) { int c = (unsigned char)cov[i] + run; cov[i] = (char)(c > '~' ? '~' : c); }
+        }
+        dcov.clear();
     }
 
     // unitig1 + the bookkeeping of worker(); returns true when a vertex was appended to g
