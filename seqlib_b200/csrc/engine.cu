@@ -778,11 +778,18 @@ int b200_mem_align_batch(const b200_index_t *idx, const b200_mem_opt_t *opt, int
     if (!out) return fail(B200_ERR_ARG, "out is NULL");
     *out = nullptr;
     b200_batch_t *b = nullptr;
+    static int trace = getenv("B200_TRACE") ? 1 : 0;
+    double t0 = wall_now();
     int rc = b200_batch_create(idx, opt, n, seqs, off, ids, &b);
     if (rc != B200_OK) return rc;
+    double t1 = wall_now();
     rc = b200_batch_run(b, nullptr);
+    double t2 = wall_now();
     if (rc == B200_OK) rc = b200_batch_fetch(b, out);
+    double t3 = wall_now();
     b200_batch_destroy(b);
+    if (trace) fprintf(stderr, "[b200 trace] align_batch n=%lld: create %.1f ms, run %.1f ms, fetch %.1f ms, destroy %.1f ms\n", (long long)n,
+                       1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (wall_now() - t3));
     return rc;
 }
 

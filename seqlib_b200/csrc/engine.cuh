@@ -4,6 +4,8 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <mutex>
+#include <cstdlib>
 #include "pipeline.cuh"
 #include "hostutil.h"
 
@@ -17,16 +19,64 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 #define CU_CHECK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \
     throw b200::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); } while (0)
 
-// A cudaMalloc'd buffer that grows on demand (never shrinks).
+// Device memory comes from a process-wide pool: cudaMalloc / cudaFree of the 10^8..10^9-byte buffers a batch needs cost
+// 10-500 ms per call (cudaFree also synchronises the device), which was most of the end-to-end time of
+// b200_mem_align_batch.  Blocks are handed back on release() and reused best-fit; the pool keeps at most
+// B200_DEVPOOL_GB (default 48) GB and frees the rest.  A block is only released after the work that used it was
+// synchronised (every caller syncs its stream before its buffers go out of scope).
+struct DevPool {
+    struct Blk { void *p; size_t cap; int dev; };
+    std::vector<Blk> free_;
+    std::mutex mu;
+    size_t pooled = 0, limit = 0;
+    void *get(size_t want, size_t &cap)
+    {
+        int dev = 0; cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int best = -1;
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].dev == dev && free_[i].cap >= want && free_[i].cap <= 2 * want + (1u << 20) && (best < 0 || free_[i].cap < free_[best].cap)) best = (int)i;
+            if (best >= 0) { Blk b = free_[best]; free_.erase(free_.begin() + best); pooled -= b.cap; cap = b.cap; return b.p; }
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {              // out of memory: drop everything pooled and try once more
+            cudaGetLastError();
+            trim(0);
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+        cap = want;
+        return p;
+    }
+    void put(void *p, size_t cap)
+    {
+        if (!p) return;
+        int dev = 0; cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> g(mu);
+        if (!limit) { const char *e = getenv("B200_DEVPOOL_GB"); limit = (size_t)((e ? atof(e) : 48.0) * (1ull << 30)); if (!limit) limit = 1; }
+        if (cap > limit / 2 || pooled + cap > limit || free_.size() >= 256) { cudaFree(p); return; }
+        free_.push_back(Blk{p, cap, dev}); pooled += cap;
+    }
+    void trim(size_t keep)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        while (!free_.empty() && pooled > keep) { cudaFree(free_.back().p); pooled -= free_.back().cap; free_.pop_back(); }
+    }
+};
+inline DevPool &dev_pool() { static DevPool *p = new DevPool(); return *p; }     // never destroyed: outlives static DevBufs
+
+// A device buffer that grows on demand (never shrinks), backed by the pool.
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        release();
         size_t want = bytes + (bytes >> 3) + 256;
-        CU_CHECK(cudaMalloc(&p, want)); cap = want;
+        p = dev_pool().get(want, cap);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) dev_pool().put(p, cap); p = nullptr; cap = 0; }
     template <class T> T *as() const { return (T *)p; }
     ~DevBuf() { release(); }
 };

@@ -87,6 +87,7 @@ int pick_sa_shift(u64 seq_len, int max_shift)
     if (e) { int v = atoi(e); if (v < 0) v = 0; if (v > max_shift) v = max_shift; return v; }
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return max_shift;
+    fr += dev_pool().pooled;          // pooled blocks are reclaimable
     for (int s = 0; s <= max_shift; ++s) {
         u64 bytes = ((seq_len >> s) + 1) * 8;
         if (bytes <= fr / 3) return s;
@@ -210,7 +211,7 @@ void image_from_bwa_arrays(b200_index *idx)
     BlobHeader h = plan_blob(N, idx->l_pac, shift, idx->contigs);
     h.primary = idx->primary; for (int i = 0; i < 5; ++i) h.L2[i] = idx->L2[i];
     void *blob = nullptr;
-    CU_CHECK(cudaMalloc(&blob, h.total_bytes));
+    if (cudaMalloc(&blob, h.total_bytes) != cudaSuccess) { cudaGetLastError(); dev_pool().trim(0); CU_CHECK(cudaMalloc(&blob, h.total_bytes)); }
     CU_CHECK(cudaMemset(blob, 0, h.total_bytes));
     idx->owns_blob = true;
     upload_blob_meta(blob, h, idx->contigs, 0);
@@ -337,7 +338,7 @@ static int construct_common(b200_index *idx, int flags)
     int shift = pick_sa_shift(N, 5);
     BlobHeader h = plan_blob(N, idx->l_pac, shift, idx->contigs);
     void *blob = nullptr;
-    CU_CHECK(cudaMalloc(&blob, h.total_bytes));
+    if (cudaMalloc(&blob, h.total_bytes) != cudaSuccess) { cudaGetLastError(); dev_pool().trim(0); CU_CHECK(cudaMalloc(&blob, h.total_bytes)); }
     CU_CHECK(cudaMemset(blob, 0, h.total_bytes));
     idx->owns_blob = true;
     idx->seq_len = N;
