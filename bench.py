@@ -92,6 +92,16 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def seed_traffic_per_read():
+    """DRAM bytes per read of the seeding kernel from the committed ncu --set full capture (None if absent)."""
+    p = os.path.join(ROOT, "profiles", "r01_seed_traffic.json")
+    try:
+        d = json.load(open(p))
+        return (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["reads_in_launch"], d["source"]
+    except Exception:
+        return None, None
+
+
 def make_workload(args, n_total_reads):
     from seqlib_b200 import synth
     l_pac = args.ref_len
@@ -334,8 +344,12 @@ def main():
         # roofline of the dominant kernel (k_seed): algorithmic bytes = 32 B per Occ block fetched + the read bases + the emitted intervals
         seed_s = stage["ms_seed"] / 1000.0 / args.steps
         occ_per_step = stats["occ_blocks"]
+        # one launch of the seeding kernel covers one chunk of min(2^20, n_per) reads; achieved / traffic are per launch
+        chunk = min(1 << 20, n_per)
+        n_seed_launches = (n_per + chunk - 1) // chunk
         alg_bytes = occ_per_step * 32 + n_per * L
         achieved = alg_bytes / seed_s / 1e9 if seed_s > 0 else 0.0
+        tpr, tsrc = seed_traffic_per_read()
         line = {
             "metric": "150bp reads/sec (seed+chain+SW end-to-end)", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True,
@@ -348,8 +362,11 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_stage<0> (SMEM seeding)", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                         "frac": achieved / peaks.get("hbm_gbs", 6650.0), "traffic": None, "peak_source": how,
-                         "algorithmic_bytes_per_read": alg_bytes / n_per, "kernel_ms": 1000.0 * seed_s},
+                         "frac": achieved / peaks.get("hbm_gbs", 6650.0), "traffic": (tpr * chunk if tpr else None), "peak_source": how,
+                         "traffic_source": tsrc, "algorithmic_bytes_per_launch": alg_bytes / n_seed_launches,
+                         "launches_per_step": n_seed_launches, "kernel_ms_per_launch": 1000.0 * seed_s / n_seed_launches,
+                         "algorithmic_bytes_per_read": alg_bytes / n_per, "kernel_ms": 1000.0 * seed_s,
+                         "note": "dependent random 32-B gathers: the measured ceiling of this access pattern on B200 is 38.4 G gathers/s = 1229 GB/s (scripts/microbench/gather_bw.cu)"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_s_timed_region": wall_s, "mapped_fraction": mapped, "hits_per_step": n_hits_dev,
             "index_build_s": t_index, "index_bcast_s": t_bcast, "spill_reads_per_step": stats["n_overflow"],

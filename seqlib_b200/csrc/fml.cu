@@ -136,7 +136,8 @@ struct CountingTable {       // CountTable + a probe counter (roofline accountin
     __device__ int kmer_occ(const Kmer4 &z) const { ++n; return t.kmer_occ(z); }
 };
 
-__global__ void __launch_bounds__(128) k_ec(const __grid_constant__ EcArgs A)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_ec(const __grid_constant__ EcArgs A)
 {
     const int lane = threadIdx.x & 31;
     EcScratch e;
@@ -228,7 +229,8 @@ struct UtgArgs {
 };
 
 // one string per thread: fm6_retrieve + fm6_get_nei + check_left (unitig.cuh), results bump-allocated into the pools
-__global__ void __launch_bounds__(128) k_utg_nodes(const __grid_constant__ UtgArgs A)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_utg_nodes(const __grid_constant__ UtgArgs A)
 {
     const int lane = threadIdx.x & 31;
     u8 *mine = A.scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.stride;
@@ -418,7 +420,7 @@ static void correct_on_device(FmlEngine &E, ReadPool R, const b200_kmer_table *t
         A.maxlen = (int)std::min<i64>(maxlen, 512); A.heap_cap = bo.max_heap + 8; A.stack_cap = 1536;
         A.scratch_stride = (ec_scratch_bytes(A.maxlen, A.heap_cap, A.stack_cap) + 15) & ~(size_t)15;
         const int threads = 128;
-        int blocks = (int)std::min<i64>((n + threads - 1) / threads, (i64)E.sm_count * 8);
+        int blocks = (int)std::min<i64>((n + threads - 1) / threads, (i64)E.sm_count * 8);       // >= the resident blocks of either variant
         E.d_scratch.reserve((size_t)blocks * threads * A.scratch_stride);
         A.scratch = E.d_scratch.as<u8>();
         A.todo = nullptr; A.n_todo = 0; A.codes = E.d_codes.as<u8>(); A.work = ctr; A.lookups = ctr + 1;
@@ -431,7 +433,9 @@ static void correct_on_device(FmlEngine &E, ReadPool R, const b200_kmer_table *t
             cub::DeviceRadixSort::SortPairs(E.d_tmp.p, tb, E.d_cnt.as<u32>(), E.d_starts.as<u32>(), E.d_order[0].as<u32>(), E.d_order[1].as<u32>(), (int)n, 0, 32, st); ++nl;
             A.todo = E.d_order[1].as<u32>(); A.n_todo = n;
         }
-        k_ec<<<blocks, threads, 0, st>>>(A); ++nl;
+        static const int ec_minb = getenv("B200_EC_MINB") ? atoi(getenv("B200_EC_MINB")) : 5;
+        if (ec_minb >= 8) k_ec<8><<<blocks, threads, 0, st>>>(A); else k_ec<5><<<blocks, threads, 0, st>>>(A);
+        ++nl;
         std::vector<u8> codes((size_t)n);
         CU_CHECK(cudaMemcpyAsync(codes.data(), E.d_codes.p, (size_t)n, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaStreamSynchronize(st));
@@ -452,7 +456,7 @@ static void correct_on_device(FmlEngine &E, ReadPool R, const b200_kmer_table *t
             CU_CHECK(cudaMemcpyAsync(E.d_todo.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
             CU_CHECK(cudaMemsetAsync(ctr + 2, 0, 8, st));
             B.todo = E.d_todo.as<u32>(); B.n_todo = (i64)todo.size(); B.work = ctr + 2;
-            k_ec<<<sb, 32, 0, st>>>(B); ++nl;
+            k_ec<5><<<sb, 32, 0, st>>>(B); ++nl;
             CU_CHECK(cudaMemcpyAsync(codes.data(), E.d_codes.p, (size_t)n, cudaMemcpyDeviceToHost, st));
             CU_CHECK(cudaStreamSynchronize(st));
             CU_CHECK(cudaGetLastError());
@@ -524,7 +528,9 @@ static void utg_nodes_on_device(FmlEngine &E, const FmdDevice &F, int min_match,
         E.d_scratch.reserve((size_t)blocks * threads * A.stride);
         A.scratch = E.d_scratch.as<u8>();
         CU_CHECK(cudaMemsetAsync(ctr, 0, 64, st));
-        k_utg_nodes<<<blocks, threads, 0, st>>>(A); ++nl;
+        static const int utg_minb = getenv("B200_UTG_MINB") ? atoi(getenv("B200_UTG_MINB")) : 5;
+        if (utg_minb >= 8) k_utg_nodes<8><<<blocks, threads, 0, st>>>(A); else k_utg_nodes<5><<<blocks, threads, 0, st>>>(A);
+        ++nl;
         unsigned long long c[8];
         CU_CHECK(cudaMemcpyAsync(c, ctr, 64, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaMemcpyAsync(H.node.data(), d_node.p, n_str * sizeof(UtgNode), cudaMemcpyDeviceToHost, st));
@@ -545,7 +551,7 @@ static void utg_nodes_on_device(FmlEngine &E, const FmdDevice &F, int min_match,
             CU_CHECK(cudaMemcpyAsync(d_todo.p, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
             CU_CHECK(cudaMemsetAsync(ctr, 0, 8, st));
             B.todo = d_todo.as<u32>(); B.n_todo = todo.size();
-            k_utg_nodes<<<sb, 32, 0, st>>>(B); ++nl;
+            k_utg_nodes<5><<<sb, 32, 0, st>>>(B); ++nl;
             CU_CHECK(cudaMemcpyAsync(c, ctr, 64, cudaMemcpyDeviceToHost, st));
             CU_CHECK(cudaMemcpyAsync(H.node.data(), d_node.p, n_str * sizeof(UtgNode), cudaMemcpyDeviceToHost, st));
             CU_CHECK(cudaStreamSynchronize(st));
