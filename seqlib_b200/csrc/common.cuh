@@ -25,6 +25,7 @@ typedef int32_t i32;
 typedef uint8_t u8;
 typedef int8_t i8;
 typedef uint16_t u16;
+typedef int16_t i16;
 
 HD int popc64(u64 x)
 {

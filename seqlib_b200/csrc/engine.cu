@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
         if (w < A.n_work) {
             i64 rid = A.order ? A.order[w] : w;
             if (STAGE == 0) stage_seed_t<true>(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
-            else if (STAGE == 1) stage_chain(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
+            else if (STAGE == 1) stage_chain(A.ix, A.opt, A.caps, A.B, rid, scr, ctr, A.log_tab, A.n_log);
             else if (STAGE == 2) stage_extend(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
             else stage_finalize(A.ix, A.opt, A.caps, A.B, rid, scr, A.log_tab, A.n_log, ctr);
         }
@@ -448,6 +448,13 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
     if (A.B.dp_jobs) tc.z = 64;          // gapped hits go to k_finalize_dp, the thread-per-read stage needs no direction matrix
     size_t stride = max4(seed_scratch_bytes(tc), chain_scratch_bytes(tc), extend_scratch_bytes(tc), finalize_scratch_bytes(tc));
     stride = (stride + 63) & ~(size_t)63;
+    {   // long reads: the per-thread slot grows with the read length (hundreds of KB in the main pass, up to ~100 MB in the
+        // spill pass), so the number of resident threads is bounded by a scratch budget instead of by occupancy alone
+        static const double budget_gb = getenv("B200_SCRATCH_GB") ? atof(getenv("B200_SCRATCH_GB")) : 16.0;
+        i64 fit = (i64)(budget_gb * (double)(1ull << 30) / (double)(stride * 128));
+        if (fit < 1) fit = 1;
+        for (int i = 0; i < 4; ++i) if (g[i] > fit) g[i] = (int)fit;
+    }
     int gmax = std::max(std::max(g[0], g[1]), std::max(g[2], g[3]));
     DevBuf &S = spill ? E.spill_scratch : E.scratch;
     S.reserve(stride * (size_t)gmax * 128);
@@ -667,10 +674,8 @@ static int check_reads(const b200_mem_opt_t *opt, i64 n, const int64_t *off, int
         if (l < 0 || l > (1 << 20)) return fail(B200_ERR_ARG, "bad read length");
         if (l > maxlen) maxlen = (int)l;
     }
-    // mem_flt_chained_seeds (bwa/bwamem.c:624-628) starts to act once 5.5*ln(l) <= 0.05*l (l >~ 730 bp with min_chain_weight 0);
-    // that seed-SW filter is not part of this engine yet, so such reads are refused instead of silently diverging.
-    double lim = opt->min_chain_weight ? 1.1 * opt->min_chain_weight : 5.5 * log((double)maxlen);
-    if (!(lim > 0.05 * maxlen)) return fail(B200_ERR_LIMIT, "reads long enough to trigger mem_flt_chained_seeds (> ~730 bp) are not supported yet");
+    // reads long enough for mem_flt_chained_seeds (bwa/bwamem.c:624-641, > ~730 bp) are handled in stage_chain (seedsw.cuh)
+    (void)opt;
     *maxlen_out = maxlen;
     return B200_OK;
 }

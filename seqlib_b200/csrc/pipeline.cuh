@@ -14,11 +14,14 @@
 // pass with few threads and large slots; a full pool fails the chunk, which is
 // retried with larger pools.
 #pragma once
+#include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 #include "seed.cuh"
 #include "seed_fsm.cuh"
 #include "seed2.cuh"
 #include "chain.cuh"
+#include "seedsw.cuh"
 #include "extend.cuh"
 #include "finalize.cuh"
 #include "../../include/seqlib_b200.h"
@@ -141,7 +144,36 @@ HD size_t chain_scratch_bytes(const Caps &c)
     return sizeof(Chain) * c.wchains + sizeof(Seed) * c.wseeds + sizeof(BtNode) * chain_nodes(c) + sizeof(i32) * 2 * (size_t)c.wchains + 64;
 }
 
-HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
+// mem_flt_chained_seeds (bwa/bwamem.c:624-641) over the kept chains; a no-op unless 5.5 ln(len) <= 0.05 len
+HD void flt_chained_seeds(const DevIndex &ix, const Opt &opt, int len, const u8 *query, double log_len, ChainWork &w, const i32 *kept, int n)
+{
+    double min_l = opt.min_chain_weight ? (double)(1.1f * (float)opt.min_chain_weight) : (double)5.5f * log_len;
+    int min_HSP_score = (int)(opt.a * min_l + .499);
+    if (min_l > (double)(0.05f * (float)len)) return;
+#if !defined(__CUDA_ARCH__)
+    if (getenv("HOSTSIM_NO_SEEDSW")) return;        // test harness: lets the CPU suite prove the filter matters for its inputs
+#endif
+    for (int i = 0; i < n; ++i) {
+        Chain &c = w.chains[kept[i]];
+        int head = -1, tail = -1, k = 0;
+        for (int s = c.head; s >= 0;) {
+            Seed &sd = w.seeds[s];
+            int next = sd.next;
+            sd.score = seed_sw(ix, opt, len, query, sd.rbeg, sd.qbeg, sd.len);
+            if (sd.score < 0 || sd.score >= min_HSP_score) {
+                sd.score = sd.score < 0 ? sd.len * opt.a : sd.score;
+                sd.next = -1;
+                if (tail >= 0) w.seeds[tail].next = s; else head = s;
+                tail = s; ++k;
+            }
+            s = next;
+        }
+        c.head = head; c.tail = tail; c.n = k;
+    }
+}
+
+HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr,
+                    const double *log_tab = nullptr, int n_log = 0)
 {
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
     ReadRec &R = B.rec[rid];
@@ -159,7 +191,14 @@ HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const 
     int l_rep = build_chains(ix, opt, len, B.pool.intv + R.intv_off, R.n_intv, w, order, &n_order, ctr);
     if (w.ovf) { B.ovf[rid] |= w.ovf; return; }
     int n = filter_chains(opt, w, order, n_order, kept);
-    // mem_flt_chained_seeds (bwa/bwamem.c:624-641) only acts on reads longer than ~730 bp; the host driver rejects those
+    {
+#if defined(__CUDA_ARCH__)
+        double lg = log_tab[len < n_log ? len : n_log - 1];       // host libm values (hostutil.h)
+#else
+        double lg = log_tab && len < n_log ? log_tab[len] : std::log((double)len);
+#endif
+        flt_chained_seeds(ix, opt, len, B.seq + B.seq_off[rid], lg, w, order, n);
+    }
     int ns = 0;
     for (int i = 0; i < n; ++i) ns += w.chains[order[i]].n;
     if (ns > caps.seeds) { B.ovf[rid] |= OVF_SEED; return; }

@@ -168,3 +168,46 @@ def fml_reads(n, region=20000, read_len=150, err=0.01, seed=0x5EED0004, junk=0.0
     off = np.zeros(n + 1, dtype=np.int64)
     off[1:] = np.cumsum([len(s) for s in seqs])
     return np.concatenate(seqs), np.concatenate(quals), off
+
+
+def long_reads(pac, l_pac, n=40, seed=0x5EED0007, lo=800, hi=4000):
+    """Contig-like queries (longer than the ~730 bp where mem_flt_chained_seeds starts to act, bwa/bwamem.c:624-628):
+    segments of the reference with 1-3 % substitutions, a few indels, some chimeras of two segments, some reverse strand,
+    one stretch of unrelated sequence; returns list[str]."""
+    rng = np.random.default_rng(seed)
+    idx = np.arange(l_pac)
+    ref = (pac[idx >> 2] >> ((~idx & 3) << 1)) & 3
+    comp = np.array([3, 2, 1, 0], dtype=np.uint8)
+
+    def seg(ln):
+        p = int(rng.integers(0, l_pac - ln))
+        s = ref[p:p + ln].astype(np.uint8).copy()
+        e = rng.random(ln) < rng.choice([0.01, 0.03])
+        s[e] = (s[e] + rng.integers(1, 4, int(e.sum()), dtype=np.uint8)) & 3
+        out = []
+        i = 0
+        while i < ln:
+            u = rng.random()
+            if u < 0.002:
+                i += int(rng.integers(1, 12))          # deletion
+                continue
+            if u < 0.004:
+                out.extend(rng.integers(0, 4, int(rng.integers(1, 12))).tolist())   # insertion
+            out.append(int(s[i]))
+            i += 1
+        s = np.array(out, dtype=np.uint8)
+        if rng.random() < 0.5:
+            s = comp[s[::-1]]
+        return s
+
+    reads = []
+    for i in range(n):
+        ln = int(rng.integers(lo, hi))
+        if i % 5 == 4:
+            s = np.concatenate([seg(ln // 2), seg(ln - ln // 2)])
+        elif i % 11 == 10:
+            s = np.concatenate([seg(ln // 2), rng.integers(0, 4, 300, dtype=np.uint8), seg(ln // 3)])
+        else:
+            s = seg(ln)
+        reads.append("".join("ACGT"[b] for b in s))
+    return reads

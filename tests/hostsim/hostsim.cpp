@@ -82,7 +82,7 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
             if (dbg) fprintf(stderr, "read %ld pass %d\n", (long)r, pass);
             if (seed_v2) stage_seed_v2(ix, opt, c, B, r, s1.data(), ctr, seed_v2);
             else stage_seed(ix, opt, c, B, r, s1.data(), ctr);
-            stage_chain(ix, opt, c, B, r, s2.data(), ctr);
+            stage_chain(ix, opt, c, B, r, s2.data(), ctr, logtab.data(), (int)logtab.size());
             stage_extend(ix, opt, c, B, r, s3.data(), ctr);
             raws[r].assign(B.pool.regs + rec[r].reg_off, B.pool.regs + rec[r].reg_off + rec[r].n_regs);
             stage_finalize(ix, opt, c, B, r, s4.data(), logtab.data(), (int)logtab.size(), ctr);

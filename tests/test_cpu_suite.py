@@ -79,6 +79,28 @@ def test_stage_functions_on_cpu_vs_golden(name, small, seed_v2, monkeypatch):
         assert np.array_equal(got.intv_off, z["intv_off"]) and np.array_equal(got.intv, z["intv"])
 
 
+def test_long_reads_seed_sw_filter_on_cpu_vs_reference(monkeypatch):
+    """Contig-like queries (0.8-4 kb) activate mem_flt_chained_seeds / mem_seed_sw -> ksw_i16 (bwa/bwamem.c:597-641): the host
+    build of the stage functions (seedsw.cuh replays the striped kernel) gives the reference's hits, CIGARs and MAPQs; with
+    the filter switched off the same inputs differ, so the inputs do exercise it."""
+    from oracle import pyref
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import simlib
+    sidx, tidx = _sim_index_for_tiny()
+    a = tidx.arrays()
+    reads = cases.long_reads(a["pac"], int(a["l_pac"]), n=24)
+    opt = pyref.default_opt()
+    ids = cases.ids_for(len(reads))
+    exp, _ = pyref.align(tidx, reads, opt, ids)
+    monkeypatch.delenv("HOSTSIM_SEED_V2", raising=False)
+    got = simlib.align(sidx, reads, opt, ids, False)
+    assert parity.compare_results(got, exp) == []
+    monkeypatch.setenv("HOSTSIM_NO_SEEDSW", "1")
+    off = simlib.align(sidx, reads, opt, ids, False)
+    assert parity.compare_results(off, exp) != []
+
+
 def test_reference_library_reproduces_golden():
     """oracle/_ref (when present) still produces the committed vectors: guards the fixtures themselves."""
     from oracle import pyref

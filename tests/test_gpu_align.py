@@ -190,6 +190,22 @@ def test_scale_properties(capi):
     assert np.all(per_hit == 150)
 
 
+def test_long_reads_vs_live_reference(capi):
+    """Contig-like queries (0.8-4 kb, chimeras, indels): mem_flt_chained_seeds / mem_seed_sw (bwa/bwamem.c:597-641) is active,
+    every read goes through the large-slot spill pass; hits, CIGARs, MD and MAPQ equal the reference library's."""
+    from oracle import pyref
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    tidx = pyref.RefIndex.load(goldenlib.path("tiny", "tiny.fa"))
+    a = tidx.arrays()
+    reads = cases.long_reads(a["pac"], int(a["l_pac"]), n=60) + cases.read_lines(goldenlib.path("bcr_2k.txt"))[:200]
+    ids = cases.ids_for(len(reads))
+    exp, _ = pyref.align(tidx, reads, pyref.default_opt(), ids)
+    idx = capi.Index.load(goldenlib.path("tiny", "tiny.fa"))
+    got = capi.align(idx, reads, capi.default_opt(), ids)
+    assert parity.compare_results(got, exp) == []
+
+
 def test_cxx_dropin_kat(capi, tmp_path):
     """The reference's bwa_wrapper Boost test (seq_test/seq_test.cpp:793-915) against the C++ drop-in classes."""
     import subprocess
