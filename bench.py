@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (config 4: FermiAssembler::PerformAssembly)")
     return ap.parse_args()
 
 
@@ -100,6 +101,41 @@ def seed_traffic_per_read():
         return (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["reads_in_launch"], d["source"]
     except Exception:
         return None, None
+
+
+def fermi_extra(args, with_cpu):
+    """Config 4 (FermiAssembler::PerformAssembly, 1M x 150bp at 150x): secondary numbers carried in the same JSON line."""
+    from seqlib_b200 import capi, synth
+    n = int(os.environ.get("B200_BENCH_ASM_READS", 1_000_000))
+    pac = synth.reference(n, seed=0x5EED0005)
+    ctg = synth.contigs_for(n, 1, "asm")
+    seqs, off, _, _ = synth.reads(pac, n, ctg, n, 150, 0.01, 0.0, seed=0x5EED0006)
+    quals = np.full(len(seqs), ord("I"), dtype=np.uint8)
+    opt = capi.fml_default_opt()
+    capi.fml_assemble_flat(opt, seqs, quals, off)          # warm-up (allocations, first launches)
+    ts, st = [], None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        utgs = capi.fml_assemble_flat(opt, seqs, quals, off)
+        ts.append(time.perf_counter() - t0)
+        st = capi.fml_last_stats()
+    out = {"workload": "fml_assemble: %d x 150bp reads from a %d bp random region (150x), 1%% substitutions" % (n, n),
+           "e2e_reads_per_s": n / float(np.mean(ts)), "e2e_seconds": float(np.mean(ts)),
+           "stage_ms": {k: st[k] for k in ("ms_count", "ms_ec", "ms_flt", "ms_fmd", "ms_nodes", "ms_walk_host", "ms_clean_host")},
+           "n_utg": len(utgs), "longest_utg": max([len(u["seq"]) for u in utgs] + [0]), "gpu_launches": st["n_launches"],
+           "ec_table_probes": st["n_lookups"], "fmd_symbols": st["fmd_symbols"]}
+    if with_cpu:
+        try:
+            from oracle import pyref_fml
+            m = 50_000
+            pac2 = synth.reference(m, seed=0x5EED0005)
+            s2, o2, _, _ = synth.reads(pac2, m, synth.contigs_for(m, 1, "asm"), m, 150, 0.01, 0.0, seed=0x5EED0006)
+            exp, sec = pyref_fml.assemble(pyref_fml.default_opt(), s2, np.full(len(s2), ord("I"), dtype=np.uint8), o2)
+            out["cpu_baseline"] = {"value": m / sec, "unit": "reads/s", "cores": 1, "kind": "reference",
+                                   "sample": "fml_assemble (fermi-lite/misc.c:280-302), n_threads=1, %d reads at the same coverage, %.1f s" % (m, sec)}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "sample": "unavailable: %s" % e}
+    return out
 
 
 def make_workload(args, n_total_reads):
@@ -374,6 +410,12 @@ def main():
         }
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
+        if world == 1 and not args.no_extra:
+            try:
+                idx.close()
+                line["extra"] = {"config4_fermi_assemble": fermi_extra(args, not args.no_cpu_baseline)}
+            except Exception as e:   # secondary numbers never fail the headline line
+                line["extra"] = {"config4_fermi_assemble": {"error": str(e)}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
