@@ -346,13 +346,23 @@ struct HostResults {
         b_off = pin_pool().get((size_t)(nr + 1) * 8); b_hits = pin_pool().get((size_t)nh * sizeof(b200_hit_t));
         b_cigar = pin_pool().get((size_t)nc * 4); b_md = pin_pool().get((size_t)nm);
     }
+    // streaming fill (b200_mem_align_batch): capacities are estimates, grown when a chunk does not fit
+    static void grow(PinBuf &b, size_t used, size_t need, cudaStream_t copy_stream)
+    {
+        if (need <= b.cap) return;
+        CU_CHECK(cudaStreamSynchronize(copy_stream));          // copies into the old buffer must have landed
+        PinBuf nb = pin_pool().get(need + need / 2);
+        if (used) memcpy(nb.p, b.p, used);
+        pin_pool().put(b);
+        b = nb;
+    }
     ~HostResults() { pin_pool().put(b_off); pin_pool().put(b_hits); pin_pool().put(b_cigar); pin_pool().put(b_md); }
 };
 
 struct Engine {
     int device = -1, sms = 148;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev[8];
+    cudaStream_t st = nullptr, st_copy = nullptr;      // kernels / result copies that overlap the next chunk's kernels
+    cudaEvent_t ev[8], ev_copy, ev_up;
     // chunk buffers
     DevBuf packed, seedflag, seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
     DevBuf p_intv, p_chain, p_seed, p_reg, p_hit, p_cigar, p_md;
@@ -368,6 +378,9 @@ struct Engine {
         device = d;
         CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
         CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CU_CHECK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+        CU_CHECK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
+        CU_CHECK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
         if (const char *g = getenv("B200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
         for (int i = 0; i < 8; ++i) CU_CHECK(cudaEventCreate(&ev[i]));
         memset(&stats, 0, sizeof(stats));
@@ -655,14 +668,20 @@ static i64 chunk_reads()
 struct b200_results { HostResults r; };
 
 struct b200_batch {
+    HostResults *sink = nullptr;      // when set, b200_batch_run copies every chunk's result to the host while the next chunk runs
     const b200_index *idx; Opt opt; i64 n; int maxlen;
-    std::vector<i64> h_off;
+    const i64 *h_off = nullptr;       // the caller's offsets; only dereferenced inside b200_mem_align_batch (lazy upload)
     DevBuf d_seq, d_off, d_ids, d_log; int n_log;
+    // lazy upload (b200_mem_align_batch): the bases of chunk i are copied on the copy stream and encoded right before chunk i
+    // runs, so chunk 0 starts after its own 1/k of the transfer; `uploaded` = bytes already issued
+    const char *lazy_src = nullptr; DevBuf lazy_ascii; i64 uploaded = 0, total_bytes = 0; bool lazy = false;
     // device-resident compact results of the last run, per chunk
     struct Chunk { i64 r0, n; ChunkOut out; DevBuf hit_off, hits, cigar, md; };
     std::vector<Chunk *> chunks;
     ~b200_batch() { for (auto c : chunks) delete c; }
 };
+
+static thread_local bool g_lazy_upload = false;
 
 extern "C" {
 
@@ -691,18 +710,23 @@ int b200_batch_create(const b200_index_t *idx, const b200_mem_opt_t *opt, int64_
     try {
         Engine &E = engine();
         b->idx = idx; b->opt = opt_from_abi(*opt); b->n = n; b->maxlen = maxlen;
-        b->h_off.assign(off, off + n + 1);
+        b->h_off = off;
         i64 base = off[0], total = off[n] - base;
-        std::vector<i64> rel(n + 1);
-        for (i64 i = 0; i <= n; ++i) rel[i] = off[i] - base;
+        std::vector<i64> rel;
+        const i64 *rel_src = off;                 // offsets relative to the first base: the caller's array when it starts at 0
+        if (base != 0) { rel.resize(n + 1); for (i64 i = 0; i <= n; ++i) rel[i] = off[i] - base; rel_src = rel.data(); }
         std::vector<i64> myids;
         if (!ids) { myids.resize(n); for (i64 i = 0; i < n; ++i) myids[i] = lrand48(); ids = myids.data(); }
         b->d_seq.reserve(total + 64); b->d_off.reserve((n + 1) * 8); b->d_ids.reserve(n * 8 + 8);
-        E.seq_ascii.reserve(total + 64);
-        CU_CHECK(cudaMemcpyAsync(E.seq_ascii.p, seqs + base, total, cudaMemcpyHostToDevice, E.st));
-        CU_CHECK(cudaMemcpyAsync(b->d_off.p, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, E.st));
+        b->total_bytes = total;
+        if (g_lazy_upload) { b->lazy = true; b->lazy_src = seqs + base; b->lazy_ascii.reserve(total + 64); }
+        else {
+            E.seq_ascii.reserve(total + 64);
+            CU_CHECK(cudaMemcpyAsync(E.seq_ascii.p, seqs + base, total, cudaMemcpyHostToDevice, E.st));
+        }
+        CU_CHECK(cudaMemcpyAsync(b->d_off.p, rel_src, (n + 1) * 8, cudaMemcpyHostToDevice, E.st));
         CU_CHECK(cudaMemcpyAsync(b->d_ids.p, ids, n * 8, cudaMemcpyHostToDevice, E.st));
-        if (total) k_encode<<<E.sms * 8, 256, 0, E.st>>>(E.seq_ascii.as<u8>(), b->d_seq.as<u8>(), total);
+        if (total && !b->lazy) k_encode<<<E.sms * 8, 256, 0, E.st>>>(E.seq_ascii.as<u8>(), b->d_seq.as<u8>(), total);
         std::vector<double> lt = make_log_table(maxlen, b->opt);
         b->n_log = (int)lt.size();
         b->d_log.reserve(lt.size() * 8);
@@ -724,6 +748,19 @@ int b200_batch_run(b200_batch_t *b, int *n_launches)
         size_t ci = 0;
         for (i64 r0 = 0; r0 < b->n; r0 += CH, ++ci) {
             i64 n = std::min(CH, b->n - r0);
+            if (b->lazy) {
+                // issue the transfer of this chunk AND the next one (so the next one overlaps this chunk's kernels), encode this one
+                i64 upto = b->h_off[std::min(b->n, r0 + 2 * CH)] - b->h_off[0];
+                if (upto > b->uploaded) {
+                    CU_CHECK(cudaMemcpyAsync(b->lazy_ascii.as<u8>() + b->uploaded, b->lazy_src + b->uploaded, upto - b->uploaded, cudaMemcpyHostToDevice, E.st_copy));
+                    b->uploaded = upto;
+                }
+                i64 lo = b->h_off[r0] - b->h_off[0], hi = b->h_off[r0 + n] - b->h_off[0];
+                // the copy stream is in order: an event recorded now covers every piece issued so far
+                CU_CHECK(cudaEventRecord(E.ev_up, E.st_copy));
+                CU_CHECK(cudaStreamWaitEvent(E.st, E.ev_up, 0));
+                if (hi > lo) k_encode<<<E.sms * 4, 256, 0, E.st>>>(b->lazy_ascii.as<u8>() + lo, b->d_seq.as<u8>() + lo, hi - lo);
+            }
             b200_batch::Chunk *c = ci < b->chunks.size() ? b->chunks[ci] : nullptr;
             if (c) {    // hand the previous run's result buffers back to the engine so they are reused, not re-allocated
                 std::swap(c->hit_off.p, E.o_hit_off.p); std::swap(c->hit_off.cap, E.o_hit_off.cap);
@@ -739,7 +776,25 @@ int b200_batch_run(b200_batch_t *b, int *n_launches)
             std::swap(c->hits.p, E.o_hits.p); std::swap(c->hits.cap, E.o_hits.cap);
             std::swap(c->cigar.p, E.o_cigar.p); std::swap(c->cigar.cap, E.o_cigar.cap);
             std::swap(c->md.p, E.o_md.p); std::swap(c->md.cap, E.o_md.cap);
+            if (b->sink) {
+                HostResults &H = *b->sink;
+                HostResults::grow(H.b_hits, (size_t)bh * sizeof(b200_hit_t), (size_t)(bh + o.n_hits) * sizeof(b200_hit_t), E.st_copy);
+                HostResults::grow(H.b_cigar, (size_t)bc * 4, (size_t)(bc + o.n_cigar) * 4, E.st_copy);
+                HostResults::grow(H.b_md, (size_t)bm, (size_t)(bm + o.n_md), E.st_copy);
+                CU_CHECK(cudaEventRecord(E.ev_copy, E.st));
+                CU_CHECK(cudaStreamWaitEvent(E.st_copy, E.ev_copy, 0));
+                CU_CHECK(cudaMemcpyAsync(H.hit_off() + r0, c->hit_off.p, n * 8, cudaMemcpyDeviceToHost, E.st_copy));
+                if (o.n_hits) CU_CHECK(cudaMemcpyAsync(H.hits() + bh, c->hits.p, o.n_hits * sizeof(b200_hit_t), cudaMemcpyDeviceToHost, E.st_copy));
+                if (o.n_cigar) CU_CHECK(cudaMemcpyAsync(H.cigar() + bc, c->cigar.p, o.n_cigar * 4, cudaMemcpyDeviceToHost, E.st_copy));
+                if (o.n_md) CU_CHECK(cudaMemcpyAsync(H.md() + bm, c->md.p, o.n_md, cudaMemcpyDeviceToHost, E.st_copy));
+            }
             bh += o.n_hits; bc += o.n_cigar; bm += o.n_md;
+        }
+        if (b->sink) {
+            CU_CHECK(cudaStreamSynchronize(E.st_copy));
+            HostResults &H = *b->sink;
+            H.n_reads = b->n; H.n_hits = bh; H.n_cigar = bc; H.n_md = bm;
+            H.hit_off()[b->n] = bh;
         }
         CU_CHECK(cudaEventRecord(E.ev[7], E.st));
         CU_CHECK(cudaEventSynchronize(E.ev[7]));
@@ -785,16 +840,29 @@ int b200_mem_align_batch(const b200_index_t *idx, const b200_mem_opt_t *opt, int
     b200_batch_t *b = nullptr;
     static int trace = getenv("B200_TRACE") ? 1 : 0;
     double t0 = wall_now();
+    g_lazy_upload = getenv("B200_EAGER_UPLOAD") ? false : true;
     int rc = b200_batch_create(idx, opt, n, seqs, off, ids, &b);
+    g_lazy_upload = false;
     if (rc != B200_OK) return rc;
     double t1 = wall_now();
+    b200_results *R = new b200_results;
+    try {
+        // results stream to the host chunk by chunk (copy stream) while the next chunk's kernels run
+        HostResults &H = R->r;
+        H.b_off = pin_pool().get((size_t)(n + 1) * 8);
+        H.b_hits = pin_pool().get((size_t)(2 * n + 1024) * sizeof(b200_hit_t));
+        H.b_cigar = pin_pool().get((size_t)(4 * n + 1024) * 4);
+        H.b_md = pin_pool().get((size_t)(16 * n + 1024));
+        H.hit_off()[0] = 0;
+        b->sink = &H;
+    } catch (const std::exception &e) { delete R; b200_batch_destroy(b); return fail(B200_ERR_NOMEM, e.what()); }
     rc = b200_batch_run(b, nullptr);
     double t2 = wall_now();
-    if (rc == B200_OK) rc = b200_batch_fetch(b, out);
-    double t3 = wall_now();
+    b->sink = nullptr;
     b200_batch_destroy(b);
-    if (trace) fprintf(stderr, "[b200 trace] align_batch n=%lld: create %.1f ms, run %.1f ms, fetch %.1f ms, destroy %.1f ms\n", (long long)n,
-                       1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (wall_now() - t3));
+    if (rc == B200_OK) *out = R; else delete R;
+    if (trace) fprintf(stderr, "[b200 trace] align_batch n=%lld: create %.1f ms, run+copy %.1f ms, destroy %.1f ms\n", (long long)n,
+                       1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (wall_now() - t2));
     return rc;
 }
 

@@ -75,6 +75,7 @@ char *fmd_emul_mag_text(const uint8_t *bwt, uint64_t n, const b200_fml_opt_t *op
         for (int i = 0; i < N.n_nei; ++i) nei.push_back(UtgNei{S.nei[i].x[0], S.nei[i].x[1], S.nei[i].x[2], (i64)S.nei[i].info});
         for (int i = 0; i < N.n_mark_r + N.n_mark_c; ++i) mark.push_back(S.mark[i]);
         if (!(N.flags & (UTG_CONTAINED | UTG_SHORT))) ++st[0];
+        if (getenv("FMD_EMUL_CHECK_K") && N.len > 0 && N.ret_k != N.x0 + (x - N.x1)) ++st[3];
         if (N.n_nei > st[1]) st[1] = N.n_nei;
         if (N.n_mark_r + N.n_mark_c > st[2]) st[2] = N.n_mark_r + N.n_mark_c;
     }
