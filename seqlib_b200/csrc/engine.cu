@@ -704,6 +704,8 @@ int b200_batch_create(const b200_index_t *idx, const b200_mem_opt_t *opt, int64_
 {
     if (!idx || !opt || !out || n < 0 || (n && (!seqs || !off))) return fail(B200_ERR_ARG, "bad argument");
     *out = nullptr;
+    static const int64_t zero_off[1] = {0};
+    if (n == 0 && !off) off = zero_off;
     int maxlen = 1, rc;
     if ((rc = check_reads(opt, n, off, &maxlen)) != B200_OK) return rc;
     b200_batch *b = new b200_batch;

@@ -56,12 +56,13 @@ __global__ void __launch_bounds__(256) k_fmd_text(const char *seq, const i64 *of
     text[a + l] = 0; text[b + l] = 0;
 }
 
-struct RotKey {              // chunk `depth` of the key of row id = string << 24 | offset
-    const u8 *text; const u64 *start;
-    __device__ __forceinline__ u64 operator()(u64 id, int depth) const
+struct RotKey {              // chunk `depth` of the key of row p (its string comes from row_str)
+    const u8 *text; const u64 *start; const u32 *row_str;
+    __device__ __forceinline__ u64 operator()(u64 p, int depth) const
     {
-        u64 j = id >> 24; int i = (int)(id & 0xffffff);
+        u64 j = row_str[p];
         u64 sj = start[j], sp = start[j ^ 1];
+        int i = (int)(p - sj);
         int L = (int)(start[j + 1] - sj) - 1;
         const u8 *a = text + sj + i;             // chars d = 0 .. L - i   (suffix + its sentinel)
         const u8 *b = text + sp - 1;             // chars d = L - i + 1 .. L + 1  -> partner[d - 1]
@@ -77,25 +78,28 @@ struct RotKey {              // chunk `depth` of the key of row id = string << 2
     }
 };
 
-__global__ void __launch_bounds__(256) k_fmd_rows(const u64 *start, u64 n_str, RotKey kf, u64 *keys, u64 *ids)
+__global__ void __launch_bounds__(256) k_fmd_row_str(const u64 *start, u64 n_str, u32 *row_str)
 {
     u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_str) return;
-    u64 a = start[j], b = start[j + 1];
-    for (u64 p = a; p < b; ++p) {
-        u64 id = j << 24 | (p - a);
-        ids[p] = id;
-        keys[p] = kf(id, 0);
-    }
+    for (u64 p = start[j], b = start[j + 1]; p < b; ++p) row_str[p] = (u32)j;
+}
+
+__global__ void __launch_bounds__(256) k_fmd_rows(u64 n, RotKey kf, u64 *keys, u32 *ids)
+{
+    u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    ids[p] = (u32)p;
+    keys[p] = kf(p, 0);
 }
 
 // BWT symbol of every sorted row
-__global__ void __launch_bounds__(256) k_fmd_emit(const u8 *text, const u64 *start, const u64 *ids, u64 n, u8 *bwt8)
+__global__ void __launch_bounds__(256) k_fmd_emit(const u8 *text, const u64 *start, const u32 *row_str, const u32 *ids, u64 n, u8 *bwt8)
 {
     u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
-    u64 id = ids[x], j = id >> 24; u32 i = (u32)(id & 0xffffff);
-    bwt8[x] = i ? text[start[j] + i - 1] : (u8)0;
+    u64 p = ids[x];
+    bwt8[x] = p != start[row_str[p]] ? text[p - 1] : (u8)0;      // the symbol before the row's suffix; rows at offset 0 carry $
 }
 
 struct Cnt4 { u32 c[4]; };
@@ -148,12 +152,13 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
     F.text.reserve(n + 16);
     k_fmd_text<<<nblk(n_reads, 256), 256>>>(d_seq, d_off, n_reads, F.start.as<u64>(), F.text.as<u8>());
     // sort all rows
-    DevBuf keys, ids;
-    keys.reserve(n * 8); ids.reserve(n * 8);
-    Sorter<RotKey> S;
-    S.kf.text = F.text.as<u8>(); S.kf.start = F.start.as<u64>();
+    DevBuf keys, ids, row_str;
+    keys.reserve(n * 8); ids.reserve(n * 4); row_str.reserve(n * 4);
+    k_fmd_row_str<<<nblk(n_str, 256), 256>>>(F.start.as<u64>(), n_str, row_str.as<u32>());
+    Sorter<RotKey, u32> S;
+    S.kf.text = F.text.as<u8>(); S.kf.start = F.start.as<u64>(); S.kf.row_str = row_str.as<u32>();
     // longest key = (longest read + 2) symbols
-    k_fmd_rows<<<nblk(n_str, 256), 256>>>(F.start.as<u64>(), n_str, S.kf, keys.as<u64>(), ids.as<u64>());
+    k_fmd_rows<<<nblk(n, 256), 256>>>(n, S.kf, keys.as<u64>(), ids.as<u32>());
     u32 max_rows = 0;
     {
         DevBuf mx; mx.reserve(16);
@@ -163,13 +168,12 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
         CU_CHECK(cub::DeviceReduce::Max(tmp.p, tb, rows.as<u32>(), mx.as<u32>(), (int)n_str));
         CU_CHECK(cudaMemcpy(&max_rows, mx.p, 4, cudaMemcpyDeviceToHost));
     }
-    if (max_rows >= (1u << 24)) throw std::length_error("read longer than 2^24 bases");
     S.max_depth = (int)((max_rows + 1 + FMD_KEY_SYMS - 1) / FMD_KEY_SYMS);
-    u64 *kp = keys.as<u64>(), *ip = ids.as<u64>();
+    u64 *kp = keys.as<u64>(); u32 *ip = ids.as<u32>();
     S.sort_bucket(kp, ip, n);
     // BWT symbols, rank blocks
     DevBuf bwt8; bwt8.reserve(n + 16);
-    k_fmd_emit<<<nblk(n, 256), 256>>>(F.text.as<u8>(), F.start.as<u64>(), ip, n, bwt8.as<u8>());
+    k_fmd_emit<<<nblk(n, 256), 256>>>(F.text.as<u8>(), F.start.as<u64>(), row_str.as<u32>(), ip, n, bwt8.as<u8>());
     const u64 n_blk = (n + 127) / 128 + 1;          // one spare block: rank(n) with n % 128 == 0 stays in range
     F.blocks.reserve(n_blk * sizeof(FmdBlock));
     DevBuf cnt; cnt.reserve(n_blk * sizeof(Cnt4));

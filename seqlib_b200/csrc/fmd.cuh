@@ -123,14 +123,33 @@ HD void fmd_extend(const FmdIndex &e, const FmdIntv &ik, FmdIntv ok[6], int is_b
     ok[5].x[is_back] = ok[1].x[is_back] + tl[1];
 }
 
+// number of sentinels in bwt[0, k): the only count rld_extend0 consumes (one block load, two popcounts)
+HD u64 fmd_rank_sentinel(const FmdIndex &e, u64 k)
+{
+    if (k == 0) return 0;
+    u64 b = (k - 1) >> 7; int o = (int)((k - 1) & 127) + 1;
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(e.blk + b);
+    ulonglong2 v0 = __ldg(p), v3 = __ldg(p + 3);
+    u64 before = (u64)(u32)v0.x + (u32)(v0.x >> 32) + (u32)v0.y + (u32)(v0.y >> 32);
+    u64 q0 = v3.x, q1 = v3.y;
+#else
+    const FmdBlock &B = e.blk[b];
+    u64 before = (u64)B.cnt[0] + B.cnt[1] + B.cnt[2] + B.cnt[3];
+    u64 q0 = B.p2[0], q1 = B.p2[1];
+#endif
+    u64 m0 = o >= 64 ? ~0ull : (1ull << o) - 1;
+    u64 m1 = o <= 64 ? 0ull : (o >= 128 ? ~0ull : (1ull << (o - 64)) - 1);
+    return (b << 7) - before + (u64)(popc64(q0 & m0) + popc64(q1 & m1));
+}
+
 // rld_extend0 (fermi-lite/unitig.c:21-30): only the sentinel branch of an extension
 HD void fmd_extend0(const FmdIndex &e, const FmdIntv &ik, FmdIntv &ok0, int is_back)
 {
-    u64 tk[6], tl[6];
-    fmd_rank2a(e, ik.x[!is_back], ik.x[!is_back] + ik.x[2], tk, tl);
-    ok0.x[!is_back] = tk[0];
+    u64 tk = fmd_rank_sentinel(e, ik.x[!is_back]), tl = fmd_rank_sentinel(e, ik.x[!is_back] + ik.x[2]);
+    ok0.x[!is_back] = tk;
     ok0.x[is_back] = ik.x[is_back];
-    ok0.x[2] = tl[0] - tk[0];
+    ok0.x[2] = tl - tk;
 }
 
 } // namespace b200

@@ -21,7 +21,9 @@ namespace b200 {
 
 struct UtgMark { u64 x0, x1, x2; };          // one set_bits(used, intv) call
 
-struct UtgNode {
+struct UtgNei { u64 x0, x1, x2; i64 ovlp; };
+
+struct UtgNode {             // 128 bytes = two cache lines: the host walk touches one record per absorbed read
     u64 x0, x1, x2;          // interval of $s$: x0 = first rank among the copies of s, x1 = same for revcomp(s), x2 = copies
     u64 ret_k;               // fm6_retrieve's return value
     i32 len;                 // length of s
@@ -34,11 +36,11 @@ struct UtgNode {
     u64 seq_off;             // pools (UtgPools): s at seq[seq_off, +len), appended bases follow at seq[seq_off + len, +ext_len)
     u64 nei_off;             // nei[nei_off, +n_nei)  (x[0], x[1], overlap length)
     u64 mark_off;            // mark[mark_off, +n_mark_r) then +n_mark_c
+    UtgNei nei0;             // copy of nei[nei_off] (valid when n_nei >= 1) and of the first appended bases, so that the common
+    u8 ext8[8];              // step of a walk (one neighbour, a few new bases, no marks) needs no second random access
 };
 
 enum { UTG_DUP = 1, UTG_CONTAINED = 2, UTG_SHORT = 4, UTG_NO_OVLP = 8, UTG_OVERFLOW = 16 };
-
-struct UtgNei { u64 x0, x1, x2; i64 ovlp; };
 
 struct UtgScratch {
     FmdIntv *a[2], *nei; i32 *cat; int cap;      // interval vectors (prev / curr / neighbours) and the category array
@@ -72,13 +74,19 @@ HD void utg_mark(UtgScratch &S, const FmdIntv &p)
     S.mark[S.n_mark++] = m;
 }
 
-// fm6_retrieve: the string whose sentinel row is x (symbols 1..4, REVERSED as the reference leaves it before seq_reverse)
-HD u64 utg_retrieve(const FmdIndex &e, u64 x, u8 *s, int s_cap, int &l_out, FmdIntv &k2, int &contained, bool &overflow)
+// fm6_retrieve: the string whose sentinel row is x (symbols 1..4, REVERSED as the reference leaves it before seq_reverse).
+// The backward extensions it performs are exactly those of overlap_intv(s, at5 = 0) that fm6_is_contained / fm6_get_nei run
+// next on the same string, so the overlap candidates (suffix intervals preceded by a sentinel, depth >= min) are collected
+// here: p[0..pn) in discovery order (shortest suffix first) with info = number of bases of the suffix; the caller turns that
+// into positions and reverses the list.  Intervals of size 1 take the reference's shortcut (no extension): a size-1 interval
+// whose row is preceded by a base has no sentinel extension, so nothing is missed.
+HD u64 utg_retrieve(const FmdIndex &e, u64 x, u8 *s, int s_cap, int &l_out, FmdIntv &k2, int &contained, bool &overflow,
+                    int min, FmdIntv *p, int &pn, int cap)
 {
     u64 k = x, ok[6];
     FmdIntv ok2[6];
     int l = 0;
-    contained = 0;
+    contained = 0; pn = 0;
     k2.x[0] = k2.x[1] = k2.x[2] = 0; k2.info = 0;
     for (;;) {
         int c = fmd_rank1a(e, k + 1, ok);
@@ -86,7 +94,15 @@ HD u64 utg_retrieve(const FmdIndex &e, u64 x, u8 *s, int s_cap, int &l_out, FmdI
         if (c == 0) break;
         if (l > 0) {
             if (k2.x[2] == 1) k2.x[0] = k;
-            else { fmd_extend(e, k2, ok2, 1); k2 = ok2[c]; }
+            else {
+                fmd_extend(e, k2, ok2, 1);
+                if (l >= min && ok2[0].x[2]) {            // overlap_intv: depth = l, the suffix of l bases ends a read on its left
+                    if (pn >= cap) { overflow = true; break; }
+                    FmdIntv t = k2; t.info = (u64)l;
+                    p[pn++] = t;
+                }
+                k2 = ok2[c];
+            }
         } else fmd_set_intv(e, c, k2);
         if (l >= s_cap) { overflow = true; break; }
         s[l++] = (u8)c;
@@ -273,10 +289,15 @@ HD void utg_node(const FmdIndex &e, int min_match, u64 x, UtgScratch &S, UtgNode
     FmdIntv intv0;
     int contained = 0, l = 0;
     N.flags = 0; N.n_nei = 0; N.rbeg = -1; N.ext_len = 0; N.cl = 0; N.n_mark_r = N.n_mark_c = 0;
+    N.nei0.x0 = N.nei0.x1 = N.nei0.x2 = 0; N.nei0.ovlp = 0;
+    for (int a = 0; a < 8; ++a) N.ext8[a] = 0;
     S.n[0] = S.n[1] = S.n_nei = S.n_mark = 0; S.overflow = false;
-    N.ret_k = utg_retrieve(e, x, S.s, S.s_cap / 2, l, intv0, contained, S.overflow);
+    N.ret_k = utg_retrieve(e, x, S.s, S.s_cap / 2, l, intv0, contained, S.overflow, min_match, S.a[0], S.n[0], S.cap);
     // seq_reverse
     for (int a = 0, b = l - 1; a < b; ++a, --b) { u8 t = S.s[a]; S.s[a] = S.s[b]; S.s[b] = t; }
+    // overlap candidates: suffix of d bases starts at l - d; longest suffix (smallest interval) first, as kv_reverse leaves them
+    for (int a = 0; a < S.n[0]; ++a) S.a[0][a].info = (u64)(l - (int)S.a[0][a].info);
+    for (int a = 0, b = S.n[0] - 1; a < b; ++a, --b) { FmdIntv t = S.a[0][a]; S.a[0][a] = S.a[0][b]; S.a[0][b] = t; }
     N.len = l;
     N.x0 = intv0.x[0]; N.x1 = intv0.x[1]; N.x2 = intv0.x[2];
     if (S.overflow) { N.flags |= UTG_OVERFLOW; return; }
@@ -285,14 +306,16 @@ HD void utg_node(const FmdIndex &e, int min_match, u64 x, UtgScratch &S, UtgNode
     if (intv0.x[2] > 1 && N.ret_k != intv0.x[0]) N.flags |= UTG_DUP;
     if (contained) { N.flags |= UTG_CONTAINED; return; }
     if (l <= min_match) { N.flags |= UTG_SHORT; return; }
-    // fm6_is_contained only pre-computes the overlap list here (its verdict is not used by unitig1); fm6_get_nei builds
-    // the identical list itself when handed an empty one.
-    int rbeg = utg_get_nei(e, min_match, 0, S.s, l, S);
+    // fm6_is_contained only pre-computes the overlap list (its verdict is not used by unitig1): utg_retrieve has left that
+    // list in S.a[0].  An empty list means "no overlap" (fm6_get_nei would rebuild the same empty list and return -1).
+    int rbeg = S.n[0] ? utg_get_nei(e, min_match, 0, S.s, l, S) : -1;
     if (S.overflow) { N.flags |= UTG_OVERFLOW; return; }
     N.n_mark_r = S.n_mark;
     N.rbeg = rbeg; N.n_nei = rbeg < 0 ? 0 : S.n_nei;
     if (rbeg < 0) { N.flags |= UTG_NO_OVLP; l = N.len; }
     N.ext_len = l - N.len;
+    if (N.n_nei >= 1) { N.nei0.x0 = S.nei[0].x[0]; N.nei0.x1 = S.nei[0].x[1]; N.nei0.x2 = S.nei[0].x[2]; N.nei0.ovlp = (i64)S.nei[0].info; }
+    for (int a = 0; a < 8; ++a) N.ext8[a] = a < N.ext_len ? S.s[N.len + a] : (u8)0;
     if (N.n_nei == 1) {
         N.cl = utg_check_left(e, min_match, 0, rbeg, S.s, l, S);
         if (S.overflow) { N.flags |= UTG_OVERFLOW; return; }

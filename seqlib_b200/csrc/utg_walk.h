@@ -56,28 +56,35 @@ struct UtgWalker {
             apply_marks(N, false);                         // try_right's set_bits happen whatever it returns
             if (N.rbeg < 0) break;
             int rbeg = beg + N.rbeg;
-            const UtgNei *nn = P.nei + N.nei_off;
-            for (int i = 0; i < N.n_nei; ++i) nei.push_back(MagEdge{nn[i].x0, (u64)nn[i].ovlp});
-            if (N.n_nei > 1) { set(bend, end); break; }
-            u64 k = nn[0].x0;
+            if (N.n_nei > 1) {
+                const UtgNei *nn = P.nei + N.nei_off;
+                for (int i = 0; i < N.n_nei; ++i) nei.push_back(MagEdge{nn[i].x0, (u64)nn[i].ovlp});
+                set(bend, end); break;
+            }
+            const UtgNei &n0 = N.nei0;                     // the single neighbour, inline in the record
+            __builtin_prefetch(&P.node[n0.x1]);            // the record the walk needs next, if this step is accepted
+            __builtin_prefetch((const char *)&P.node[n0.x1] + 64);
+            nei.push_back(MagEdge{n0.x0, (u64)n0.ovlp});
+            u64 k = n0.x0;
             if (k == end) break;
             if (get(bend, k)) { set(bend, k); break; }
             apply_marks(N, true);
             if (N.cl < 0) { set(bend, k); break; }
             if (k == k0) { is_loop = 1; break; }
-            if (nn[0].x1 == end) { nei.clear(); break; }
-            if ((int)nn[0].ovlp < min_merge_len) break;
-            end = nn[0].x1;
-            set_bits(nn[0].x0, nn[0].x1, nn[0].x2);
+            if (n0.x1 == end) { nei.clear(); break; }
+            if ((int)n0.ovlp < min_merge_len) break;
+            end = n0.x1;
+            set_bits(n0.x0, n0.x1, n0.x2);
             ++n_reads;
-            s.append((const char *)(P.seq + N.seq_off + N.len), (size_t)N.ext_len);
+            if (N.ext_len <= 8) s.append((const char *)N.ext8, (size_t)N.ext_len);
+            else s.append((const char *)(P.seq + N.seq_off + N.len), (size_t)N.ext_len);
             // the reference bumps cov[rbeg, ori_l) by one, saturating at '~': saturating adds commute, so the bumps are
             // collected as a difference array and applied once per direction (flush_cov)
             dcov.resize(s.size() + 1, 0);
             ++dcov[rbeg]; --dcov[ori_l];
             cov.append((size_t)N.ext_len, '"');
             beg = rbeg; ori_l = (int)s.size();
-            cur = nn[0].x1;
+            cur = n0.x1;
         }
         flush_cov();
         return n_reads;
