@@ -7,6 +7,9 @@
 #include <cstring>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
+#include <exception>
+#include <algorithm>
 #include "SeqLib/BWAIndex.h"
 #include "SeqLib/BWAAligner.h"
 #include "SeqLib/BWAWrapper.h"
@@ -241,11 +244,24 @@ void BWAAligner::alignSequences(const UnalignedSequenceVector &reads, std::vecto
     if (rc != B200_OK) throw std::runtime_error(std::string("BWAAligner::alignSequences: ") + b200_last_error());
     b200_results_view_t v;
     b200_results_view(res, &v);
-    try {
-        for (size_t i = 0; i < reads.size(); ++i)
-            emit_records(reads[i].Seq, reads[i].Name, v, (int64_t)i, hardclip, keepSecFrac, maxSecondary, false, out[i]);
-    } catch (...) { b200_results_free(res); throw; }
+    // bam1_t packing (src/BWAAligner.cpp:151-247) is independent per read: large batches are packed by all host threads
+    const size_t n = reads.size();
+    unsigned nt = n >= 4096 ? std::max(1u, std::min(std::thread::hardware_concurrency(), 32u)) : 1u;
+    std::vector<std::exception_ptr> errs(nt);
+    auto work = [&](unsigned t) {
+        try {
+            for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i)
+                emit_records(reads[i].Seq, reads[i].Name, v, (int64_t)i, hardclip, keepSecFrac, maxSecondary, false, out[i]);
+        } catch (...) { errs[t] = std::current_exception(); }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
     b200_results_free(res);
+    for (auto &e : errs) if (e) std::rethrow_exception(e);
 }
 
 // ------------------------------------------------------------------ BWAWrapper (legacy facade)
