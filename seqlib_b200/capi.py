@@ -358,6 +358,7 @@ def fml_last_stats():
 
 class KmerTable:
     """b200_kmer_table_t: the device-resident k-mer count table (bfc_ch_t)."""
+    h = None
 
     def __init__(self, seqs, quals, off, k, q=20, l_pre=20):
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
@@ -445,6 +446,7 @@ def fml_mag_text(opt, stage, seqs, off):
 
 class Fmd:
     """b200_fmd_t: device-resident FMD-index of a read set."""
+    h = None
 
     def __init__(self, seqs, off):
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)

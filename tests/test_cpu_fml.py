@@ -96,3 +96,25 @@ def test_edge_cases_vs_reference():
     e = _emul_correct(o, seqs, None, off)
     assert np.isnan(r[3]) and np.isnan(e[3])
     assert np.array_equal(r[0], e[0])
+
+
+def test_product_fails_loudly_without_a_device():
+    """No CPU fallback: on a box without a CUDA device the fermi entry points return B200_ERR_CUDA (the k <= 0 no-op, which does
+    no device work at all, is the only call that succeeds)."""
+    import os
+    from seqlib_b200 import capi
+    if not os.path.exists(capi.SO_PATH):
+        pytest.skip("libseqlib_b200.so not built")
+    if capi.lib().b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    seqs, quals, off = cases.fml_reads(50, region=500, seed=2)
+    o = capi.fml_default_opt()
+    s, q, l, kcov = capi.fml_correct_flat(o, seqs, quals, off)          # ec_k == 0: reference no-op
+    assert kcov == 255.0 and np.array_equal(s, seqs)
+    o.ec_k = 17
+    with pytest.raises(capi.B200Error, match="-2"):
+        capi.fml_correct_flat(o, seqs, quals, off)
+    with pytest.raises(capi.B200Error, match="-2"):
+        capi.fml_assemble_flat(capi.fml_default_opt(), seqs, quals, off)
+    with pytest.raises(capi.B200Error, match="-2"):
+        capi.Fmd(seqs, off)
