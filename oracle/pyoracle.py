@@ -100,3 +100,30 @@ def ksw_extend2_batch(jobs, qpool, tpool, mat, o_del=6, e_del=1, o_ins=6, e_ins=
     mat = np.ascontiguousarray(mat, dtype=np.int8)
     lib().oracle_ksw_extend2_batch(len(jobs), jobs.ctypes.data, qpool.ctypes.data, tpool.ctypes.data, mat.ctypes.data, o_del, e_del, o_ins, e_ins, out.ctypes.data)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- fermi-lite BFC stages
+def fml_default_opt():
+    """fml_opt_init values (fermi-lite/misc.c:31-41) without needing any library."""
+    from seqlib_b200.abi import FmlOpt
+    o = FmlOpt()
+    o.n_threads, o.ec_k, o.min_cnt, o.max_cnt, o.min_asm_ovlp, o.min_merge_len = 1, 0, 4, 8, 33, 0
+    return o
+
+
+def fml_correct_flat(opt, seqs, quals, off, flt_uniq=False):
+    """oracle_fml_correct_flat (oracle/oracle_fml.c): (seqs, quals, lens, kcov, hist[320]); inputs are not modified."""
+    from seqlib_b200.abi import FmlOpt  # noqa: F401
+    L = lib()
+    L.oracle_fml_correct_flat.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_float), C.c_void_p]
+    seqs = np.array(seqs, dtype=np.uint8, copy=True)
+    quals = None if quals is None else np.array(quals, dtype=np.uint8, copy=True)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    n = len(off) - 1
+    lens = np.zeros(max(n, 1), dtype=np.int32)
+    hist = np.zeros(320, dtype=np.uint64)
+    kcov = C.c_float(0)
+    L.oracle_fml_correct_flat(C.byref(opt), int(bool(flt_uniq)), n, seqs.ctypes.data, quals.ctypes.data if quals is not None else None,
+                              off.ctypes.data, lens.ctypes.data, C.byref(kcov), hist.ctypes.data)
+    return seqs, quals, lens[:n], kcov.value, hist

@@ -31,6 +31,38 @@ def test_bfc_device_code_on_cpu_vs_golden(name):
     assert fmlcases.compare(got, z) == []
 
 
+@pytest.mark.parametrize("name", fmlcases.FML_SETS)
+def test_c_restatement_vs_golden(name):
+    """oracle/oracle_fml.c (plain-C restatement of fml_count / bfc_ec1 / fml_fltuniq, sorted-array count table) reproduces
+    the reference's committed output: this pins the oracle that checks the CUDA path where oracle/_ref is absent."""
+    from oracle import pyoracle
+    seqs, quals, off, z = fmlcases.load(name)
+    got = fmlcases.pipeline(lambda *a, **k: pyoracle.fml_correct_flat(*a, **k)[:4], pyoracle.fml_default_opt(), seqs, quals, off)
+    assert fmlcases.compare(got, z) == []
+
+
+def test_c_restatement_vs_live_reference():
+    from oracle import pyoracle, pyref_fml
+    if not pyref_fml.have_ref():
+        pytest.skip("oracle/_ref not built")
+    seqs, quals, off = cases.fml_reads(700, region=1800, seed=12)
+    for ec_k in (15, 23, 33):
+        o = pyoracle.fml_default_opt()
+        o.ec_k = ec_k
+        ro = pyref_fml.default_opt()
+        ro.ec_k = ec_k
+        for qq in (quals, None):
+            for flt in (False, True):
+                r = pyref_fml.correct_flat(ro, seqs, qq, off, flt_uniq=flt)
+                e = pyoracle.fml_correct_flat(o, seqs, qq, off, flt_uniq=flt)
+                assert np.array_equal(r[2], e[2]) and r[3] == e[3]
+                for i in range(len(off) - 1):
+                    a, b = int(off[i]), int(off[i]) + int(r[2][i])
+                    assert np.array_equal(r[0][a:b], e[0][a:b])
+                    if qq is not None:
+                        assert np.array_equal(r[1][a:b], e[1][a:b])
+
+
 def test_golden_matches_live_reference():
     """The committed fixtures are what the reference library produces here (pins the oracle)."""
     from oracle import pyref_fml
