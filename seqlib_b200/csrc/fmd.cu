@@ -102,6 +102,66 @@ __global__ void __launch_bounds__(256) k_fmd_emit(const u8 *text, const u64 *sta
     bwt8[x] = p != start[row_str[p]] ? text[p - 1] : (u8)0;      // the symbol before the row's suffix; rows at offset 0 carry $
 }
 
+// ------------------------------------------------------------------------------------------------ prefix doubling
+// The row key s[i..) $ revcomp(s[0..i)) $ is (A $, B $) with A = s_j[i..) and B = s_j'[L - i ..) -- both SUFFIXES of strings of
+// the collection.  So: (1) rank every row by its own suffix A $ (equal suffixes share a rank): one radix sort on the first
+// 27 symbols, then doubling rounds on (rank of row p, rank of row p + h), h = 27, 54, 108, ...; (2) one last sort on
+// (suffix rank of the row, suffix rank of the partner's row at offset L - i).  log2(L / 27) + 3 sorts of all rows instead of
+// one refinement round per 27 symbols of the deepest tie.
+__global__ void __launch_bounds__(256) k_pd_key0(const u8 *text, const u64 *start, const u32 *row_str, u64 n, u64 *keys, u32 *ids)
+{
+    u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    u64 e = start[row_str[p] + 1] - 1;            // position of the string's sentinel
+    u64 key = 0;
+#pragma unroll 1
+    for (int t = 0; t < FMD_KEY_SYMS; ++t) { u64 q = p + t; key = key * 5 + (q <= e ? (u64)text[q] : 0ull); }
+    keys[p] = key; ids[p] = (u32)p;
+}
+
+// head[x] = first element of a run of equal keys (in sorted order); hidx = its own index there, 0 elsewhere
+__global__ void __launch_bounds__(256) k_pd_heads(const u64 *keys, u64 n, u32 *hidx, u32 *n_groups_partial)
+{
+    u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    bool head = x == 0 || keys[x] != keys[x - 1];
+    hidx[x] = head ? (u32)x : 0u;
+    if (head) atomicAdd(n_groups_partial, 1u);
+}
+
+// rank[row] = index of the head of the row's run (after an inclusive max-scan of hidx)
+__global__ void __launch_bounds__(256) k_pd_scatter_rank(const u32 *ids, const u32 *hidx, u64 n, u32 *rank)
+{
+    u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    rank[ids[x]] = hidx[x];
+}
+
+// doubling key of the row at sorted position x: (rank of p) << 32 | (rank of p + h) + 1, 0 past the string's sentinel
+__global__ void __launch_bounds__(256) k_pd_key_double(const u32 *ids, const u32 *rank, const u64 *start, const u32 *row_str, u64 n, u32 h, u64 *keys)
+{
+    u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    u64 p = ids[x];
+    u64 e = start[row_str[p] + 1] - 1;
+    u64 q = p + h;
+    u64 r2 = q <= e ? (u64)rank[q] + 1 : 0ull;
+    keys[x] = (u64)rank[p] << 32 | r2;
+}
+
+// final key: (suffix rank of the row) << 32 | suffix rank of the partner strand's row at offset L - i
+__global__ void __launch_bounds__(256) k_pd_key_final(const u32 *ids, const u32 *rank, const u64 *start, const u32 *row_str, u64 n, u64 *keys)
+{
+    u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    u64 p = ids[x];
+    u64 j = row_str[p], sj = start[j], L = start[j + 1] - sj - 1, i = p - sj;
+    u64 pp = start[j ^ 1] + (L - i);
+    keys[x] = (u64)rank[p] << 32 | (u64)rank[pp];
+}
+
+struct PdMax { __device__ __forceinline__ u32 operator()(u32 a, u32 b) const { return a > b ? a : b; } };
+
 struct Cnt4 { u32 c[4]; };
 struct Cnt4Add { __device__ __forceinline__ Cnt4 operator()(const Cnt4 &a, const Cnt4 &b) const { Cnt4 r; for (int i = 0; i < 4; ++i) r.c[i] = a.c[i] + b.c[i]; return r; } };
 
@@ -151,14 +211,11 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
     if (n >= (1ull << 31) - 1024) throw std::length_error("FMD-index of more than 2^31 symbols");
     F.text.reserve(n + 16);
     k_fmd_text<<<nblk(n_reads, 256), 256>>>(d_seq, d_off, n_reads, F.start.as<u64>(), F.text.as<u8>());
-    // sort all rows
-    DevBuf keys, ids, row_str;
-    keys.reserve(n * 8); ids.reserve(n * 4); row_str.reserve(n * 4);
+    // sort all rows (prefix doubling, see above)
+    DevBuf keys[2], ids[2], row_str, rank, hidx, ngrp;
+    keys[0].reserve(n * 8); keys[1].reserve(n * 8); ids[0].reserve(n * 4); ids[1].reserve(n * 4);
+    row_str.reserve(n * 4); rank.reserve(n * 4); hidx.reserve(n * 4); ngrp.reserve(16);
     k_fmd_row_str<<<nblk(n_str, 256), 256>>>(F.start.as<u64>(), n_str, row_str.as<u32>());
-    Sorter<RotKey, u32> S;
-    S.kf.text = F.text.as<u8>(); S.kf.start = F.start.as<u64>(); S.kf.row_str = row_str.as<u32>();
-    // longest key = (longest read + 2) symbols
-    k_fmd_rows<<<nblk(n, 256), 256>>>(n, S.kf, keys.as<u64>(), ids.as<u32>());
     u32 max_rows = 0;
     {
         DevBuf mx; mx.reserve(16);
@@ -168,9 +225,40 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
         CU_CHECK(cub::DeviceReduce::Max(tmp.p, tb, rows.as<u32>(), mx.as<u32>(), (int)n_str));
         CU_CHECK(cudaMemcpy(&max_rows, mx.p, 4, cudaMemcpyDeviceToHost));
     }
-    S.max_depth = (int)((max_rows + 1 + FMD_KEY_SYMS - 1) / FMD_KEY_SYMS);
-    u64 *kp = keys.as<u64>(); u32 *ip = ids.as<u32>();
-    S.sort_bucket(kp, ip, n);
+    int cur = 0;
+    auto sort_rows = [&](int bits) {
+        cub::DoubleBuffer<u64> dk(keys[cur].as<u64>(), keys[cur ^ 1].as<u64>());
+        cub::DoubleBuffer<u32> dv(ids[cur].as<u32>(), ids[cur ^ 1].as<u32>());
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)n, 0, bits);
+        tmp.reserve(tb);
+        CU_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int)n, 0, bits));
+        if (dk.Current() != keys[cur].as<u64>()) { std::swap(keys[0].p, keys[1].p); std::swap(keys[0].cap, keys[1].cap); }
+        if (dv.Current() != ids[cur].as<u32>()) { std::swap(ids[0].p, ids[1].p); std::swap(ids[0].cap, ids[1].cap); }
+    };
+    auto rerank = [&]() -> u32 {            // rank[] from the sorted keys; returns the number of distinct keys
+        CU_CHECK(cudaMemset(ngrp.p, 0, 4));
+        k_pd_heads<<<nblk(n, 256), 256>>>(keys[cur].as<u64>(), n, hidx.as<u32>(), ngrp.as<u32>());
+        size_t tb = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, tb, hidx.as<u32>(), hidx.as<u32>(), PdMax(), (int)n);
+        tmp.reserve(tb);
+        CU_CHECK(cub::DeviceScan::InclusiveScan(tmp.p, tb, hidx.as<u32>(), hidx.as<u32>(), PdMax(), (int)n));
+        k_pd_scatter_rank<<<nblk(n, 256), 256>>>(ids[cur].as<u32>(), hidx.as<u32>(), n, rank.as<u32>());
+        u32 g = 0;
+        CU_CHECK(cudaMemcpy(&g, ngrp.p, 4, cudaMemcpyDeviceToHost));
+        return g;
+    };
+    k_pd_key0<<<nblk(n, 256), 256>>>(F.text.as<u8>(), F.start.as<u64>(), row_str.as<u32>(), n, keys[cur].as<u64>(), ids[cur].as<u32>());
+    sort_rows(63);
+    u32 groups = rerank();
+    for (u32 h = FMD_KEY_SYMS; h < max_rows && groups < n; h <<= 1) {
+        k_pd_key_double<<<nblk(n, 256), 256>>>(ids[cur].as<u32>(), rank.as<u32>(), F.start.as<u64>(), row_str.as<u32>(), n, h, keys[cur].as<u64>());
+        sort_rows(64);
+        groups = rerank();
+    }
+    k_pd_key_final<<<nblk(n, 256), 256>>>(ids[cur].as<u32>(), rank.as<u32>(), F.start.as<u64>(), row_str.as<u32>(), n, keys[cur].as<u64>());
+    sort_rows(64);
+    u32 *ip = ids[cur].as<u32>();
     // BWT symbols, rank blocks
     DevBuf bwt8; bwt8.reserve(n + 16);
     k_fmd_emit<<<nblk(n, 256), 256>>>(F.text.as<u8>(), F.start.as<u64>(), row_str.as<u32>(), ip, n, bwt8.as<u8>());
