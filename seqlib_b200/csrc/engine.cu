@@ -430,6 +430,7 @@ static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
     int per = 0;
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP>, 128, smem));
     if (per < 1) per = 1;
+    { static const int occ = getenv("B200_OCC_SEED") ? atoi(getenv("B200_OCC_SEED")) : 0; if (occ > 0 && occ < per) per = occ; }
     k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
 }
 static void launch_seed2(Engine &E, KArgs &A)
@@ -492,6 +493,7 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
                 CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_group<G, false>, 128, smem));
             }
             if (per < 1) per = 1;
+            { static const int occ = getenv("B200_OCC_EXT") ? atoi(getenv("B200_OCC_EXT")) : 0; if (occ > 0 && occ < per) per = occ; }
             int grid = (int)std::min<i64>((i64)E.sms * per, std::max<i64>(1, (A.n_work + (128 / G) - 1) / (128 / G)));
             size_t gstride = (extend_group_scratch_bytes(A.caps) + 63) & ~(size_t)63;
             (spill ? E.group_scratch2 : E.group_scratch).reserve(gstride * (size_t)grid * (128 / G));

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cmath>
+#include <climits>
 #include <string>
 #include <vector>
 #include <unordered_map>
@@ -491,11 +492,95 @@ struct Mag {
         merge(0, 0);
     }
 
+    // ------------------------------------------------------------------ closed bubbles (bubble.c:22-176)
+    struct TrInfo {                                  // trinfo_t / g_trinull
+        u64 id; int cnt[2]; int n[2][2], d[2][2]; u64 v[2][2];
+        explicit TrInfo(u64 id_) : id(id_)
+        {
+            cnt[0] = cnt[1] = 0;
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { n[a][b] = INT32_MIN; d[a][b] = INT32_MIN; v[a][b] = (u64)-1; }
+        }
+    };
+    // mag_vh_simplify_bubble: keep the two best-supported paths of a bubble starting at end idd, delete the other vertices
+    void vh_simplify_bubble(u64 idd, int max_vtx, int max_dist, std::vector<TrInfo> &pool, std::vector<u64> &stack,
+                            std::vector<i32> &ptr, std::unordered_map<u64, int> &hh)
+    {
+        int n_pending = 0;
+        MagV *p = &v[idd >> 1], *q;
+        if (p->len < 0 || p->nei[idd & 1].size() < 2) return;
+        stack.clear(); pool.clear(); hh.clear();
+        auto tip_alloc = [&](u64 id) { pool.emplace_back(id); return (i32)pool.size() - 1; };
+        ptr[idd >> 1] = tip_alloc(idd >> 1);
+        pool[ptr[idd >> 1]].d[(idd & 1) ^ 1][0] = -p->len;
+        pool[ptr[idd >> 1]].n[(idd & 1) ^ 1][0] = -p->nsr;
+        stack.push_back(idd ^ 1);
+        while (!stack.empty()) {
+            u64 x, y;
+            if (stack.size() == 1 && stack[0] != (idd ^ 1) && n_pending == 0) break;
+            x = stack.back(); stack.pop_back();
+            p = &v[x >> 1];
+            std::vector<MagEdge> &r = p->nei[(x & 1) ^ 1];
+            {
+                const TrInfo &tp = pool[ptr[x >> 1]];
+                if ((int)pool.size() > max_vtx || tp.d[x & 1][0] > max_dist || tp.d[x & 1][1] > max_dist || r.empty()) break;
+            }
+            for (size_t i = 0; i < r.size(); ++i) {
+                int nsr, dist, which;
+                if ((i64)r[i].x < 0) continue;
+                y = tid2idd(r[i].x);
+                if (y == (idd ^ 1)) { stack.clear(); break; }
+                q = &v[y >> 1];
+                if (ptr[y >> 1] < 0) {
+                    ptr[y >> 1] = tip_alloc(y >> 1); ++n_pending;
+                    v128_clean(q->nei[y & 1]);
+                }
+                const TrInfo tp = pool[ptr[x >> 1]];          // copy: tip_alloc may have moved the pool
+                TrInfo &tq = pool[ptr[y >> 1]];
+                nsr = tp.n[x & 1][0] + p->nsr; which = 0;
+                dist = tp.d[x & 1][0] + p->len - (int)r[i].y;
+                if (nsr > tq.n[y & 1][0]) {
+                    tq.n[y & 1][1] = tq.n[y & 1][0]; tq.n[y & 1][0] = nsr;
+                    tq.v[y & 1][1] = tq.v[y & 1][0]; tq.v[y & 1][0] = (x ^ 1) << 32 | (u64)i << 1 | (u64)which;
+                    tq.d[y & 1][1] = tq.d[y & 1][0]; tq.d[y & 1][0] = dist;
+                    nsr = tp.n[x & 1][1] + p->nsr; which = 1;
+                    dist = tp.d[x & 1][1] + p->len - (int)r[i].y;
+                }
+                if (nsr > tq.n[y & 1][1]) { tq.n[y & 1][1] = nsr; tq.v[y & 1][1] = (x ^ 1) << 32 | (u64)i << 1 | (u64)which; tq.d[y & 1][1] = dist; }
+                if (++tq.cnt[y & 1] == (int)q->nei[y & 1].size()) { stack.push_back(y); --n_pending; }
+            }
+        }
+        u64 top = stack.empty() ? 0 : stack[0];
+        if (n_pending == 0 && stack.size() == 1) {
+            u64 x = stack[0];
+            for (int w = 0; w < 2; ++w) {                 // backtrace along the best and the second best path
+                u64 end = pool[ptr[x >> 1]].v[x & 1][w];
+                while (end >> 32 != idd) {
+                    hh.emplace(end >> 33, 1);
+                    end = pool[ptr[end >> 33]].v[((end >> 32) ^ 1) & 1][end & 1];
+                }
+            }
+        }
+        for (size_t i = 0; i < pool.size(); ++i) ptr[pool[i].id] = -1;
+        if (!hh.empty())
+            for (size_t i = 1; i < pool.size(); ++i) {
+                u64 id = pool[i].id;
+                if (id != top >> 1 && hh.find(id) == hh.end()) v_del(v[id]);
+            }
+    }
+    void simplify_bubble(int max_vtx, int max_dist)
+    {
+        std::vector<TrInfo> pool; std::vector<u64> stack; std::vector<i32> ptr(v.size(), -1); std::unordered_map<u64, int> hh;
+        for (size_t i = 0; i < v.size(); ++i) {
+            vh_simplify_bubble((u64)i << 1 | 0, max_vtx, max_dist, pool, stack, ptr, hh);
+            vh_simplify_bubble((u64)i << 1 | 1, max_vtx, max_dist, pool, stack, ptr, hh);
+        }
+        merge(0, 0);
+    }
+
     // ------------------------------------------------------------------ portal (mag.c:559-620, misc.c:130-137)
     void clean(const b200_magopt_t &o)
     {
         const int F_AGGRESSIVE = 0x20, F_POPOPEN = 0x40, F_NO_SIMPL = 0x80;
-        if (!(o.flag & F_NO_SIMPL)) throw std::invalid_argument("mag_g_simplify_bubble (flag without MAG_F_NO_SIMPL) is not implemented");
         if (min_ovlp < o.min_ovlp) min_ovlp = o.min_ovlp;
         for (int j = 2; j <= o.min_ensr; ++j) rm_vext(o.min_elen, j);
         merge(0, o.min_merge_len);
@@ -504,6 +589,7 @@ struct Mag {
         for (int j = 2; j <= o.min_ensr; ++j) rm_vext(o.min_elen, j);
         merge(0, o.min_merge_len);
         if ((o.flag & F_AGGRESSIVE) || (o.flag & F_POPOPEN)) pop_open(o.min_elen);
+        if (!(o.flag & F_NO_SIMPL)) simplify_bubble(o.max_bvtx, o.max_bdist);
         pop_simple(o.max_bcov, o.max_bfrac, o.min_merge_len, o.max_bdiff, o.flag & F_AGGRESSIVE);
         rm_vint(o.min_elen, o.min_insr, min_ovlp);
         rm_edge(min_ovlp, o.min_dratio1, o.min_elen, o.min_ensr);

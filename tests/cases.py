@@ -211,3 +211,28 @@ def long_reads(pac, l_pac, n=40, seed=0x5EED0007, lo=800, hi=4000):
             s = seg(ln)
         reads.append("".join("ACGT"[b] for b in s))
     return reads
+
+
+def fml_diploid_reads(n, region, seed, snp=0.004, indel=0.001, err=0.005):
+    """Reads from two haplotypes (SNPs + small deletions between them): the unitig graph has real bubbles, which is what
+    mag_g_pop_simple / mag_g_simplify_bubble / the AGGRESSIVE flag act on.  Returns (seqs, quals, off), quality 'I'."""
+    rng = np.random.default_rng(seed)
+    h1 = rng.integers(0, 4, region, dtype=np.uint8)
+    h2 = h1.copy()
+    m = rng.random(region) < snp
+    h2[m] = (h2[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
+    h2 = h2[rng.random(region) >= indel]
+    comp = np.array([3, 2, 1, 0], dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = []
+    for _ in range(n):
+        h = h1 if rng.random() < 0.5 else h2
+        p = int(rng.integers(0, len(h) - 150))
+        s = h[p:p + 150].copy()
+        e = rng.random(150) < err
+        s[e] = (s[e] + rng.integers(1, 4, int(e.sum()), dtype=np.uint8)) & 3
+        if rng.random() < 0.5:
+            s = comp[s[::-1]]
+        seqs.append(acgt[s])
+    off = np.arange(n + 1, dtype=np.int64) * 150
+    return np.concatenate(seqs), np.full(n * 150, ord("I"), dtype=np.uint8), off

@@ -73,3 +73,25 @@ def test_small_set_with_model_bwt_no_reference_needed():
         pytest.skip("set too large for the brute-force model")
     bwt = fmdmodel.bwt(unpack_reads(fs, foff))
     assert hashlib.md5(bwt.tobytes()).hexdigest() == gold["bwt_md5"]
+
+
+@pytest.mark.parametrize("flag", [0xc0, 0x40, 0x00, 0x20])
+def test_bubble_passes_vs_live_reference(flag):
+    """Graph cleaning with every combination of MAG_F_NO_SIMPL / MAG_F_POPOPEN / MAG_F_AGGRESSIVE on a diploid read set (real
+    bubbles): mag_g_simplify_bubble, mag_g_pop_simple (incl. the fork's additive-gap SW "score") and mag_g_pop_open leave
+    the same graph as the reference."""
+    from oracle import pyref_fml
+    if not pyref_fml.have_ref():
+        pytest.skip("oracle/_ref not built")
+    seqs, quals, off = cases.fml_diploid_reads(3000, 4000, 3)
+    exp = fmlcases.reference_pipeline(pyref_fml, seqs, quals, off)
+    fs, foff = fmlcases.filtered_reads(exp, off)
+    kcov = float(exp["flt_kcov"])
+    bwt = pyref_fml.bwt(fs, foff)[0]
+    ro = pyref_fml.default_opt()
+    ro.mag_opt.flag = flag
+    want, _, _ = pyref_fml.mag_text(ro, 1, kcov, fs, foff)
+    o = fmlcases.asm_opt_for(_opt(), int(foff[-1]), len(foff) - 1, kcov)
+    o.mag_opt.flag = flag
+    got, _, _ = fmdsim.mag_text(bwt, o, 1)
+    assert got == want

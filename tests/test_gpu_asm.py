@@ -177,3 +177,30 @@ def test_cxx_fermi_assembler_and_bfc(capi, tmp_path):
     o2.mag_opt.min_ensr, o2.mag_opt.min_insr = me, me - 1
     flat = capi.fml_seqs2utg_flat(o2, up, off)
     assert [u["seq"].decode() for u in flat] == contigs
+
+
+@pytest.mark.parametrize("flag", [0xc0, 0x40, 0x20])
+def test_bubble_flags_vs_live_reference(capi, flag):
+    """FermiAssembler::SetSimplifyBubble / SetAggressiveTrim paths (MAG_F_NO_SIMPL cleared, MAG_F_AGGRESSIVE set) on a diploid
+    read set: the cleaned graph equals the reference's."""
+    from oracle import pyref_fml
+    if not pyref_fml.have_ref():
+        pytest.skip("oracle/_ref not built")
+    seqs, quals, off = cases.fml_diploid_reads(3000, 4000, 3)
+    exp = fmlcases.reference_pipeline(pyref_fml, seqs, quals, off)
+    fs, foff = fmlcases.filtered_reads(exp, off)
+    kcov = float(exp["flt_kcov"])
+    ro = pyref_fml.default_opt()
+    ro.mag_opt.flag = flag
+    want, _, _ = pyref_fml.mag_text(ro, 1, kcov, fs, foff)
+    o = fmlcases.asm_opt_for(capi.fml_default_opt(), int(foff[-1]), len(foff) - 1, kcov)
+    o.mag_opt.flag = flag
+    got, _ = capi.fml_mag_text(o, 1, fs, foff)
+    assert got == want
+    # and the whole pipeline with that flag
+    ro2 = pyref_fml.default_opt()
+    ro2.mag_opt.flag = flag
+    o2 = capi.fml_default_opt()
+    o2.mag_opt.flag = flag
+    e, _ = pyref_fml.assemble(ro2, seqs, quals, off)
+    assert fmlcases.utg_text(capi.fml_assemble_flat(o2, seqs, quals, off)) == fmlcases.utg_text(e)
