@@ -1,0 +1,25 @@
+"""Latency of one FermiAssembler-sized problem (local assembly of a window: 10^3..10^5 reads) through b200_fml_assemble_flat,
+next to the reference's fml_assemble on one host core."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from seqlib_b200 import capi, synth
+from oracle import pyref_fml
+capi.set_device(0)
+for n in (1000, 5000, 20000, 100000):
+    region = max(400, n)            # 150x
+    pac = synth.reference(region, seed=0x5EED0005)
+    seqs, off, _, _ = synth.reads(pac, region, synth.contigs_for(region, 1, "w"), n, 150, 0.01, 0.0, seed=0x5EED0006)
+    quals = np.full(len(seqs), ord("I"), dtype=np.uint8)
+    opt = capi.fml_default_opt()
+    capi.fml_assemble_flat(opt, seqs, quals, off)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter(); u = capi.fml_assemble_flat(opt, seqs, quals, off); ts.append(time.perf_counter() - t0)
+    st = capi.fml_last_stats()
+    line = "n=%6d: %.1f ms per assembly (%d unitigs, longest %d, %d launches)" % (n, 1e3 * np.median(ts), len(u), max([len(x["seq"]) for x in u] + [0]), st["n_launches"])
+    if pyref_fml.have_ref() and n <= 20000:
+        exp, sec = pyref_fml.assemble(pyref_fml.default_opt(), seqs, quals, off)
+        line += "; reference %.1f ms, identical=%s" % (1e3 * sec, [x["seq"] for x in exp] == [x["seq"] for x in u])
+    print(line, flush=True)

@@ -18,6 +18,8 @@
 
 namespace b200 {
 
+thread_local int g_fmd_launches = 0;      // kernels launched by the last fmd_build_device on this thread (cub passes counted per call)
+
 static inline unsigned nblk(u64 n, int t) { return (unsigned)((n + t - 1) / t); }
 
 // per read: usable length (0 = not indexed); fml_fmi_gen's filters (fermi-lite/misc.c:85-96)
@@ -193,6 +195,7 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
 {
     (void)st_unused;        // the sorter runs on the default stream; everything here follows it
     F.release();
+    g_fmd_launches = 0;
     const u64 n_str = 2 * (u64)n_reads;
     if (n_reads == 0) return;
     DevBuf rows, tmp;
@@ -235,6 +238,7 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
         CU_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int)n, 0, bits));
         if (dk.Current() != keys[cur].as<u64>()) { std::swap(keys[0].p, keys[1].p); std::swap(keys[0].cap, keys[1].cap); }
         if (dv.Current() != ids[cur].as<u32>()) { std::swap(ids[0].p, ids[1].p); std::swap(ids[0].cap, ids[1].cap); }
+        g_fmd_launches += (bits + 7) / 8 + 2;          // onesweep: histogram + scan + one pass per 8 bits
     };
     auto rerank = [&]() -> u32 {            // rank[] from the sorted keys; returns the number of distinct keys
         CU_CHECK(cudaMemset(ngrp.p, 0, 4));
@@ -246,6 +250,7 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
         k_pd_scatter_rank<<<nblk(n, 256), 256>>>(ids[cur].as<u32>(), hidx.as<u32>(), n, rank.as<u32>());
         u32 g = 0;
         CU_CHECK(cudaMemcpy(&g, ngrp.p, 4, cudaMemcpyDeviceToHost));
+        g_fmd_launches += 4;
         return g;
     };
     k_pd_key0<<<nblk(n, 256), 256>>>(F.text.as<u8>(), F.start.as<u64>(), row_str.as<u32>(), n, keys[cur].as<u64>(), ids[cur].as<u32>());
@@ -283,6 +288,7 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
     F.idx.blk = F.blocks.as<FmdBlock>(); F.idx.n = n; F.idx.n_str = tot[0];
     F.idx.cnt[0] = 0;
     for (int c = 0; c < 6; ++c) F.idx.cnt[c + 1] = F.idx.cnt[c] + tot[c];
+    g_fmd_launches += 14;      // plan, scans, text, row map, keys, emit, pack, counts
     F.n_blk = n_blk;
     F.bwt8.p = bwt8.p; F.bwt8.cap = bwt8.cap; bwt8.p = nullptr; bwt8.cap = 0;     // kept for b200_fmd_bwt (debug / parity)
 }

@@ -18,6 +18,7 @@ struct FmdDevice {
 };
 
 // fmd.cu: builds F from reads resident on the device (ASCII pool + offsets [+ per-read kept lengths])
+extern thread_local int g_fmd_launches;
 void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i32 *d_len, i64 n_reads, cudaStream_t st);
 
 } // namespace b200

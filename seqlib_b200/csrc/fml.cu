@@ -583,6 +583,7 @@ static bool mag_from_device_reads(FmlEngine &E, ReadPool R, const i32 *d_len, in
     CU_CHECK(cudaEventRecord(E.ev[5], 0));
     CU_CHECK(cudaEventSynchronize(E.ev[5]));
     g_fml_stats.ms_fmd = ms_between(E.ev[4], E.ev[5]);
+    g_fml_stats.n_launches += g_fmd_launches;
     g_fml_stats.fmd_symbols = F.idx.n; g_fml_stats.n_strings = F.idx.n_str;
     g.v.clear();
     if (F.idx.n == 0) return false;          // fml_seq2fmi returned NULL
