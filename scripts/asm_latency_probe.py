@@ -18,6 +18,7 @@ for n in (1000, 5000, 20000, 100000):
     for _ in range(5):
         t0 = time.perf_counter(); u = capi.fml_assemble_flat(opt, seqs, quals, off); ts.append(time.perf_counter() - t0)
     st = capi.fml_last_stats()
+    print("   stages:", {k: round(st[k], 2) for k in ("ms_count", "ms_ec", "ms_flt", "ms_fmd", "ms_nodes", "ms_walk_host", "ms_clean_host", "ms_total")}, flush=True)
     line = "n=%6d: %.1f ms per assembly (%d unitigs, longest %d, %d launches)" % (n, 1e3 * np.median(ts), len(u), max([len(x["seq"]) for x in u] + [0]), st["n_launches"])
     if pyref_fml.have_ref() and n <= 20000:
         exp, sec = pyref_fml.assemble(pyref_fml.default_opt(), seqs, quals, off)

@@ -228,6 +228,26 @@ struct UtgArgs {
     u8 *scratch; size_t stride; int cap, s_cap, tmark_cap;
 };
 
+// copies what utg_node left in the scratch slot into the pools (bump allocation) and stores the record
+__device__ __forceinline__ void utg_emit_node(const UtgArgs &A, u64 x, const UtgScratch &S, UtgNode &N)
+{
+    N.seq_off = N.nei_off = N.mark_off = 0;
+    if (!(N.flags & UTG_OVERFLOW)) {
+        u64 ns = (u64)(N.len + N.ext_len), nn = (u64)N.n_nei, nm = (u64)(N.n_mark_r + N.n_mark_c);
+        u64 so = ns ? atomicAdd(A.ctr + 1, (unsigned long long)ns) : 0;
+        u64 no = nn ? atomicAdd(A.ctr + 2, (unsigned long long)nn) : 0;
+        u64 mo = nm ? atomicAdd(A.ctr + 3, (unsigned long long)nm) : 0;
+        if (so + ns > A.seq_cap || no + nn > A.nei_cap || mo + nm > A.mark_cap) atomicAdd(A.ctr + 4, 1ull);
+        else {
+            N.seq_off = so; N.nei_off = no; N.mark_off = mo;
+            for (u64 i = 0; i < ns; ++i) A.seq[so + i] = S.s[i];
+            for (u64 i = 0; i < nn; ++i) { UtgNei o; o.x0 = S.nei[i].x[0]; o.x1 = S.nei[i].x[1]; o.x2 = S.nei[i].x[2]; o.ovlp = (i64)S.nei[i].info; A.nei[no + i] = o; }
+            for (u64 i = 0; i < nm; ++i) A.mark[mo + i] = S.mark[i];
+        }
+    }
+    A.node[x] = N;
+}
+
 // one string per thread: fm6_retrieve + fm6_get_nei + check_left (unitig.cuh), results bump-allocated into the pools
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_utg_nodes(const __grid_constant__ UtgArgs A)
@@ -246,25 +266,89 @@ __global__ void __launch_bounds__(128, MINB) k_utg_nodes(const __grid_constant__
         if (t < n) {
             u64 x = A.todo ? (u64)A.todo[t] : t;
             UtgNode N;
-            utg_node(A.e, A.min_match, x, S, N);
-            N.seq_off = N.nei_off = N.mark_off = 0;
-            if (!(N.flags & UTG_OVERFLOW)) {
-                u64 ns = (u64)(N.len + N.ext_len), nn = (u64)N.n_nei, nm = (u64)(N.n_mark_r + N.n_mark_c);
-                u64 so = ns ? atomicAdd(A.ctr + 1, (unsigned long long)ns) : 0;
-                u64 no = nn ? atomicAdd(A.ctr + 2, (unsigned long long)nn) : 0;
-                u64 mo = nm ? atomicAdd(A.ctr + 3, (unsigned long long)nm) : 0;
-                if (so + ns > A.seq_cap || no + nn > A.nei_cap || mo + nm > A.mark_cap) atomicAdd(A.ctr + 4, 1ull);
-                else {
-                    N.seq_off = so; N.nei_off = no; N.mark_off = mo;
-                    for (u64 i = 0; i < ns; ++i) A.seq[so + i] = S.s[i];
-                    for (u64 i = 0; i < nn; ++i) { UtgNei o; o.x0 = S.nei[i].x[0]; o.x1 = S.nei[i].x[1]; o.x2 = S.nei[i].x[2]; o.ovlp = (i64)S.nei[i].info; A.nei[no + i] = o; }
-                    for (u64 i = 0; i < nm; ++i) A.mark[mo + i] = S.mark[i];
-                }
-            }
-            A.node[x] = N;
+            utg_node(A.e, A.min_match, x, S, N, UtgNoCoop());
+            utg_emit_node(A, x, S, N);
         }
         __syncwarp();
     }
+}
+
+// ---- G lanes per string, for inputs too small to fill the machine with one string per thread (window-sized assemblies):
+// the time of k_utg_nodes is then the latency of ONE string (~9 ms).  Lane 0 of a group (the master) runs the reference-
+// shaped code; the extensions of all overlap intervals of a round -- independent of each other, ~120 per round at 150x
+// coverage -- are shared out over the G lanes through a shared-memory mailbox (two-phase loops of unitig.cuh) and consumed
+// in interval order by the master.  Per-string latency drops ~4x; with 10^5+ strings the one-thread-per-string kernel
+// keeps 10x more strings in flight and wins (measured 496 ms vs 1 391 ms at 2*10^6 strings).
+struct UtgMailbox { int cmd, pn, arg; const FmdIntv *prev; const i32 *cat; UtgExt *R; };
+enum { UTG_CMD_FWD = 1, UTG_CMD_BWD = 2, UTG_CMD_EXIT = 3 };
+
+template <int G>
+struct UtgGroupCoop {
+    static constexpr bool kTwoPhase = true;
+    volatile UtgMailbox *mb; unsigned mask; int gl;
+    __device__ __forceinline__ static void share_fwd(const FmdIndex &e, const FmdIntv *prev, int pn, const i32 *cat, bool later, UtgExt *R, int gl)
+    {
+        for (int j = gl; j < pn; j += G) if (cat[j] >= 0) utg_ext_forward(e, prev[j], later, R[j]);
+    }
+    __device__ __forceinline__ static void share_bwd(const FmdIndex &e, const FmdIntv *prev, int pn, int sym, UtgExt *R, int gl)
+    {
+        for (int j = gl; j < pn; j += G) utg_ext_backward(e, prev[j], sym, R[j]);
+    }
+    // master side
+    __device__ __forceinline__ void forward(const FmdIndex &e, const FmdIntv *prev, int pn, const i32 *cat, bool later, UtgExt *R) const
+    {
+        if (pn <= 2) { for (int j = 0; j < pn; ++j) if (cat[j] >= 0) utg_ext_forward(e, prev[j], later, R[j]); return; }
+        mb->cmd = UTG_CMD_FWD; mb->pn = pn; mb->arg = later; mb->prev = prev; mb->cat = cat; mb->R = R;
+        __syncwarp(mask);
+        share_fwd(e, prev, pn, cat, later, R, 0);
+        __syncwarp(mask);
+    }
+    __device__ __forceinline__ void backward(const FmdIndex &e, const FmdIntv *prev, int pn, int sym, UtgExt *R) const
+    {
+        if (pn <= 2) { for (int j = 0; j < pn; ++j) utg_ext_backward(e, prev[j], sym, R[j]); return; }
+        mb->cmd = UTG_CMD_BWD; mb->pn = pn; mb->arg = sym; mb->prev = prev; mb->cat = nullptr; mb->R = R;
+        __syncwarp(mask);
+        share_bwd(e, prev, pn, sym, R, 0);
+        __syncwarp(mask);
+    }
+    // helper side: serve commands until the master posts EXIT
+    __device__ __forceinline__ void serve(const FmdIndex &e) const
+    {
+        for (;;) {
+            __syncwarp(mask);
+            int cmd = mb->cmd;
+            if (cmd == UTG_CMD_EXIT) break;
+            const FmdIntv *prev = mb->prev; int pn = mb->pn, arg = mb->arg; UtgExt *R = mb->R;
+            if (cmd == UTG_CMD_FWD) share_fwd(e, prev, pn, mb->cat, arg != 0, R, gl);
+            else share_bwd(e, prev, pn, arg, R, gl);
+            __syncwarp(mask);
+        }
+    }
+};
+
+template <int G>
+__global__ void __launch_bounds__(128) k_utg_nodes_group(const __grid_constant__ UtgArgs A)
+{
+    __shared__ UtgMailbox mbox[128 / G];
+    const int lane = threadIdx.x & 31, gl = lane % G, gib = threadIdx.x / G;
+    UtgGroupCoop<G> coop;
+    coop.mb = &mbox[gib]; coop.gl = gl;
+    coop.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
+    if (gl != 0) { coop.serve(A.e); return; }
+    const u64 group_id = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    UtgScratch S;
+    utg_scratch_bind(S, A.scratch + group_id * A.stride, A.cap, A.s_cap, A.tmark_cap, true);
+    const u64 n = A.todo ? A.n_todo : A.e.n_str;
+    for (;;) {
+        u64 t = atomicAdd(A.ctr, 1ull);
+        if (t >= n) break;
+        u64 x = A.todo ? (u64)A.todo[t] : t;
+        UtgNode N;
+        utg_node(A.e, A.min_match, x, S, N, coop);
+        utg_emit_node(A, x, S, N);
+    }
+    mbox[gib].cmd = UTG_CMD_EXIT;
+    __syncwarp(coop.mask);
 }
 
 __global__ void __launch_bounds__(256) k_fmd_rank(FmdIndex e, i64 n, const u64 *q, u64 *ranks, i32 *sym)
@@ -522,14 +606,19 @@ static void utg_nodes_on_device(FmlEngine &E, const FmdDevice &F, int min_match,
         A.seq_cap = seq_cap; A.nei_cap = nei_cap; A.mark_cap = mark_cap; A.ctr = ctr;
         A.todo = nullptr; A.n_todo = 0;
         A.cap = 2 * maxlen + 64; A.s_cap = 2 * maxlen + 32; A.tmark_cap = 64;
-        A.stride = (utg_scratch_bytes(A.cap, A.s_cap, A.tmark_cap) + 15) & ~(size_t)15;
         const int threads = 128;
-        int blocks = (int)std::min<u64>((n_str + threads - 1) / threads, (u64)E.sm_count * 8);
-        E.d_scratch.reserve((size_t)blocks * threads * A.stride);
+        // few strings (window-sized assemblies): 8 lanes per string cut the latency of a string ~4x; many strings: one thread
+        // per string keeps 10x more of them in flight
+        static const int utg_group = getenv("B200_UTG_GROUP") ? atoi(getenv("B200_UTG_GROUP")) : 0;     // 0: by size
+        const bool group = utg_group ? utg_group == 8 : n_str * 8 <= (u64)E.sm_count * 4 * threads * 2;
+        A.stride = (utg_scratch_bytes(A.cap, A.s_cap, A.tmark_cap, group) + 15) & ~(size_t)15;
+        const int gsz = group ? 8 : 1;
+        int blocks = (int)std::min<u64>((n_str * gsz + threads - 1) / threads, (u64)E.sm_count * 8);
+        E.d_scratch.reserve((size_t)blocks * (threads / gsz) * A.stride);          // one slot per thread / per group
         A.scratch = E.d_scratch.as<u8>();
         CU_CHECK(cudaMemsetAsync(ctr, 0, 64, st));
-        static const int utg_minb = getenv("B200_UTG_MINB") ? atoi(getenv("B200_UTG_MINB")) : 5;
-        if (utg_minb >= 8) k_utg_nodes<8><<<blocks, threads, 0, st>>>(A); else k_utg_nodes<5><<<blocks, threads, 0, st>>>(A);
+        if (group) k_utg_nodes_group<8><<<blocks, threads, 0, st>>>(A);
+        else k_utg_nodes<5><<<blocks, threads, 0, st>>>(A);
         ++nl;
         unsigned long long c[8];
         CU_CHECK(cudaMemcpyAsync(c, ctr, 64, cudaMemcpyDeviceToHost, st));

@@ -42,7 +42,19 @@ struct UtgNode {             // 128 bytes = two cache lines: the host walk touch
 
 enum { UTG_DUP = 1, UTG_CONTAINED = 2, UTG_SHORT = 4, UTG_NO_OVLP = 8, UTG_OVERFLOW = 16 };
 
+// What the forward (fm6_get_nei) or backward (check_left_simple) extension of ONE interval yields.  The extensions of all
+// intervals of a round are independent of each other; the two-phase variants below compute them first (one thread, or the
+// lanes of a group: the Coop policies) and then consume them in interval order with the reference's sequential logic.
+struct UtgExt {
+    u64 c0[3];               // ok[0] (x0, x1, x2)
+    u64 s0[3];               // rld_extend0(ok[0]) when has0
+    u64 ch[4][3];            // ok[1..4]; check_left_simple: ch[0] = ok[s[i]]
+    u32 has0;                // ok[0].x[2] != 0 in a round after the first: s0 is valid
+    u32 child;               // bit c-1: ok[c].x[2] != 0 and its sentinel extension is non-empty
+};
+
 struct UtgScratch {
+    UtgExt *ext;                                  // cap entries, or null (one-phase code only)
     FmdIntv *a[2], *nei; i32 *cat; int cap;      // interval vectors (prev / curr / neighbours) and the category array
     int n[2], n_nei;
     u8 *s, *str; int s_cap;                      // the growing unitig string and check_left's reversed copy
@@ -50,15 +62,18 @@ struct UtgScratch {
     bool overflow;
 };
 
-HD size_t utg_scratch_bytes(int cap, int s_cap, int mark_cap)
+HD size_t utg_scratch_bytes(int cap, int s_cap, int mark_cap, bool with_ext = false)
 {
-    return (size_t)cap * (3 * sizeof(FmdIntv) + sizeof(i32)) + (size_t)mark_cap * sizeof(UtgMark) + 2 * (size_t)((s_cap + 15) & ~15) + 64;
+    return (size_t)cap * (3 * sizeof(FmdIntv) + sizeof(i32) + (with_ext ? sizeof(UtgExt) : 0)) + (size_t)mark_cap * sizeof(UtgMark)
+         + 2 * (size_t)((s_cap + 15) & ~15) + 64;
 }
 
-HD void utg_scratch_bind(UtgScratch &S, u8 *p, int cap, int s_cap, int mark_cap)
+HD void utg_scratch_bind(UtgScratch &S, u8 *p, int cap, int s_cap, int mark_cap, bool with_ext = false)
 {
     S.a[0] = (FmdIntv *)p; S.a[1] = S.a[0] + cap; S.nei = S.a[1] + cap;
     p += (size_t)cap * 3 * sizeof(FmdIntv);
+    S.ext = nullptr;
+    if (with_ext) { S.ext = (UtgExt *)p; p += (size_t)cap * sizeof(UtgExt); }
     S.mark = (UtgMark *)p; p += (size_t)mark_cap * sizeof(UtgMark);
     S.cat = (i32 *)p; p += (size_t)cap * sizeof(i32);
     p = (u8 *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
@@ -148,9 +163,56 @@ HD FmdIntv utg_overlap_intv(const FmdIndex &e, int len, const u8 *seq, int min, 
 
 struct UtgInfoLess { HD bool operator()(const FmdIntv &a, const FmdIntv &b) const { return a.info < b.info; } };
 
+// forward extension of one interval as fm6_get_nei consumes it (fermi-lite/unitig.c:162-186)
+HD void utg_ext_forward(const FmdIndex &e, const FmdIntv &p, bool later_round, UtgExt &R)
+{
+    FmdIntv ok[6], ok0;
+    fmd_extend(e, p, ok, 0);
+    R.c0[0] = ok[0].x[0]; R.c0[1] = ok[0].x[1]; R.c0[2] = ok[0].x[2];
+    R.has0 = 0; R.child = 0;
+    if (ok[0].x[2] && later_round) {
+        fmd_extend0(e, ok[0], ok0, 1);
+        R.s0[0] = ok0.x[0]; R.s0[1] = ok0.x[1]; R.s0[2] = ok0.x[2];
+        R.has0 = 1;
+    }
+    for (int c = 1; c < 5; ++c) {
+        R.ch[c - 1][0] = ok[c].x[0]; R.ch[c - 1][1] = ok[c].x[1]; R.ch[c - 1][2] = ok[c].x[2];
+        if (ok[c].x[2]) {
+            fmd_extend0(e, ok[c], ok0, 1);
+            if (ok0.x[2]) R.child |= 1u << (c - 1);
+        }
+    }
+}
+
+// backward extension of one interval as check_left_simple consumes it (fermi-lite/unitig.c:241-247)
+HD void utg_ext_backward(const FmdIndex &e, const FmdIntv &p, int sym, UtgExt &R)
+{
+    FmdIntv ok[6];
+    fmd_extend(e, p, ok, 1);
+    R.c0[0] = ok[0].x[0]; R.c0[1] = ok[0].x[1]; R.c0[2] = ok[0].x[2];
+    R.ch[0][0] = ok[sym].x[0]; R.ch[0][1] = ok[sym].x[1]; R.ch[0][2] = ok[sym].x[2];
+}
+
+// Coop policies.  UtgNoCoop: the reference-shaped one-phase loops (one thread per string, large inputs).  UtgScalarCoop: the
+// two-phase loops with one thread doing every extension itself (host emulation of the logic the group kernel runs).  The
+// device's group policy (fml.cu) shares the extensions of a round out over the lanes of a group.
+struct UtgNoCoop { static constexpr bool kTwoPhase = false; };
+struct UtgScalarCoop {
+    static constexpr bool kTwoPhase = true;
+    HD void forward(const FmdIndex &e, const FmdIntv *prev, int pn, const i32 *cat, bool later_round, UtgExt *R) const
+    {
+        for (int j = 0; j < pn; ++j) if (cat[j] >= 0) utg_ext_forward(e, prev[j], later_round, R[j]);
+    }
+    HD void backward(const FmdIndex &e, const FmdIntv *prev, int pn, int sym, UtgExt *R) const
+    {
+        for (int j = 0; j < pn; ++j) utg_ext_backward(e, prev[j], sym, R[j]);
+    }
+};
+
 // fm6_get_nei with `used` always present (marks recorded in S.mark).  s / l: the string, extended in place.
 // prev = S.a[0] on entry (may be pre-filled).  Returns rbeg or -1.
-HD int utg_get_nei(const FmdIndex &e, int min_match, int beg, u8 *s, int &l, UtgScratch &S)
+template <class Coop>
+HD int utg_get_nei(const FmdIndex &e, int min_match, int beg, u8 *s, int &l, UtgScratch &S, const Coop &coop)
 {
     int ori_l = l, j, i, c, rbeg, is_forked = 0;
     int pi = 0, ci = 1;              // indices of prev / curr in S.a
@@ -166,6 +228,36 @@ HD int utg_get_nei(const FmdIndex &e, int min_match, int beg, u8 *s, int &l, Utg
     while (S.n[pi]) {
         FmdIntv *prev = S.a[pi], *curr = S.a[ci];
         int pn = S.n[pi], cn = 0;
+        if constexpr (Coop::kTwoPhase) {
+        coop.forward(e, prev, pn, S.cat, ori_l != l, S.ext);        // every extension this round can need
+        for (j = 0; j < pn; ++j) {
+            FmdIntv *p = &prev[j];
+            if (S.cat[j] < 0) continue;
+            const UtgExt &R = S.ext[j];
+            if (R.has0) {                       // ok[0].x[2] && ori_l != l
+                ok0.x[0] = R.s0[0]; ok0.x[1] = R.s0[1]; ok0.x[2] = R.s0[2];
+                if (ok0.x[2]) {
+                    if (R.c0[2] == p->x[2] && p->x[2] == ok0.x[2]) {
+                        int cat0 = S.cat[j];
+                        ok0.info = (u64)(i64)(ori_l - (i64)(p->info & 0xffffffffu));
+                        for (i = j; i < pn && S.cat[i] == cat0; ++i) S.cat[i] = -1;
+                        if (S.n_nei >= S.cap) { S.overflow = true; return -1; }
+                        S.nei[S.n_nei++] = ok0;
+                        continue;
+                    } else utg_mark(S, ok0);
+                }
+            }
+            if (S.cat[j] < 0) continue;
+            for (c = 1; c < 5; ++c)
+                if (R.child >> (c - 1) & 1) {
+                    FmdIntv t;
+                    t.x[0] = R.ch[c - 1][0]; t.x[1] = R.ch[c - 1][1]; t.x[2] = R.ch[c - 1][2];
+                    t.info = (p->info & 0xfffffff0ffffffffull) | (u64)c << 32;
+                    if (cn >= S.cap) { S.overflow = true; return -1; }
+                    curr[cn++] = t;
+                }
+        }
+        } else {
         for (j = 0; j < pn; ++j) {
             FmdIntv *p = &prev[j];
             if (S.cat[j] < 0) continue;
@@ -193,6 +285,7 @@ HD int utg_get_nei(const FmdIndex &e, int min_match, int beg, u8 *s, int &l, Utg
                         curr[cn++] = ok[c];
                     }
                 }
+        }
         }
         S.n[ci] = cn;
         if (cn) {
@@ -240,7 +333,8 @@ HD int utg_get_nei(const FmdIndex &e, int min_match, int beg, u8 *s, int &l, Utg
 }
 
 // check_left_simple
-HD int utg_check_left_simple(const FmdIndex &e, int min_match, int beg, int rbeg, const u8 *s, int l, UtgScratch &S)
+template <class Coop>
+HD int utg_check_left_simple(const FmdIndex &e, int min_match, int beg, int rbeg, const u8 *s, int l, UtgScratch &S, const Coop &coop)
 {
     FmdIntv ok[6];
     int pi = 0, ci = 1, i, j;
@@ -249,12 +343,24 @@ HD int utg_check_left_simple(const FmdIndex &e, int min_match, int beg, int rbeg
     for (i = rbeg - 1; i >= beg; --i) {
         FmdIntv *prev = S.a[pi], *curr = S.a[ci];
         int cn = 0;
+        if constexpr (Coop::kTwoPhase) {
+        coop.backward(e, prev, S.n[pi], (int)s[i], S.ext);
+        for (j = 0; j < S.n[pi]; ++j) {
+            FmdIntv *p = &prev[j];
+            const UtgExt &R = S.ext[j];
+            if (R.c0[2]) { FmdIntv t; t.x[0] = R.c0[0]; t.x[1] = R.c0[1]; t.x[2] = R.c0[2]; t.info = 0; utg_mark(S, t); }
+            if (R.c0[2] + R.ch[0][2] != p->x[2]) { S.n[ci] = cn; return -1; }
+            FmdIntv t; t.x[0] = R.ch[0][0]; t.x[1] = R.ch[0][1]; t.x[2] = R.ch[0][2]; t.info = 0;
+            curr[cn++] = t;
+        }
+        } else {
         for (j = 0; j < S.n[pi]; ++j) {
             FmdIntv *p = &prev[j];
             fmd_extend(e, *p, ok, 1);
             if (ok[0].x[2]) utg_mark(S, ok[0]);
             if (ok[0].x[2] + ok[(int)s[i]].x[2] != p->x[2]) { S.n[ci] = cn; return -1; }
             curr[cn++] = ok[(int)s[i]];
+        }
         }
         S.n[ci] = cn;
         int t = ci; ci = pi; pi = t;
@@ -263,11 +369,12 @@ HD int utg_check_left_simple(const FmdIndex &e, int min_match, int beg, int rbeg
 }
 
 // check_left; the caller has exactly one neighbour in S.nei[0]
-HD int utg_check_left(const FmdIndex &e, int min_match, int beg, int rbeg, const u8 *s, int l, UtgScratch &S)
+template <class Coop>
+HD int utg_check_left(const FmdIndex &e, int min_match, int beg, int rbeg, const u8 *s, int l, UtgScratch &S, const Coop &coop)
 {
     int i, ret;
     FmdIntv tmp;
-    ret = utg_check_left_simple(e, min_match, beg, rbeg, s, l, S);
+    ret = utg_check_left_simple(e, min_match, beg, rbeg, s, l, S, coop);
     if (S.overflow) return -1;
     if (ret == 0) return 0;
     tmp = S.nei[0];
@@ -275,7 +382,7 @@ HD int utg_check_left(const FmdIndex &e, int min_match, int beg, int rbeg, const
     int sl = 0;
     if (l - rbeg + 1 > S.s_cap) { S.overflow = true; return -1; }
     for (i = l - 1; i >= rbeg; --i) S.str[sl++] = (u8)fmd_comp(s[i]);
-    utg_get_nei(e, min_match, 0, S.str, sl, S);
+    utg_get_nei(e, min_match, 0, S.str, sl, S, coop);
     if (S.overflow) return -1;
     ret = S.n_nei > 1 ? -1 : 0;
     S.n_nei = 1; S.nei[0] = tmp;
@@ -284,7 +391,8 @@ HD int utg_check_left(const FmdIndex &e, int min_match, int beg, int rbeg, const
 
 // Everything unitig1 / unitig_unidir can ask the index about string x.  seq_out (>= 2 * longest read + 2 bytes) receives
 // the string followed by the appended bases; nei_out / mark_out are the thread's staging areas (S.nei / S.mark).
-HD void utg_node(const FmdIndex &e, int min_match, u64 x, UtgScratch &S, UtgNode &N)
+template <class Coop>
+HD void utg_node(const FmdIndex &e, int min_match, u64 x, UtgScratch &S, UtgNode &N, const Coop &coop)
 {
     FmdIntv intv0;
     int contained = 0, l = 0;
@@ -308,7 +416,7 @@ HD void utg_node(const FmdIndex &e, int min_match, u64 x, UtgScratch &S, UtgNode
     if (l <= min_match) { N.flags |= UTG_SHORT; return; }
     // fm6_is_contained only pre-computes the overlap list (its verdict is not used by unitig1): utg_retrieve has left that
     // list in S.a[0].  An empty list means "no overlap" (fm6_get_nei would rebuild the same empty list and return -1).
-    int rbeg = S.n[0] ? utg_get_nei(e, min_match, 0, S.s, l, S) : -1;
+    int rbeg = S.n[0] ? utg_get_nei(e, min_match, 0, S.s, l, S, coop) : -1;
     if (S.overflow) { N.flags |= UTG_OVERFLOW; return; }
     N.n_mark_r = S.n_mark;
     N.rbeg = rbeg; N.n_nei = rbeg < 0 ? 0 : S.n_nei;
@@ -317,7 +425,7 @@ HD void utg_node(const FmdIndex &e, int min_match, u64 x, UtgScratch &S, UtgNode
     if (N.n_nei >= 1) { N.nei0.x0 = S.nei[0].x[0]; N.nei0.x1 = S.nei[0].x[1]; N.nei0.x2 = S.nei[0].x[2]; N.nei0.ovlp = (i64)S.nei[0].info; }
     for (int a = 0; a < 8; ++a) N.ext8[a] = a < N.ext_len ? S.s[N.len + a] : (u8)0;
     if (N.n_nei == 1) {
-        N.cl = utg_check_left(e, min_match, 0, rbeg, S.s, l, S);
+        N.cl = utg_check_left(e, min_match, 0, rbeg, S.s, l, S, coop);
         if (S.overflow) { N.flags |= UTG_OVERFLOW; return; }
         N.n_mark_c = S.n_mark - N.n_mark_r;
     }

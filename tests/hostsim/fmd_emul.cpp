@@ -60,16 +60,17 @@ char *fmd_emul_mag_text(const uint8_t *bwt, uint64_t n, const b200_fml_opt_t *op
 {
     HostFmd F; F.build(bwt, n);
     const int cap = 4096, s_cap = 1 << 16, mark_cap = 4096;
-    std::vector<u8> scratch(utg_scratch_bytes(cap, s_cap, mark_cap) + 16);
+    const bool two_phase = getenv("FMD_EMUL_TWO_PHASE") != nullptr;      // the loops the device's group kernel runs
+    std::vector<u8> scratch(utg_scratch_bytes(cap, s_cap, mark_cap, two_phase) + 16);
     u8 *sp = (u8 *)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15);
     UtgScratch S;
-    utg_scratch_bind(S, sp, cap, s_cap, mark_cap);
+    utg_scratch_bind(S, sp, cap, s_cap, mark_cap, two_phase);
     std::vector<UtgNode> node(F.idx.n_str);
     std::vector<u8> seq; std::vector<UtgNei> nei; std::vector<UtgMark> mark;
     int64_t st[4] = {0, 0, 0, 0};
     for (u64 x = 0; x < F.idx.n_str; ++x) {
         UtgNode &N = node[x];
-        utg_node(F.idx, opt->min_asm_ovlp, x, S, N);
+        if (two_phase) utg_node(F.idx, opt->min_asm_ovlp, x, S, N, UtgScalarCoop()); else utg_node(F.idx, opt->min_asm_ovlp, x, S, N, UtgNoCoop());
         N.seq_off = seq.size(); N.nei_off = nei.size(); N.mark_off = mark.size();
         seq.insert(seq.end(), S.s, S.s + N.len + N.ext_len);
         for (int i = 0; i < N.n_nei; ++i) nei.push_back(UtgNei{S.nei[i].x[0], S.nei[i].x[1], S.nei[i].x[2], (i64)S.nei[i].info});

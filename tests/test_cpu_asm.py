@@ -44,10 +44,16 @@ def test_bwt_model_matches_reference_digest():
     assert np.array_equal(rb, fmdmodel.bwt(reads))
 
 
+@pytest.mark.parametrize("two_phase", [False, True])
 @pytest.mark.parametrize("name", fmlcases.FML_SETS)
-def test_rank_graph_and_cleaning_on_cpu_vs_golden(name):
+def test_rank_graph_and_cleaning_on_cpu_vs_golden(name, two_phase, monkeypatch):
     """Over the reference's BWT of the filtered reads: rld_rank1a answers, the graph out of fml_fmi2mag, and the graph after
     fml_mag_clean are identical, as mag_g_print text, to the committed reference output."""
+    # two_phase: the extension-then-consume loops the lane-cooperative kernel runs (one thread standing in for the group)
+    if two_phase:
+        monkeypatch.setenv("FMD_EMUL_TWO_PHASE", "1")
+    else:
+        monkeypatch.delenv("FMD_EMUL_TWO_PHASE", raising=False)
     seqs, quals, off, z = fmlcases.load(name)
     gold = fmlcases.load_asm(name)
     fs, foff = fmlcases.filtered_reads(z, off)
