@@ -9,6 +9,7 @@
 #include <vector>
 #include <string>
 #include "../../seqlib_b200/csrc/pipeline.cuh"
+#include "../../seqlib_b200/csrc/extend_lane.cuh"
 #include "hostindex.h"
 
 using namespace b200;
@@ -72,6 +73,8 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
     B.pool.cap[POOL_REG] = p_reg.size(); B.pool.cap[POOL_HIT] = p_hit.size(); B.pool.cap[POOL_CIGAR] = p_cig.size(); B.pool.cap[POOL_MD] = p_md.size();
     bool dbg = getenv("HOSTSIM_DEBUG") != 0;
     int seed_v2 = getenv("HOSTSIM_SEED_V2") ? atoi(getenv("HOSTSIM_SEED_V2")) : 0;   // list capacity of the seed2.cuh machine, 0 = seed_fsm
+    bool ext_lane = getenv("HOSTSIM_EXTEND_LANE") && lane_extend_eligible(opt, maxlen);   // the one-lane-per-read machine of extend_lane.cuh
+    std::vector<u32> lane_cols((size_t)maxlen + 2 * LANE_U + 2), lane_q((size_t)maxlen / 8 + 8);
     std::vector<std::vector<Reg> > raws(n);
     for (int64_t r = 0; r < n; ++r) {
         for (int pass = 0; pass < 2; ++pass) {
@@ -83,7 +86,10 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
             if (seed_v2) stage_seed_v2(ix, opt, c, B, r, s1.data(), ctr, seed_v2);
             else stage_seed(ix, opt, c, B, r, s1.data(), ctr);
             stage_chain(ix, opt, c, B, r, s2.data(), ctr, logtab.data(), (int)logtab.size());
-            stage_extend(ix, opt, c, B, r, s3.data(), ctr);
+            if (ext_lane) {
+                std::vector<u8> s3l(extend_lane_scratch_bytes(c) + 64);
+                stage_extend_lane_host(ix, opt, c, B, r, s3l.data(), lane_cols.data(), lane_q.data(), ctr);
+            } else stage_extend(ix, opt, c, B, r, s3.data(), ctr);
             raws[r].assign(B.pool.regs + rec[r].reg_off, B.pool.regs + rec[r].reg_off + rec[r].n_regs);
             stage_finalize(ix, opt, c, B, r, s4.data(), logtab.data(), (int)logtab.size(), ctr);
             if (ovf[r] && pass == 0) { R->ovf[r] = ovf[r]; continue; }
