@@ -379,6 +379,45 @@ typedef struct b200_fml_stats {
 } b200_fml_stats_t;
 int b200_fml_last_stats(b200_fml_stats_t *out);
 
+/* ------------------------------------------------------------------ */
+/* FASTA/FASTQ ingest                            */
+/* replaces FastqReader::Open / GetNextSequence                        */
+/* (src/FastqReader.cpp:8-59) = kseq_read over gzread                  */
+/* (bwa/kseq.h:176-226): same records, same name/comment split, same   */
+/* multi-line, blank-line, CR and truncation behaviour.                */
+/* ------------------------------------------------------------------ */
+typedef struct b200_fastq b200_fastq_t;
+/* One batch of records in the flat layout b200_mem_align_batch() takes:
+ * field f of record i = f[f_off[i], f_off[i+1]).  The buffers belong to the reader
+ * and stay valid until its next b200_fastq_next_batch / b200_fastq_close. */
+typedef struct b200_fastq_batch {
+    int64_t n;                                   /* records in this batch                                   */
+    const char *seq;     const int64_t *seq_off;
+    const char *qual;    const int64_t *qual_off;    /* empty for FASTA records                          */
+    const char *name;    const int64_t *name_off;
+    const char *comment; const int64_t *comment_off;
+    int32_t status;      /* 0: more may follow; 1: end of input; -2: kseq's "truncated quality" (-2) ended the stream */
+    int32_t parsed_on_device;                    /* 1 if the batch came from the GPU line parser            */
+    const uint8_t *has;  /* per record: bit 0 = kseq's comment string exists, bit 1 = its quality string exists, after this
+                          * record -- FastqReader::GetNextSequence only assigns Com / Qual then (src/FastqReader.cpp:49-56) */
+} b200_fastq_batch_t;
+/* path "-" = stdin, like the reference; gzip or plain.  B200_ERR_IO if the file cannot be opened. */
+int b200_fastq_open(const char *path, b200_fastq_t **out);
+/* an in-memory (already decompressed) FASTA/FASTQ text; the text is not copied and must outlive the reader */
+int b200_fastq_open_mem(const char *text, int64_t len, b200_fastq_t **out);
+/* up to max_records records (FastqReader::GetNextSequence x max_records) */
+int b200_fastq_next_batch(b200_fastq_t *r, int64_t max_records, b200_fastq_batch_t *out);
+void b200_fastq_close(b200_fastq_t *r);
+/* FastqReader::GetNextSequence assigns Com / Qual only once kseq has allocated those strings (src/FastqReader.cpp:49-56):
+ * bit 0 = a comment has been read, bit 1 = a '+' line has been seen, as of the last record returned. */
+int b200_fastq_buffers_seen(const b200_fastq_t *r);
+/* Strict four-line FASTQ text parsed on the device: newline positions by a stream compaction, one thread per record for
+ * the '@' / '+' / length checks and the name/comment split, bases gathered into the contiguous layout above.  Gives exactly
+ * what b200_fastq_next_batch gives on such text; returns B200_ERR_ARG (and no batch) if the text is not strict four-line
+ * FASTQ (multi-line records, FASTA, blank lines, truncated last record) -- the caller then uses the stream parser.
+ * `text` is a host buffer (pinned or not); copies are inside the call.  Buffers in *out are owned by the reader. */
+int b200_fastq_parse_device(b200_fastq_t *r, const char *text, int64_t len, b200_fastq_batch_t *out);
+
 /* Device selection for multi-GPU processes (one process per GPU). */
 int b200_set_device(int ordinal);
 int b200_device_count(void);
