@@ -380,6 +380,22 @@ typedef struct b200_fml_stats {
 int b200_fml_last_stats(b200_fml_stats_t *out);
 
 /* ------------------------------------------------------------------ */
+/* SAM text of single-end reads                  */
+/* replaces mem_reg2sam (bwa/bwamem.c:1034-1086) = mem_gen_alt        */
+/* (bwa/bwamem_extra.c:125-173) + mem_aln2sam (bwa/bwamem.c:851-976)  */
+/* ------------------------------------------------------------------ */
+/* One SAM record per reported alignment of every read of `view` (b200_results_view), rnames[rid] = contig names, reads in order, exactly the text bwa's mem_reg2sam puts
+ * in bseq1_t.sam for mem_align1's regions (extra_flag 0, no mate): supplementary records hard-clipped unless
+ * MEM_F_SOFTCLIP, MAPQ capped by the primary's, SA / XA (or XB) / pa tags, the unaligned record when nothing reaches opt->T.
+ * seqs/names (and optionally quals/comments) in the flat layout of b200_mem_align_batch / b200_fastq_batch_t; a read
+ * whose quality or comment range is empty prints '*' / nothing.  *sam is malloc'd and NUL-terminated: free() it.
+ * Host-side formatting on all host threads; B200_ERR_LIMIT for MEM_F_REF_HDR (no contig annotations in the index image). */
+int b200_results_to_sam(const b200_results_view_t *view, const b200_mem_opt_t *opt, const char *const *rnames, int n_rnames,
+                        const char *seqs, const int64_t *seq_off, const char *quals, const int64_t *qual_off,
+                        const char *names, const int64_t *name_off, const char *comments, const int64_t *comment_off,
+                        char **sam, int64_t *sam_len);
+
+/* ------------------------------------------------------------------ */
 /* FASTA/FASTQ ingest                            */
 /* replaces FastqReader::Open / GetNextSequence                        */
 /* (src/FastqReader.cpp:8-59) = kseq_read over gzread                  */

@@ -190,3 +190,25 @@ def ksw_extend2_batch(jobs, qpool, tpool, mat, o_del=6, e_del=1, o_ins=6, e_ins=
 
 def srand48(seed):
     lib().refdrv_srand48(seed)
+
+
+def sam(idx, reads, opt, ids, names, quals=None, comments=None):
+    """SAM text of mem_align1 + mem_reg2sam per read (oracle/refdrv_bwa.c refdrv_sam); names/quals/comments: lists of bytes"""
+    seqs, off = pack_reads(reads) if not isinstance(reads, tuple) else reads
+    n = len(off) - 1
+
+    def flat(items):
+        o = np.zeros(len(items) + 1, dtype=np.int64)
+        o[1:] = np.cumsum([len(x) for x in items])
+        return np.frombuffer(b"".join(items) + b"\0", dtype=np.uint8).copy(), o
+    nm, nmo = flat(names)
+    q, qo = flat(quals) if quals is not None else (None, None)
+    c, co = flat(comments) if comments is not None else (None, None)
+    ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+    out = C.c_void_p(); ln = C.c_int64()
+    L = lib()
+    L.refdrv_sam.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 9 + [C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.refdrv_sam(idx.h, C.byref(opt), n, _p(seqs), _p(off), _p(ids_a), _p(nm), _p(nmo), _p(q), _p(qo), _p(c), _p(co), C.byref(out), C.byref(ln))
+    text = C.string_at(out, ln.value)
+    L.refdrv_free(out)
+    return text

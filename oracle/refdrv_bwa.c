@@ -544,3 +544,36 @@ double refdrv_ksw_extend2_batch(int64_t n, const b200_ext_job_t *jobs, const uin
 void refdrv_free(void *p) { free(p); }
 void refdrv_srand48(long seed) { srand48(seed); }
 long refdrv_lrand48(void) { return lrand48(); }
+
+/* SAM text of single-end reads: per read mem_align1 (with the tie-break id made explicit) then mem_reg2sam
+ * (bwa/bwamem.c:1034-1086), i.e. mem_gen_alt (bwa/bwamem_extra.c:125-173) + mem_aln2sam (bwa/bwamem.c:851-976).
+ * quals / comments may be NULL.  *sam is malloc'd (refdrv_free). */
+int refdrv_sam(void *h, const b200_mem_opt_t *o, int64_t n, const char *seqs, const int64_t *off, const int64_t *ids,
+               const char *names, const int64_t *name_off, const char *quals, const int64_t *qual_off,
+               const char *comments, const int64_t *comment_off, char **sam, int64_t *sam_len)
+{
+	refidx_t *r = h;
+	mem_opt_t *opt = opt_from(o);
+	int64_t i, cap = 1 << 16, len = 0;
+	char *out = malloc(cap);
+	for (i = 0; i < n; ++i) {
+		int l = (int)(off[i+1] - off[i]), k;
+		bseq1_t s; memset(&s, 0, sizeof(s));
+		s.l_seq = l;
+		s.seq = malloc(l + 1); memcpy(s.seq, seqs + off[i], l); s.seq[l] = 0;
+		s.name = strndup(names + name_off[i], name_off[i+1] - name_off[i]);
+		if (quals && qual_off[i+1] > qual_off[i]) s.qual = strndup(quals + qual_off[i], qual_off[i+1] - qual_off[i]);
+		if (comments && comment_off[i+1] > comment_off[i]) s.comment = strndup(comments + comment_off[i], comment_off[i+1] - comment_off[i]);
+		mem_alnreg_v ar = mem_align1_core(opt, r->idx->bwt, r->idx->bns, r->idx->pac, l, s.seq, 0); /* converts s.seq to codes in place */
+		mem_mark_primary_se(opt, ar.n, ar.a, ids? ids[i] : lrand48());
+		mem_reg2sam(opt, r->idx->bns, r->idx->pac, &s, &ar, 0, 0);
+		k = strlen(s.sam);
+		if (len + k + 1 > cap) { while (len + k + 1 > cap) cap *= 2; out = realloc(out, cap); }
+		memcpy(out + len, s.sam, k); len += k;
+		free(s.sam); free(s.seq); free(s.name); free(s.qual); free(s.comment); free(ar.a);
+	}
+	out[len] = 0;
+	*sam = out; *sam_len = len;
+	free(opt);
+	return 0;
+}
