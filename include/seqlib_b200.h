@@ -339,6 +339,16 @@ typedef struct b200_utgs b200_utgs_t;
  * an empty set (the reference returns NULL when every read was filtered out). */
 int b200_fml_assemble_flat(const b200_fml_opt_t *opt, int64_t n, const char *seqs, const char *quals,
                            const int64_t *off, b200_utgs_t **out);
+/* Many independent assemblies in one call -- what a caller of FermiAssembler does window after window (one genomic window
+ * per assembler, SeqLib/FermiAssembler.h:25-123): window w owns reads [win_off[w], win_off[w+1]) of the flat pools and gets
+ * exactly the unitigs b200_fml_assemble_flat returns for those reads alone (out[w], each released with b200_utgs_free).
+ * A window-sized assembly is latency bound on a B200 (one string per thread for a few thousand strings), so the windows
+ * run concurrently: n_threads host threads (0 = 4, at most 32), each with its own stream, claim windows from a shared
+ * counter.  Returns the first error any window produced (the other windows still complete).  b200_fml_last_stats()
+ * afterwards holds the stage times summed over the windows. */
+int b200_fml_assemble_windows(const b200_fml_opt_t *opt, int64_t n_windows, const int64_t *win_off,
+                              const char *seqs, const char *quals, const int64_t *off, int n_threads, b200_utgs_t **out);
+
 /* the assembly half alone, as FermiAssembler::DirectAssemble drives it (src/FermiAssembler.cpp:24-39):
  * fml_seq2fmi + fml_fmi2mag + fml_mag_clean(opt as given) + fml_mag2utg on reads taken as they are. */
 int b200_fml_seqs2utg_flat(const b200_fml_opt_t *opt, int64_t n, const char *seqs, const int64_t *off,

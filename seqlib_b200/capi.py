@@ -423,6 +423,24 @@ def fml_assemble_flat(opt, seqs, quals, off):
     return _utgs_out(h)
 
 
+def fml_assemble_windows(opt, seqs, quals, off, win_off, n_threads=0):
+    """b200_fml_assemble_windows: window w = reads [win_off[w], win_off[w+1]); returns one unitig list per window."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    quals = None if quals is None else np.ascontiguousarray(quals, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    win_off = np.ascontiguousarray(win_off, dtype=np.int64)
+    nw = len(win_off) - 1
+    hs = (C.c_void_p * max(nw, 1))()
+    L = lib()
+    L.b200_fml_assemble_windows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    rc = L.b200_fml_assemble_windows(C.byref(opt), nw, _p(win_off), _p(seqs), _p(quals), _p(off), n_threads, hs)
+    outs = []
+    for w in range(nw):
+        outs.append(_utgs_out(C.c_void_p(hs[w])) if hs[w] else None)
+    _check(rc)
+    return outs
+
+
 def fml_seqs2utg_flat(opt, seqs, off):
     seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.int64)

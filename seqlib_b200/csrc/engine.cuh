@@ -1,5 +1,6 @@
 // engine.cuh -- internal declarations shared by engine.cu, index.cu and index_build.cu
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
@@ -29,6 +30,9 @@ struct DevPool {
     std::vector<Blk> free_;
     std::mutex mu;
     size_t pooled = 0, limit = 0;
+    size_t n_malloc = 0, n_free = 0, n_hit = 0, slots = 0;      // B200_POOL_DEBUG=1 prints them at exit
+    ~DevPool() {}
+    void report() const { fprintf(stderr, "[devpool] cudaMalloc %zu, cudaFree %zu, reused %zu, pooled %.1f MB in %zu blocks\n", n_malloc, n_free, n_hit, pooled / 1048576.0, free_.size()); }
     void *get(size_t want, size_t &cap)
     {
         int dev = 0; cudaGetDevice(&dev);
@@ -37,7 +41,8 @@ struct DevPool {
             int best = -1;
             for (size_t i = 0; i < free_.size(); ++i)
                 if (free_[i].dev == dev && free_[i].cap >= want && free_[i].cap <= 2 * want + (1u << 20) && (best < 0 || free_[i].cap < free_[best].cap)) best = (int)i;
-            if (best >= 0) { Blk b = free_[best]; free_.erase(free_.begin() + best); pooled -= b.cap; cap = b.cap; return b.p; }
+            if (best >= 0) { Blk b = free_[best]; free_.erase(free_.begin() + best); pooled -= b.cap; cap = b.cap; ++n_hit; return b.p; }
+            ++n_malloc;
         }
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, want);
@@ -56,7 +61,8 @@ struct DevPool {
         int dev = 0; cudaGetDevice(&dev);
         std::lock_guard<std::mutex> g(mu);
         if (!limit) { const char *e = getenv("B200_DEVPOOL_GB"); limit = (size_t)((e ? atof(e) : 48.0) * (1ull << 30)); if (!limit) limit = 1; }
-        if (cap > limit / 2 || pooled + cap > limit || free_.size() >= 256) { cudaFree(p); return; }
+        if (!slots) { const char *e = getenv("B200_POOL_SLOTS"); slots = e ? (size_t)atol(e) : 4096; if (!slots) slots = 1; }
+        if (cap > limit / 2 || pooled + cap > limit || free_.size() >= slots) { ++n_free; cudaFree(p); return; }
         free_.push_back(Blk{p, cap, dev}); pooled += cap;
     }
     void trim(size_t keep)
@@ -65,7 +71,11 @@ struct DevPool {
         while (!free_.empty() && pooled > keep) { cudaFree(free_.back().p); pooled -= free_.back().cap; free_.pop_back(); }
     }
 };
-inline DevPool &dev_pool() { static DevPool *p = new DevPool(); return *p; }     // never destroyed: outlives static DevBufs
+inline DevPool &dev_pool()
+{
+    static DevPool *p = [] { DevPool *q = new DevPool(); if (getenv("B200_POOL_DEBUG")) atexit([] { dev_pool().report(); }); return q; }();
+    return *p;
+}     // never destroyed: outlives static DevBufs
 
 // A device buffer that grows on demand (never shrinks), backed by the pool.
 struct DevBuf {

@@ -280,7 +280,7 @@ void fmd_build_device(FmdDevice &F, const char *d_seq, const i64 *d_off, const i
     k_fmd_counts<<<nblk(n_blk, 256), 256>>>(cnt.as<Cnt4>(), F.blocks.as<FmdBlock>(), n_blk);
     Cnt4 last;
     CU_CHECK(cudaMemcpy(&last, cnt.as<Cnt4>() + (n_blk - 1), sizeof(Cnt4), cudaMemcpyDeviceToHost));
-    CU_CHECK(cudaDeviceSynchronize());
+    CU_CHECK(cudaStreamSynchronize(0));      // this file is compiled with --default-stream per-thread: 0 = the calling thread's own stream
     CU_CHECK(cudaGetLastError());
     // the spare block is empty, so its running counts are the totals
     u64 tot[6] = {0, last.c[0], last.c[1], last.c[2], last.c[3], 0};

@@ -12,6 +12,11 @@
 #include <cstring>
 #include <cstdlib>
 #include <ctime>
+#include <thread>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
 #include <cub/cub.cuh>
 #include "engine.cuh"
 #include "bfc.cuh"
@@ -367,6 +372,13 @@ struct FmlEngine {
     int sm_count = 0;
     DevBuf d_seq, d_qual, d_off, d_cnt, d_recoff, d_lo[2], d_hi[2], d_flags, d_starts, d_tmp, d_hist, d_len, d_codes, d_scratch, d_ctr, d_todo, d_order[2];
     bool ready = false;
+    ~FmlEngine()        // worker threads of b200_fml_assemble_windows come and go: give the stream and events back
+    {
+        if (!ready) return;
+        cudaStreamDestroy(st);
+        for (auto &e : ev) cudaEventDestroy(e);
+        cudaGetLastError();
+    }
     void init()
     {
         if (ready) return;
@@ -1076,6 +1088,54 @@ int b200_fml_assemble_flat(const b200_fml_opt_t *opt0, int64_t n, const char *se
         g_fml_stats.ms_total = ms_between(E.ev[0], E.ev[3]);
         return (int)B200_OK;
     });
+}
+
+int b200_fml_assemble_windows(const b200_fml_opt_t *opt, int64_t n_windows, const int64_t *win_off,
+                              const char *seqs, const char *quals, const int64_t *off, int n_threads, b200_utgs_t **out)
+{
+    if (!opt || !out || n_windows < 0 || (n_windows > 0 && (!win_off || !off || !seqs))) return fail(B200_ERR_ARG, "b200_fml_assemble_windows: bad arguments");
+    for (int64_t w = 0; w < n_windows; ++w) {
+        out[w] = nullptr;
+        if (win_off[w + 1] < win_off[w]) return fail(B200_ERR_ARG, "b200_fml_assemble_windows: win_off must not decrease");
+    }
+    if (n_windows == 0) return B200_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(B200_ERR_CUDA, "b200_fml_assemble_windows: no CUDA device"); }
+    unsigned nt = n_threads > 0 ? (unsigned)n_threads : 4;      // measured best on a B200 box (scripts/win_probe.py); see DESIGN.md section 6
+    if (nt > 32) nt = 32;
+    if ((int64_t)nt > n_windows) nt = (unsigned)n_windows;
+    std::atomic<int64_t> next(0);
+    std::mutex mu; int first_rc = B200_OK; std::string first_msg;
+    b200_fml_stats_t total; memset(&total, 0, sizeof(total));
+    auto work = [&]() {
+        cudaSetDevice(dev);
+        std::vector<int64_t> loff;
+        for (;;) {
+            int64_t w = next.fetch_add(1);
+            if (w >= n_windows) break;
+            const int64_t r0 = win_off[w], n = win_off[w + 1] - r0;
+            loff.resize((size_t)n + 1);
+            for (int64_t i = 0; i <= n; ++i) loff[(size_t)i] = off[r0 + i] - off[r0];
+            int rc = b200_fml_assemble_flat(opt, n, seqs + off[r0], quals ? quals + off[r0] : nullptr, loff.data(), &out[w]);
+            std::lock_guard<std::mutex> g(mu);
+            if (rc != B200_OK && first_rc == B200_OK) { first_rc = rc; first_msg = b200_last_error(); }
+            total.n_launches += g_fml_stats.n_launches; total.n_utg += g_fml_stats.n_utg; total.n_strings += g_fml_stats.n_strings;
+            total.fmd_symbols += g_fml_stats.fmd_symbols; total.n_lookups += g_fml_stats.n_lookups;
+            // summed over the windows: with concurrent windows the stage times add up to more than the wall time
+            total.ms_count += g_fml_stats.ms_count; total.ms_ec += g_fml_stats.ms_ec; total.ms_flt += g_fml_stats.ms_flt; total.ms_fmd += g_fml_stats.ms_fmd;
+            total.ms_nodes += g_fml_stats.ms_nodes; total.ms_walk_host += g_fml_stats.ms_walk_host; total.ms_clean_host += g_fml_stats.ms_clean_host;
+            total.ms_total += g_fml_stats.ms_total;
+        }
+    };
+    if (nt == 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work);
+        for (auto &x : th) x.join();
+    }
+    g_fml_stats = total;
+    if (first_rc != B200_OK) return fail(first_rc, first_msg.c_str());
+    return B200_OK;
 }
 
 int b200_utgs_view(const b200_utgs_t *u, int *n_utg, const b200_utg_t **utg)

@@ -287,6 +287,9 @@ int b200_set_device(int ordinal)
 {
     cudaError_t e = cudaSetDevice(ordinal);
     if (e != cudaSuccess) return fail(B200_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    // keep the local-memory reservation at its high-water mark: the overlap-record kernels have 1.5 KB stack frames, and
+    // shrinking / regrowing the reservation between launches synchronises the device (concurrent windows would serialise)
+    if (!getenv("B200_NO_LMEM_MAX")) { cudaSetDeviceFlags(cudaDeviceLmemResizeToMax); cudaGetLastError(); }
     return B200_OK;
 }
 

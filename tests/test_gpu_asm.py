@@ -101,6 +101,34 @@ def test_assemble_vs_live_reference(capi):
     assert capi.fml_assemble_flat(capi.fml_default_opt(), np.zeros(0, np.uint8), None, np.zeros(1, np.int64)) == []
 
 
+@pytest.mark.parametrize("n_threads", [1, 6])
+def test_assemble_windows_equals_one_window_at_a_time(capi, n_threads):
+    """b200_fml_assemble_windows: every window gets the unitigs b200_fml_assemble_flat gives for its reads alone (golden sets, an
+    empty window, a window that filters to nothing), whatever the number of host threads / streams."""
+    sets = [fmlcases.load(name) for name in fmlcases.FML_SETS if fmlcases.load(name)[1] is not None]
+    rng = np.random.default_rng(9)
+    junk = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 30 * 100)]
+    wins = []
+    for rep in range(2):
+        for seqs, quals, off, z in sets:
+            wins.append((np.asarray(seqs, dtype=np.uint8), np.asarray(quals, dtype=np.uint8), np.asarray(off, dtype=np.int64)))
+        wins.append((junk, np.full(len(junk), ord("I"), dtype=np.uint8), np.arange(31, dtype=np.int64) * 100))
+        wins.append((np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.int64)))
+    seqs = np.concatenate([w[0] for w in wins]); quals = np.concatenate([w[1] for w in wins])
+    off = [0]; win_off = [0]
+    for s, q, o in wins:
+        base = off[-1]
+        off += [base + int(x) for x in o[1:]]
+        win_off.append(len(off) - 1)
+    opt = capi.fml_default_opt()
+    got = capi.fml_assemble_windows(opt, seqs, quals, np.array(off, dtype=np.int64), np.array(win_off, dtype=np.int64), n_threads)
+    assert len(got) == len(wins)
+    for (s, q, o), g in zip(wins, got):
+        exp = capi.fml_assemble_flat(opt, s, q, o) if len(o) > 1 else []
+        assert fmlcases.utg_text(g) == fmlcases.utg_text(exp)
+    assert capi.fml_last_stats()["n_launches"] >= 0
+
+
 def test_direct_assemble_and_fseq_entry(capi):
     """b200_fml_seqs2utg_flat (FermiAssembler::DirectAssemble's path) and the fseq1_t form b200_fml_assemble."""
     from oracle import pyref_fml
