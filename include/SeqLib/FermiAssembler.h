@@ -34,6 +34,12 @@ public:
     FermiAssembler(const FermiAssembler &) = delete;
     FermiAssembler &operator=(const FermiAssembler &) = delete;
 
+    /** (new) Many windows in one call: windows[w] holds the reads of one genomic window; element w of the result is what
+     *  AddReads(windows[w]) + PerformAssembly() + GetContigs() returns for a FermiAssembler of its own (same options; NULL =
+     *  fml_opt_init).  The windows are assembled concurrently on the device (b200_fml_assemble_windows). */
+    static std::vector<std::vector<std::string> > AssembleWindows(const std::vector<UnalignedSequenceVector> &windows,
+                                                                 const fml_opt_t *opt = 0, int n_threads = 0);
+
     void AddReads(const BamRecordVector &brv);
     void AddReads(const UnalignedSequenceVector &v);
     void AddRead(const UnalignedSequence &r);

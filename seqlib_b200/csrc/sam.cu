@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <functional>
 #include <thread>
 #include <vector>
 #include "../../include/seqlib_b200.h"
@@ -22,18 +23,41 @@ namespace {
 
 enum { F_ALL = 0x8, F_NO_MULTI = 0x10, F_REF_HDR = 0x100, F_SOFTCLIP = 0x200, F_KEEP_SUPP_MAPQ = 0x1000, F_XB = 0x2000 };   // bwa/bwamem.h:40-50
 
+// append-only byte buffer; the hot appends (bases, qualities, numbers) write through a raw pointer after one capacity check
 struct Out {
-    std::string s;
-    void num(long long v) { char b[24]; int n = snprintf(b, sizeof b, "%lld", v); s.append(b, (size_t)n); }
-    void ch(char c) { s.push_back(c); }
-    void str(const char *p) { s.append(p); }
-    void strn(const char *p, size_t n) { s.append(p, n); }
+    char *p = nullptr; size_t n = 0, cap = 0;
+    Out() {}
+    Out(const Out &) = delete;
+    Out &operator=(const Out &) = delete;
+    Out(Out &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    ~Out() { free(p); }
+    void reserve(size_t extra)
+    {
+        if (n + extra <= cap) return;
+        size_t c = cap ? cap : 1024;
+        while (c < n + extra) c += c >> 1;
+        p = (char *)realloc(p, c); cap = c;
+    }
+    char *grow(size_t k) { reserve(k); char *w = p + n; n += k; return w; }
+    void num(long long v)
+    {
+        reserve(24);
+        char b[24]; int k = 0;
+        unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+        do { b[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (v < 0) p[n++] = '-';
+        while (k) p[n++] = b[--k];
+    }
+    void ch(char c) { reserve(1); p[n++] = c; }
+    void strn(const char *q, size_t k) { memcpy(grow(k), q, k); }
+    void str(const char *q) { strn(q, strlen(q)); }
+    bool empty() const { return n == 0; }
 };
 
 struct Aln {            // mem_aln_t (bwa/bwamem.h:115-126) assembled from a b200_hit_t
     const b200_hit_t *h;
     int flag, mapq, sub;
-    const std::string *xa;
+    const Out *xa;
 };
 
 struct Ctx {
@@ -98,14 +122,17 @@ void aln2sam(const Ctx &C, int64_t read, const std::vector<Aln> &list, int which
                 if (last == 4 || last == 3) qb += cg[n_cigar - 1] >> 4;
             }
         }
+        const int len = qe > qb ? qe - qb : 0;
         if (!is_rev) {
-            for (int i = qb; i < qe; ++i) o.ch("ACGTN"[nt4((unsigned char)seq[i])]);
-            o.ch('\t');
-            if (qual) o.strn(qual + qb, (size_t)(qe > qb ? qe - qb : 0)); else o.ch('*');
+            char *w = o.grow((size_t)len + 1);
+            for (int i = qb; i < qe; ++i) *w++ = "ACGTN"[nt4((unsigned char)seq[i])];
+            *w = '\t';
+            if (qual) o.strn(qual + qb, (size_t)len); else o.ch('*');
         } else {
-            for (int i = qe - 1; i >= qb; --i) o.ch("TGCAN"[nt4((unsigned char)seq[i])]);
-            o.ch('\t');
-            if (qual) { for (int i = qe - 1; i >= qb; --i) o.ch(qual[i]); } else o.ch('*');
+            char *w = o.grow((size_t)len + 1);
+            for (int i = qe - 1; i >= qb; --i) *w++ = "TGCAN"[nt4((unsigned char)seq[i])];
+            *w = '\t';
+            if (qual) { char *x = o.grow((size_t)len); for (int i = qe - 1; i >= qb; --i) *x++ = qual[i]; } else o.ch('*');
         }
     }
     if (n_cigar) {
@@ -135,7 +162,7 @@ void aln2sam(const Ctx &C, int64_t read, const std::vector<Aln> &list, int which
         }
         if (p.h && h.alt_sc > 0) { char b[64]; snprintf(b, sizeof b, "\tpa:f:%.3f", (double)h.score / h.alt_sc); o.str(b); }
     }
-    if (p.xa && !p.xa->empty()) { o.str((C.opt->flag & F_XB) ? "\tXB:Z:" : "\tXA:Z:"); o.str(p.xa->c_str()); }
+    if (p.xa && !p.xa->empty()) { o.str((C.opt->flag & F_XB) ? "\tXB:Z:" : "\tXA:Z:"); o.strn(p.xa->p, p.xa->n); }
     if (C.comments && C.comment_off[read + 1] > C.comment_off[read]) {
         o.ch('\t'); o.strn(C.comments + C.comment_off[read], (size_t)(C.comment_off[read + 1] - C.comment_off[read]));
     }
@@ -154,22 +181,23 @@ void read2sam(const Ctx &C, int64_t read, Out &o)
     const b200_mem_opt_t &opt = *C.opt;
     const b200_hit_t *a = C.v.hits + C.v.hit_off[read];
     const int n = (int)(C.v.hit_off[read + 1] - C.v.hit_off[read]);
-    std::vector<std::string> xa;
-    if (!(opt.flag & F_ALL)) {                                   // mem_gen_alt
-        std::vector<int> cnt((size_t)n, 0); std::vector<char> has_alt((size_t)n, 0);
+    std::vector<Out> xa;
+    if (!(opt.flag & F_ALL) && n > 1) {                          // mem_gen_alt (a lone region has no secondary_all >= 0)
         int tot = 0;
-        for (int i = 0; i < n; ++i) {
-            int r = pri_idx(opt.XA_drop_ratio, a, i);
-            if (r >= 0) { ++cnt[(size_t)r]; ++tot; if (a[i].is_alt) has_alt[(size_t)r] = 1; }
-        }
+        for (int i = 0; i < n; ++i) if (pri_idx(opt.XA_drop_ratio, a, i) >= 0) ++tot;
         if (tot) {
+            std::vector<int> cnt((size_t)n, 0); std::vector<char> has_alt((size_t)n, 0);
+            for (int i = 0; i < n; ++i) {
+                int r = pri_idx(opt.XA_drop_ratio, a, i);
+                if (r >= 0) { ++cnt[(size_t)r]; if (a[i].is_alt) has_alt[(size_t)r] = 1; }
+            }
             xa.resize((size_t)n);
             for (int i = 0; i < n; ++i) {
                 int r = pri_idx(opt.XA_drop_ratio, a, i);
                 if (r < 0) continue;
                 if (cnt[(size_t)r] > opt.max_XA_hits_alt || (!has_alt[(size_t)r] && cnt[(size_t)r] > opt.max_XA_hits)) continue;
                 const b200_hit_t &t = a[i];
-                Out s;
+                Out &s = xa[(size_t)r];
                 s.str(C.rnames[t.rid]);
                 s.ch(','); s.ch("+-"[t.is_rev ? 1 : 0]); s.num((long long)t.pos + 1);
                 s.ch(',');
@@ -178,11 +206,11 @@ void read2sam(const Ctx &C, int64_t read, Out &o)
                 s.ch(','); s.num(t.NM);
                 if (opt.flag & F_XB) { s.ch(','); s.num(t.score); s.ch(','); s.num(t.mapq); }
                 s.ch(';');
-                xa[(size_t)r] += s.s;
             }
         }
     }
     std::vector<Aln> aa;
+    aa.reserve((size_t)(n > 0 ? n : 1));
     int l = 0;
     for (int k = 0; k < n; ++k) {
         const b200_hit_t &p = a[k];
@@ -229,23 +257,24 @@ extern "C" int b200_results_to_sam(const b200_results_view_t *view, const b200_m
     if ((int64_t)nt > (n + 4095) / 4096) nt = (unsigned)((n + 4095) / 4096);
     if (nt == 0) nt = 1;
     std::vector<Out> parts(nt);
-    auto work = [&](unsigned t) {
-        int64_t b = n * t / nt, e = n * (t + 1) / nt;
-        parts[t].s.reserve((size_t)(e - b) * 400);
-        for (int64_t i = b; i < e; ++i) read2sam(C, i, parts[t]);
-    };
-    if (nt == 1) work(0);
-    else {
+    auto run = [&](const std::function<void(unsigned)> &f) {
+        if (nt == 1) { f(0); return; }
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(f, t);
         for (auto &x : th) x.join();
-    }
+    };
+    run([&](unsigned t) {
+        int64_t b = n * t / nt, e = n * (t + 1) / nt;
+        int64_t bytes = (C.seq_off[e] - C.seq_off[b]) * 2 + (C.name_off[e] - C.name_off[b]) + (e - b) * 96;
+        parts[t].reserve((size_t)bytes);
+        for (int64_t i = b; i < e; ++i) read2sam(C, i, parts[t]);
+    });
     size_t tot = 0;
-    for (auto &p : parts) tot += p.s.size();
+    std::vector<size_t> at(nt);
+    for (unsigned t = 0; t < nt; ++t) { at[t] = tot; tot += parts[t].n; }
     char *out = (char *)malloc(tot + 1);
     if (!out) { b200::set_error("b200_results_to_sam: out of memory"); return B200_ERR_NOMEM; }
-    size_t at = 0;
-    for (auto &p : parts) { memcpy(out + at, p.s.data(), p.s.size()); at += p.s.size(); }
+    run([&](unsigned t) { if (parts[t].n) memcpy(out + at[t], parts[t].p, parts[t].n); });
     out[tot] = 0;
     *sam = out; *sam_len = (int64_t)tot;
     return 0;

@@ -64,6 +64,50 @@ void FermiAssembler::AddReads(const BamRecordVector &brv)
     for (BamRecordVector::const_iterator r = brv.begin(); r != brv.end(); ++r) push(r->Qname(), r->Sequence(), r->Qualities(), false);
 }
 
+std::vector<std::vector<std::string> > FermiAssembler::AssembleWindows(const std::vector<UnalignedSequenceVector> &windows,
+                                                                      const fml_opt_t *opt_, int n_threads)
+{
+    fml_opt_t o;
+    if (opt_) o = *opt_; else b200_fml_opt_init(&o);
+    std::vector<std::vector<std::string> > out(windows.size());
+    // a window has qualities if any of its reads has a quality string covering the read (push() above); windows with and
+    // without qualities go in two calls because the flat quality pool is all or nothing
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<size_t> which;
+        std::vector<char> seqs, quals;
+        std::vector<int64_t> off(1, 0), win_off(1, 0);
+        for (size_t w = 0; w < windows.size(); ++w) {
+            bool has_q = false;
+            for (size_t i = 0; i < windows[w].size(); ++i)
+                if (!windows[w][i].Seq.empty() && windows[w][i].Qual.size() == windows[w][i].Seq.size()) has_q = true;
+            if ((int)has_q != pass) continue;
+            which.push_back(w);
+            for (size_t i = 0; i < windows[w].size(); ++i) {
+                const UnalignedSequence &r = windows[w][i];
+                seqs.insert(seqs.end(), r.Seq.begin(), r.Seq.end());
+                if (pass) {
+                    if (r.Qual.size() == r.Seq.size()) quals.insert(quals.end(), r.Qual.begin(), r.Qual.end());
+                    else quals.insert(quals.end(), r.Seq.size(), '~');
+                }
+                off.push_back((int64_t)seqs.size());
+            }
+            win_off.push_back((int64_t)off.size() - 1);
+        }
+        if (which.empty()) continue;
+        seqs.push_back(0); quals.push_back(0);
+        std::vector<b200_utgs_t *> h(which.size(), (b200_utgs_t *)0);
+        int rc = b200_fml_assemble_windows(&o, (int64_t)which.size(), win_off.data(), seqs.data(), pass ? quals.data() : 0, off.data(), n_threads, h.data());
+        for (size_t k = 0; k < which.size(); ++k) {
+            if (!h[k]) continue;
+            int n = 0; const b200_utg_t *u = 0;
+            if (b200_utgs_view(h[k], &n, &u) == B200_OK) for (int i = 0; i < n; ++i) out[which[k]].push_back(std::string(u[i].seq));
+            b200_utgs_free(h[k]);
+        }
+        check(rc, "FermiAssembler::AssembleWindows");
+    }
+    return out;
+}
+
 void FermiAssembler::ClearContigs()
 {
     b200_fml_utg_destroy(n_utg, m_utgs);

@@ -40,6 +40,18 @@ int main(int argc, char **argv)
         std::ostringstream gfa;
         f.WriteGFA(gfa);
         CHECK(gfa.str().rfind("H\tVN:Z:1.0", 0) == 0);
+        {   // the same reads as two windows (all / first half) through the batch entry: each equals its own assembler
+            std::vector<UnalignedSequenceVector> wins;
+            wins.push_back(reads);
+            wins.push_back(UnalignedSequenceVector(reads.begin(), reads.begin() + reads.size() / 2));
+            wins.push_back(UnalignedSequenceVector());
+            std::vector<std::vector<std::string> > wc = FermiAssembler::AssembleWindows(wins, 0, 2);
+            CHECK(wc.size() == 3 && wc[0] == c && wc[2].empty());
+            FermiAssembler h;
+            h.AddReads(wins[1]);
+            h.PerformAssembly();
+            CHECK(wc[1] == h.GetContigs());
+        }
         f.ClearContigs();
         CHECK(f.GetContigs().empty());
         f.ClearReads();
