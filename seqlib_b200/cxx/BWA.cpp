@@ -7,6 +7,8 @@
 #include <cstring>
 #include <sstream>
 #include <stdexcept>
+#include <functional>
+#include <memory>
 #include <thread>
 #include <exception>
 #include <algorithm>
@@ -124,18 +126,22 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
     int64_t b0 = v.hit_off[read], b1 = v.hit_off[read + 1];
     int n_regs = (int)(b1 - b0);
     double primaryScore = 0;
-    std::vector<HitRef> hits;
-    hits.reserve(n_regs);
+    HitRef small[8];                                     // nearly every read has one or two regions: no heap traffic for those
+    std::vector<HitRef> big;
+    HitRef *hits = small;
+    if (n_regs > 8) { big.resize((size_t)n_regs); hits = big.data(); }
+    size_t n_hits = 0;
     for (int64_t i = b0; i < b1; ++i) {
         const b200_hit_t &r = v.hits[i];
         // Q1: tests the int `secondary` (-1 = primary is non-zero too)
         if (r.secondary && (keepSecFrac < 0.0 || keepSecFrac > 1.0)) continue;
-        HitRef h; h.h = &r; hits.push_back(h);
+        hits[n_hits++].h = &r;
     }
-    std::sort(hits.begin(), hits.end(), aln_sort);
-    if (primary_first)            // legacy BWAWrapper ordering: primaries ahead of secondaries, otherwise as sorted
-        std::stable_partition(hits.begin(), hits.end(), [](const HitRef &x) { return !(x.h->flag & BAM_FSECONDARY); });
-    for (size_t i = 0; i < hits.size(); ++i) {
+    if (n_hits > 1) std::sort(hits, hits + n_hits, aln_sort);
+    if (primary_first && n_hits > 1)   // legacy BWAWrapper ordering: primaries ahead of secondaries, otherwise as sorted
+        std::stable_partition(hits, hits + n_hits, [](const HitRef &x) { return !(x.h->flag & BAM_FSECONDARY); });
+    out.reserve(out.size() + n_hits);
+    for (size_t i = 0; i < n_hits; ++i) {
         const b200_hit_t &h = *hits[i].h;
         bool isSec = (h.flag & BAM_FSECONDARY);
         bool tooLow = isSec && (primaryScore * keepSecFrac > h.score);
@@ -148,7 +154,8 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
         b->core.n_cigar = (uint32_t)h.n_cigar; b->core.mtid = -1; b->core.mpos = -1; b->core.isize = 0;
         if (h.is_rev) b->core.flag |= BAM_FREVERSE;
         const uint32_t *cig = v.cigar + h.cigar_off;
-        std::string clipped = seq;
+        const char *clipped = seq.data();                               // the bases that go into the record (no copy)
+        size_t clipped_len = seq.size();
         if (hardclip) {                                                  // Q6
             size_t tstart = 0, clen = 0;
             for (int c = 0; c < h.n_cigar; ++c) {
@@ -156,14 +163,20 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
                 if (c == 0 && op == BAM_CREF_SKIP) tstart = bam_cigar_oplen(cig[c]);
                 else if (bam_cigar_type(op) & 1) clen += bam_cigar_oplen(cig[c]);
             }
-            clipped = seq.substr(tstart, clen);
+            if (tstart > seq.size()) throw std::out_of_range("basic_string::substr");   // what seq.substr(tstart, clen) does
+            clipped = seq.data() + tstart;
+            clipped_len = std::min(clen, seq.size() - tstart);
         }
         b->core.l_qname = (uint16_t)(name.size() + 1);
-        b->core.l_qseq = (int32_t)clipped.size();
+        b->core.l_qseq = (int32_t)clipped_len;
         b->l_data = b->core.l_qname + (h.n_cigar << 2) + ((b->core.l_qseq + 1) >> 1) + b->core.l_qseq;
-        b->data = (uint8_t *)std::malloc(b->l_data ? b->l_data : 1);
-        if (!b->data) throw std::bad_alloc();
-        b->m_data = (uint32_t)b->l_data;
+        {   // room for the three integer tags appended below (3 x 7 bytes), rounded like bam_aux_append's kroundup32 would
+            // leave it after the third append: one allocation instead of four
+            size_t m = (size_t)b->l_data + 21; --m; m |= m >> 1; m |= m >> 2; m |= m >> 4; m |= m >> 8; m |= m >> 16; ++m;
+            b->data = (uint8_t *)std::malloc(m);
+            if (!b->data) throw std::bad_alloc();
+            b->m_data = (uint32_t)m;
+        }
         std::memset(b->data, 0, b->l_data);
         std::memcpy(b->data, name.c_str(), name.size() + 1);
         uint32_t *dst = bam_get_cigar(b);
@@ -174,23 +187,29 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
             std::memcpy((uint8_t *)dst + 4 * k, &c, 4);
         }
         uint8_t *sb = bam_get_seq(b);
-        int sl = (int)clipped.size();
-        if (h.is_rev) {
+        int sl = (int)clipped_len;
+        {   // 4-bit codes, two bases per byte, high nibble first.  Reverse strand: Q11 -- src/BWAAligner.cpp:213-218 maps A->T
+            // and T->A but leaves C and G as they are; BWAAligner mirrors that, the legacy BWAWrapper facade writes the true
+            // reverse complement (what seq_test/seq_test.cpp:904 asserts).
+            static const struct Tabs {
+                uint8_t fwd[256], rev_ref[256], rev_true[256];
+                Tabs()
+                {
+                    for (int c = 0; c < 256; ++c) fwd[c] = rev_ref[c] = rev_true[c] = 15;
+                    fwd['A'] = 1; fwd['C'] = 2; fwd['G'] = 4; fwd['T'] = 8;
+                    rev_ref['A'] = 8; rev_ref['C'] = 2; rev_ref['G'] = 4; rev_ref['T'] = 1;
+                    rev_true['A'] = 8; rev_true['C'] = 4; rev_true['G'] = 2; rev_true['T'] = 1;
+                }
+            } T;
+            const uint8_t *tab = !h.is_rev ? T.fwd : (primary_first ? T.rev_true : T.rev_ref);
+            const unsigned char *src = (const unsigned char *)clipped;
             int j = 0;
-            for (int p = sl - 1; p >= 0; --p, ++j) {
-                uint8_t x = 15;
-                // Q11: src/BWAAligner.cpp:213-218 maps A->T and T->A but leaves C and G as they are on the reverse strand;
-                // BWAAligner mirrors that, the legacy BWAWrapper facade writes the true reverse complement (what
-                // seq_test/seq_test.cpp:904 asserts).
-                if (primary_first) switch (clipped[p]) { case 'A': x = 8; break; case 'C': x = 4; break; case 'G': x = 2; break; case 'T': x = 1; break; }
-                else switch (clipped[p]) { case 'A': x = 8; break; case 'C': x = 2; break; case 'G': x = 4; break; case 'T': x = 1; break; }
-                sb[j >> 1] = (uint8_t)((sb[j >> 1] & ~(0xF << ((~j & 1) << 2))) | x << ((~j & 1) << 2));
-            }
-        } else {
-            for (int p = 0; p < sl; ++p) {
-                uint8_t x = 15;
-                switch (clipped[p]) { case 'A': x = 1; break; case 'C': x = 2; break; case 'G': x = 4; break; case 'T': x = 8; break; }
-                sb[p >> 1] = (uint8_t)((sb[p >> 1] & ~(0xF << ((~p & 1) << 2))) | x << ((~p & 1) << 2));
+            if (!h.is_rev) {
+                for (; j + 1 < sl; j += 2) sb[j >> 1] = (uint8_t)(tab[src[j]] << 4 | tab[src[j + 1]]);
+                if (j < sl) sb[j >> 1] = (uint8_t)(tab[src[j]] << 4);
+            } else {
+                for (; j + 1 < sl; j += 2) sb[j >> 1] = (uint8_t)(tab[src[sl - 1 - j]] << 4 | tab[src[sl - 2 - j]]);
+                if (j < sl) sb[j >> 1] = (uint8_t)(tab[src[sl - 1 - j]] << 4);
             }
         }
         // Q4: the reference sets qual[0] = 0xff and leaves the rest uninitialised; here the whole string is "absent"
@@ -231,22 +250,31 @@ void BWAAligner::alignSequence(const UnalignedSequence &us, BamRecordPtrVector &
 void BWAAligner::alignSequences(const UnalignedSequenceVector &reads, std::vector<BamRecordPtrVector> &out, bool hardclip,
                                 double keepSecFrac, int maxSecondary) const
 {
+    const size_t n = reads.size();
+    const unsigned nt = n >= 4096 ? std::max(1u, std::min(std::thread::hardware_concurrency(), 32u)) : 1u;
+    auto on_threads = [&](const std::function<void(unsigned)> &f) {
+        if (nt == 1) { f(0); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(f, t);
+        for (auto &x : th) x.join();
+    };
+    if (out.size() >= 4096 && nt > 1) {      // records of a previous batch: millions of small frees, spread over the threads
+        const size_t m = out.size();
+        on_threads([&](unsigned t) { for (size_t i = m * t / nt, e = m * (t + 1) / nt; i < e; ++i) BamRecordPtrVector().swap(out[i]); });
+    }
     out.clear();
-    out.resize(reads.size());
+    out.resize(n);
     if (index_->IsEmpty() || reads.empty()) return;
-    std::vector<int64_t> off(reads.size() + 1, 0), ids(reads.size());
-    for (size_t i = 0; i < reads.size(); ++i) { off[i + 1] = off[i] + (int64_t)reads[i].Seq.size(); ids[i] = lrand48(); }
-    std::string all;
-    all.reserve((size_t)off.back());
-    for (auto &r : reads) all += r.Seq;
+    std::vector<int64_t> off(n + 1, 0), ids(n);
+    for (size_t i = 0; i < n; ++i) { off[i + 1] = off[i] + (int64_t)reads[i].Seq.size(); ids[i] = lrand48(); }
+    std::unique_ptr<char[]> all(new char[(size_t)off.back() + 1]);
+    on_threads([&](unsigned t) { for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) std::memcpy(all.get() + off[i], reads[i].Seq.data(), reads[i].Seq.size()); });
     b200_results_t *res = nullptr;
-    int rc = b200_mem_align_batch(index_->handle(), &opt_, (int64_t)reads.size(), all.data(), off.data(), ids.data(), &res);
+    int rc = b200_mem_align_batch(index_->handle(), &opt_, (int64_t)n, all.get(), off.data(), ids.data(), &res);
     if (rc != B200_OK) throw std::runtime_error(std::string("BWAAligner::alignSequences: ") + b200_last_error());
     b200_results_view_t v;
     b200_results_view(res, &v);
     // bam1_t packing (src/BWAAligner.cpp:151-247) is independent per read: large batches are packed by all host threads
-    const size_t n = reads.size();
-    unsigned nt = n >= 4096 ? std::max(1u, std::min(std::thread::hardware_concurrency(), 32u)) : 1u;
     std::vector<std::exception_ptr> errs(nt);
     auto work = [&](unsigned t) {
         try {
@@ -254,12 +282,7 @@ void BWAAligner::alignSequences(const UnalignedSequenceVector &reads, std::vecto
                 emit_records(reads[i].Seq, reads[i].Name, v, (int64_t)i, hardclip, keepSecFrac, maxSecondary, false, out[i]);
         } catch (...) { errs[t] = std::current_exception(); }
     };
-    if (nt == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
-        for (auto &x : th) x.join();
-    }
+    on_threads(work);
     b200_results_free(res);
     for (auto &e : errs) if (e) std::rethrow_exception(e);
 }

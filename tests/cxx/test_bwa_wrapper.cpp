@@ -94,10 +94,42 @@ int main(int argc, char **argv)
     std::vector<BamRecordPtrVector> outs;
     aln.alignSequences(batch, outs, false, 0.9, 10);
     CHECK(outs.size() == 3); CHECK(outs[0].size() == 2); CHECK(outs[1].size() == 2); CHECK(outs[2].empty());
+    {   // record contents of the batch path: name, 4-bit bases (even and odd lengths), quality marker, tags.  On the reverse
+        // strand BWAAligner writes the reference's own mapping (src/BWAAligner.cpp:213-218: A<->T swapped, C and G kept).
+        auto q11 = [](const std::string &q) { std::string r(q.rbegin(), q.rend()); for (auto &c : r) c = c == 'A' ? 'T' : c == 'T' ? 'A' : c; return r; };
+        int n_fwd = 0, n_rev = 0;
+        for (size_t i = 0; i < 2; ++i)
+            for (auto &rec : outs[i]) {
+                const std::string &q = batch[i].Seq;
+                CHECK(rec->Qname() == batch[i].Name);
+                CHECK(rec->Sequence() == (rec->ReverseFlag() ? q11(q) : q));
+                CHECK(rec->Length() == (int)q.size());
+                int32_t na = -1, nm = -1, as = -1;
+                CHECK(rec->GetIntTag("NA", na) && na == 2);
+                CHECK(rec->GetIntTag("NM", nm) && nm == 0);
+                CHECK(rec->GetIntTag("AS", as) && as == (int)q.size());
+                if (rec->ReverseFlag()) ++n_rev; else ++n_fwd;
+            }
+        CHECK(n_fwd == 2 && n_rev == 2);
+        // the same reads one by one give the same records
+        for (size_t i = 0; i < 2; ++i) {
+            BamRecordPtrVector single;
+            srand48(7 + (long)i);
+            aln.alignSequence(batch[i].Seq, batch[i].Name, single, false, 0.9, 10);
+            CHECK(single.size() == outs[i].size());
+            for (size_t k = 0; k < single.size() && k < outs[i].size(); ++k) {
+                bool found = false;
+                for (auto &rec : outs[i])
+                    if (rec->ChrID() == single[k]->ChrID() && rec->Position() == single[k]->Position() && rec->Sequence() == single[k]->Sequence() &&
+                        rec->CigarString() == single[k]->CigarString()) found = true;
+                CHECK(found);
+            }
+        }
+    }
     BamRecordPtrVector hc;
     aln.alignSequence("GGGGGGGGGG" "ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCG", "clip", hc, true, 0.9, 10);
     CHECK(!hc.empty());
-    if (!hc.empty()) { CHECK(hc[0]->CigarString().find('H') != std::string::npos); }
+    if (!hc.empty()) { CHECK(hc[0]->CigarString().find('H') != std::string::npos); CHECK(hc[0]->Sequence().size() == 38); }
     if (failures) { std::fprintf(stderr, "%d checks failed\n", failures); return 1; }
     std::printf("bwa_wrapper drop-in test OK\n");
     return 0;
