@@ -437,7 +437,7 @@ void b200_fastq_close(b200_fastq_t *r);
 /* FastqReader::GetNextSequence assigns Com / Qual only once kseq has allocated those strings (src/FastqReader.cpp:49-56):
  * bit 0 = a comment has been read, bit 1 = a '+' line has been seen, as of the last record returned. */
 int b200_fastq_buffers_seen(const b200_fastq_t *r);
-/* Strict four-line FASTQ text parsed on the device: newline positions by a stream compaction, one thread per record for
+/* Strict four-line FASTQ text parsed on the device: newline positions by a count / scan / write pass, one thread per record for
  * the '@' / '+' / length checks and the name/comment split, bases gathered into the contiguous layout above.  Gives exactly
  * what b200_fastq_next_batch gives on such text; returns B200_ERR_ARG (and no batch) if the text is not strict four-line
  * FASTQ (multi-line records, FASTA, blank lines, truncated last record) -- the caller then uses the stream parser.

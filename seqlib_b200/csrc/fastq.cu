@@ -4,7 +4,7 @@
 //                     three functions (what ends a name, when a trailing CR is dropped, how blank lines, multi-line records
 //                     and short quality strings are treated), not from their text; records go straight into the flat
 //                     (bytes, offsets) layout b200_mem_align_batch() takes.
-//   device parser  strict four-line FASTQ: newline positions by stream compaction (cub::DeviceSelect), one thread per
+//   device parser  strict four-line FASTQ: newline positions by a count / scan / write pass pair (16 bytes per thread), one thread per
 //                     record for the checks and the name/comment split, one warp per record for the gather.
 #include <cstdio>
 #include <cstring>
@@ -225,10 +225,48 @@ void b200_fastq_close(b200_fastq_t *R) { delete R; }
 // device parser
 namespace b200 {
 
-struct IsNewline {
-    const char *t;
-    __device__ bool operator()(const int64_t &i) const { return t[i] == '\n'; }
-};
+// newline positions: 16 text bytes per thread (one 128-bit load, SWAR byte compare), 4 KB per block; pass 1 counts per
+// block, pass 2 (after an exclusive scan of the block counts) writes the positions in order
+#define NL_THREADS 256
+#define NL_BLOCK_BYTES (NL_THREADS * 16)
+__device__ __forceinline__ void nl_load(const char *__restrict__ t, int64_t len, int64_t base, unsigned m[4])
+{
+    if (base + 16 <= len) {
+        uint4 v = *reinterpret_cast<const uint4 *>(t + base);
+        m[0] = __vcmpeq4(v.x, 0x0a0a0a0au); m[1] = __vcmpeq4(v.y, 0x0a0a0a0au); m[2] = __vcmpeq4(v.z, 0x0a0a0a0au); m[3] = __vcmpeq4(v.w, 0x0a0a0a0au);
+    } else {
+        for (int w = 0; w < 4; ++w) {
+            m[w] = 0;
+            for (int b = 0; b < 4; ++b) { int64_t p = base + 4 * w + b; if (p < len && t[p] == '\n') m[w] |= 0xffu << (8 * b); }
+        }
+    }
+}
+__global__ void __launch_bounds__(NL_THREADS) k_nl_count(const char *__restrict__ t, int64_t len, int64_t *__restrict__ blk_cnt)
+{
+    typedef cub::BlockReduce<unsigned, NL_THREADS> Red;
+    __shared__ typename Red::TempStorage tmp;
+    unsigned m[4];
+    nl_load(t, len, (int64_t)blockIdx.x * NL_BLOCK_BYTES + threadIdx.x * 16, m);
+    unsigned c = (__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3])) >> 3;
+    unsigned tot = Red(tmp).Sum(c);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(NL_THREADS) k_nl_write(const char *__restrict__ t, int64_t len, const int64_t *__restrict__ blk_off, int64_t *__restrict__ nl)
+{
+    typedef cub::BlockScan<unsigned, NL_THREADS> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    unsigned m[4];
+    const int64_t base = (int64_t)blockIdx.x * NL_BLOCK_BYTES + threadIdx.x * 16;
+    nl_load(t, len, base, m);
+    unsigned c = (__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3])) >> 3, at;
+    Scan(tmp).ExclusiveSum(c, at);
+    if (!c) return;
+    int64_t *o = nl + blk_off[blockIdx.x] + at;
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (m[w] >> (8 * b) & 1u) *o++ = base + 4 * w + b;
+}
 
 struct RecSpan { int64_t name_b, com_b, seq_b, qual_b; int32_t name_l, com_l, seq_l, qual_l; };
 
@@ -327,28 +365,29 @@ extern "C" int b200_fastq_parse_device(b200_fastq_t *R, const char *text, int64_
     FQ_CU(cudaMemcpy(d_t, text, (size_t)len, cudaMemcpyHostToDevice));
     // newline positions
     const int64_t max_nl = len / 2 + 2;            // a strict record has at least 2 bytes per line on two of its four lines; more newlines = not strict
+    const int64_t n_blk = (len + NL_BLOCK_BYTES - 1) / NL_BLOCK_BYTES;
+    size_t scan_tb0 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tb0, (const int64_t *)nullptr, (int64_t *)nullptr, (int)(n_blk + 1));
     size_t misc_bytes = sizeof(int64_t) * (size_t)(max_nl + 8) + 64;
+    if (n_blk + 1 > 0x7fffffff) { set_error("b200_fastq_parse_device: text larger than 8 TB"); return B200_ERR_LIMIT; }
     if (!dev_reserve(R->d_misc, R->d_misc_cap, misc_bytes)) { set_error("b200_fastq_parse_device: out of device memory"); return B200_ERR_NOMEM; }
+    if (!dev_reserve(R->d_tmp, R->d_tmp_cap, sizeof(int64_t) * 2 * (size_t)(n_blk + 1) + scan_tb0 + 512)) { set_error("b200_fastq_parse_device: out of device memory"); return B200_ERR_NOMEM; }
     int64_t *d_nl = (int64_t *)R->d_misc;
-    int64_t *d_count = d_nl + max_nl + 1;
-    int *d_bad = (int *)(d_count + 1);
-    {   // the text is scanned in slices so that the compaction never selects more than max_nl positions unnoticed
-        cub::CountingInputIterator<int64_t> it(0);
-        IsNewline op; op.t = d_t;
-        size_t tb = 0;
-        // count first (cheap), then select
-        FQ_CU(cub::DeviceSelect::If(nullptr, tb, it, d_nl, d_count, (int64_t)len, op));
-        if (!dev_reserve(R->d_tmp, R->d_tmp_cap, tb)) { set_error("b200_fastq_parse_device: out of device memory"); return B200_ERR_NOMEM; }
-        // pass 1: count only (discard iterator) to make sure the positions fit
-        cub::DiscardOutputIterator<int64_t> sink;
-        FQ_CU(cub::DeviceSelect::If(R->d_tmp, tb, it, sink, d_count, (int64_t)len, op));
-        int64_t cnt = 0;
-        FQ_CU(cudaMemcpy(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost));
-        if (cnt > max_nl) { set_error("b200_fastq_parse_device: not strict four-line FASTQ (blank lines)"); return B200_ERR_ARG; }
-        FQ_CU(cub::DeviceSelect::If(R->d_tmp, tb, it, d_nl, d_count, (int64_t)len, op));
-    }
+    int *d_bad = (int *)(d_nl + max_nl + 2);
     int64_t n_nl = 0;
-    FQ_CU(cudaMemcpy(&n_nl, d_count, sizeof(n_nl), cudaMemcpyDeviceToHost));
+    {
+        int64_t *d_cnt = (int64_t *)R->d_tmp, *d_off = d_cnt + (n_blk + 1);
+        void *d_scan0 = (void *)(d_off + (n_blk + 1));
+        FQ_CU(cudaMemset(d_cnt + n_blk, 0, sizeof(int64_t)));
+        k_nl_count<<<(unsigned)n_blk, NL_THREADS>>>(d_t, len, d_cnt);
+        FQ_CU(cudaGetLastError());
+        FQ_CU(cub::DeviceScan::ExclusiveSum(d_scan0, scan_tb0, d_cnt, d_off, (int)(n_blk + 1)));
+        FQ_CU(cudaMemcpy(&n_nl, d_off + n_blk, sizeof(n_nl), cudaMemcpyDeviceToHost));
+        if (n_nl > max_nl) { set_error("b200_fastq_parse_device: not strict four-line FASTQ (blank lines)"); return B200_ERR_ARG; }
+        k_nl_write<<<(unsigned)n_blk, NL_THREADS>>>(d_t, len, d_off, d_nl);
+        FQ_CU(cudaGetLastError());
+        FQ_CU(cudaStreamSynchronize(0));           // d_tmp is reused below
+    }
     char last = text[len - 1];
     int64_t n_lines = n_nl + (last == '\n' ? 0 : 1);
     if (n_lines % 4 != 0) { set_error("b200_fastq_parse_device: not strict four-line FASTQ (line count)"); return B200_ERR_ARG; }
