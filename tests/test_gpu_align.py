@@ -206,6 +206,30 @@ def test_long_reads_vs_live_reference(capi):
     assert parity.compare_results(got, exp) == []
 
 
+@pytest.mark.parametrize("name", ["sim1_5k", "bcr_2k"])
+def test_lane_extension_kernel_opt_in(name):
+    """B200_EXTEND_LANE=1 selects k_extend_lane (one lane per read, extend_lane.cuh) instead of the group kernel; the choice is
+    latched at the first call, so the run happens in a fresh process.  Same golden hits, CIGARs and MAPQs."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import cases, goldenlib, parity\n"
+        "from seqlib_b200 import capi\n"
+        "capi.set_device(0)\n"
+        "gold, z = goldenlib.load(%r)\n"
+        "idx = capi.Index.load(goldenlib.path('tiny', 'tiny.fa'))\n"
+        "reads = cases.read_lines(goldenlib.path(%r + '.txt'))\n"
+        "got = capi.align(idx, reads, capi.default_opt(), cases.ids_for(len(reads)))\n"
+        "bad = parity.compare_results(got, gold)\n"
+        "assert bad == [], bad[:5]\n"
+        "print('lane ok', len(got.hits))\n") % (root, os.path.join(root, "tests"), name, name)
+    env = dict(os.environ, B200_EXTEND_LANE="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "lane ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_cxx_dropin_kat(capi, tmp_path):
     """The reference's bwa_wrapper Boost test (seq_test/seq_test.cpp:793-915) against the C++ drop-in classes."""
     import subprocess
