@@ -15,11 +15,10 @@
 #include <sys/stat.h>
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
-#include "common.cuh"
+#include "engine.cuh"          // DevPool: device buffers come from the process-wide pool, like the aligner's
 #include "../../include/seqlib_b200.h"
 
 namespace b200 {
-void set_error(const std::string &msg);
 
 namespace {
 
@@ -113,9 +112,10 @@ struct b200_fastq {
     ~b200_fastq()
     {
         if (st.fp) gzclose(st.fp);
-        if (d_text) cudaFree(d_text);
-        if (d_tmp) cudaFree(d_tmp);
-        if (d_misc) cudaFree(d_misc);
+        // every parse call ends with blocking copies, so nothing is in flight on these blocks
+        if (d_text) b200::dev_pool().put(d_text, d_text_cap);
+        if (d_tmp) b200::dev_pool().put(d_tmp, d_tmp_cap);
+        if (d_misc) b200::dev_pool().put(d_misc, d_misc_cap);
     }
 };
 
@@ -341,11 +341,10 @@ __global__ void k_fastq_last_off(const int64_t *__restrict__ lens, int64_t *__re
 static bool dev_reserve(void *&p, size_t &cap, size_t need)
 {
     if (need <= cap) return true;
-    if (p) cudaFree(p);
+    if (p) dev_pool().put(p, cap);          // callers only grow a buffer after the work that used it was synchronised
     p = nullptr; cap = 0;
-    size_t want = need + need / 4 + 4096;
-    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return false; }
-    cap = want;
+    try { p = dev_pool().get(need + need / 4 + 4096, cap); }
+    catch (const CudaError &) { cudaGetLastError(); return false; }
     return true;
 }
 
