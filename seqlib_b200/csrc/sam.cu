@@ -71,6 +71,13 @@ inline int nt4(unsigned char c)
     switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return c < 4 ? c : 4; }
 }
 
+// "ACGTN"[code] / "TGCAN"[code] of every input byte (mem_aln2sam prints the nt4 codes of the read, bwa/bwamem.c:902-921)
+struct BaseTabs {
+    char fwd[256], rev[256];
+    BaseTabs() { for (int c = 0; c < 256; ++c) { fwd[c] = "ACGTN"[nt4((unsigned char)c)]; rev[c] = "TGCAN"[nt4((unsigned char)c)]; } }
+};
+const BaseTabs g_tabs;
+
 void add_cigar(const Ctx &C, const b200_hit_t &h, Out &o, int which)
 {
     if (!h.n_cigar) { o.ch('*'); return; }
@@ -83,7 +90,7 @@ void add_cigar(const Ctx &C, const b200_hit_t &h, Out &o, int which)
 }
 
 // one record; h == nullptr: the unaligned record (mem_reg2aln with ar == 0: everything zero, rid = pos = -1, flag 4)
-void aln2sam(const Ctx &C, int64_t read, const std::vector<Aln> &list, int which, Out &o)
+void aln2sam(const Ctx &C, int64_t read, const Aln *list, size_t n_list, int which, Out &o)
 {
     static const b200_hit_t zero = {};
     const Aln &p = list[(size_t)which];
@@ -94,6 +101,7 @@ void aln2sam(const Ctx &C, int64_t read, const std::vector<Aln> &list, int which
     int flag = p.flag;
     flag |= rid < 0 ? 0x4 : 0;
     flag |= is_rev ? 0x10 : 0;
+    o.reserve((size_t)(C.name_off[read + 1] - C.name_off[read]) + 2 * (size_t)(C.seq_off[read + 1] - C.seq_off[read]) + 256);   // the common case never reallocates below
     o.strn(C.names + C.name_off[read], (size_t)(C.name_off[read + 1] - C.name_off[read])); o.ch('\t');
     o.num((flag & 0xffff) | (flag & 0x10000 ? 0x100 : 0)); o.ch('\t');
     if (rid >= 0) {
@@ -125,12 +133,12 @@ void aln2sam(const Ctx &C, int64_t read, const std::vector<Aln> &list, int which
         const int len = qe > qb ? qe - qb : 0;
         if (!is_rev) {
             char *w = o.grow((size_t)len + 1);
-            for (int i = qb; i < qe; ++i) *w++ = "ACGTN"[nt4((unsigned char)seq[i])];
+            for (int i = qb; i < qe; ++i) *w++ = g_tabs.fwd[(unsigned char)seq[i]];
             *w = '\t';
             if (qual) o.strn(qual + qb, (size_t)len); else o.ch('*');
         } else {
             char *w = o.grow((size_t)len + 1);
-            for (int i = qe - 1; i >= qb; --i) *w++ = "TGCAN"[nt4((unsigned char)seq[i])];
+            for (int i = qe - 1; i >= qb; --i) *w++ = g_tabs.rev[(unsigned char)seq[i]];
             *w = '\t';
             if (qual) { char *x = o.grow((size_t)len); for (int i = qe - 1; i >= qb; --i) *x++ = qual[i]; } else o.ch('*');
         }
@@ -144,10 +152,10 @@ void aln2sam(const Ctx &C, int64_t read, const std::vector<Aln> &list, int which
     if (p.sub >= 0) { o.str("\tXS:i:"); o.num(p.sub); }
     if (!(flag & 0x100)) {
         size_t i;
-        for (i = 0; i < list.size(); ++i) if ((int)i != which && !(list[i].flag & 0x100)) break;
-        if (i < list.size()) {
+        for (i = 0; i < n_list; ++i) if ((int)i != which && !(list[i].flag & 0x100)) break;
+        if (i < n_list) {
             o.str("\tSA:Z:");
-            for (i = 0; i < list.size(); ++i) {
+            for (i = 0; i < n_list; ++i) {
                 const Aln &r = list[i];
                 if ((int)i == which || (r.flag & 0x100)) continue;
                 o.str(C.rnames[r.h->rid]); o.ch(',');
@@ -209,8 +217,11 @@ void read2sam(const Ctx &C, int64_t read, Out &o)
             }
         }
     }
-    std::vector<Aln> aa;
-    aa.reserve((size_t)(n > 0 ? n : 1));
+    Aln small[8];
+    std::vector<Aln> big;
+    Aln *aa = small;
+    if (n > 8) { big.resize((size_t)n); aa = big.data(); }
+    size_t n_aa = 0;
     int l = 0;
     for (int k = 0; k < n; ++k) {
         const b200_hit_t &p = a[k];
@@ -222,15 +233,15 @@ void read2sam(const Ctx &C, int64_t read, Out &o)
         if (p.secondary >= 0) q.sub = -1;
         if (l && p.secondary < 0) q.flag |= (opt.flag & F_NO_MULTI) ? 0x10000 : 0x800;
         if (!(opt.flag & F_KEEP_SUPP_MAPQ) && l && !p.is_alt && q.mapq > aa[0].mapq) q.mapq = aa[0].mapq;
-        aa.push_back(q);
+        aa[n_aa++] = q;
         ++l;
     }
-    if (aa.empty()) {
+    if (n_aa == 0) {
         Aln t; t.h = nullptr; t.flag = 0; t.mapq = 0; t.sub = 0; t.xa = nullptr;
-        aa.push_back(t);
-        aln2sam(C, read, aa, 0, o);
+        aa[0] = t;
+        aln2sam(C, read, aa, 1, 0, o);
     } else {
-        for (size_t k = 0; k < aa.size(); ++k) aln2sam(C, read, aa, (int)k, o);
+        for (size_t k = 0; k < n_aa; ++k) aln2sam(C, read, aa, n_aa, (int)k, o);
     }
 }
 
