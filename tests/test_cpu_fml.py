@@ -150,3 +150,8 @@ def test_product_fails_loudly_without_a_device():
         capi.fml_assemble_flat(capi.fml_default_opt(), seqs, quals, off)
     with pytest.raises(capi.B200Error, match="-2"):
         capi.Fmd(seqs, off)
+    with pytest.raises(capi.B200Error, match="-2"):
+        capi.fml_assemble_windows(capi.fml_default_opt(), seqs, quals, off, np.array([0, 25, 50], dtype=np.int64), 2)
+    # argument checks come before any device work
+    with pytest.raises(capi.B200Error, match="-1"):
+        capi.fml_assemble_windows(capi.fml_default_opt(), seqs, quals, off, np.array([0, 30, 20], dtype=np.int64), 2)
