@@ -576,7 +576,7 @@ static int ksw_extend2(int qlen, const u8 *query, int tlen, const u8 *target, co
                        int w, int end_bonus, int zdrop, int h0, int *_qle, int *_tle, int *_gtle, int *_gscore, int *_max_off)
 {
 	eh_t *eh = calloc(qlen + 1, 8);
-	int i, j, k, oe_del = o_del + e_del, oe_ins = o_ins + e_ins, beg, end, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off;
+	int i, j, oe_del = o_del + e_del, oe_ins = o_ins + e_ins, beg, end, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off;
 	eh[0].h = h0; eh[1].h = h0 > oe_ins? h0 - oe_ins : 0;
 	for (j = 2; j <= qlen && eh[j-1].h > e_ins; ++j) eh[j].h = eh[j-1].h - e_ins;
 	for (i = 0, max = 0; i < 25; ++i) max = max > mat[i]? max : mat[i];
@@ -1013,7 +1013,7 @@ static int mark_primary_se(const b200_mem_opt_t *opt, int n, reg_t *a, i64 id) /
 {
 	int i, n_pri, nz, *z;
 	if (n == 0) return 0;
-	z = malloc(2 * n * sizeof(int));
+	z = malloc(2 * (size_t)(n > 0 ? n : 0) * sizeof(int) + sizeof(int));
 	for (i = n_pri = 0; i < n; ++i) {
 		a[i].sub = a[i].alt_sc = 0, a[i].secondary = a[i].secondary_all = -1, a[i].hash = hash_64(id+i);
 		if (!a[i].is_alt) ++n_pri;
