@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (config 4: FermiAssembler::PerformAssembly)")
+    ap.add_argument("--parity-reads", type=int, default=int(os.environ.get("B200_BENCH_PARITY_READS", 500_000)),
+                    help="reads of the timed batch re-aligned by the reference library and compared bit for bit (N=1)")
     return ap.parse_args()
 
 
@@ -146,7 +148,30 @@ def make_workload(args, n_total_reads):
     pac = synth.reference(l_pac)
     ctg = synth.contigs_for(l_pac, n_ctg)
     seqs, off, pos, strand = synth.reads(pac, l_pac, ctg, n_total_reads, args.read_len, 0.01, 0.0)
+    make_workload.truth = (pos, strand)
     return pac, ctg, seqs, off, time.time() - t0
+
+
+def parity_block(res, seqs, off, ids, ctg, ridx, opt, n_par, cores):
+    """Bit-exactness inside the headline run (BASELINE.md parity gate): (a) every read's primary hit against the simulated
+    origin, (b) the first n_par reads through the reference's own mem_align1 + mem_reg2aln (oracle/_ref, bwa/bwamem_extra.c:103-115,
+    bwa/bwamem.c:1119-1189) on the SAME index arrays, compared field by field with the GPU hits (regions, CIGAR, MD, MAPQ)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity
+    pos, strand = make_workload.truth
+    n = len(off) - 1
+    rec, mapped = parity.truth_recovery(res, pos[:n], strand[:n], ctg)
+    out = {"truth_within_8bp": rec, "mapped_fraction": mapped}
+    if ridx is not None:
+        from oracle import pyref
+        n_par = int(min(n, n_par))
+        L = int(off[1] - off[0])
+        exp, sec = pyref.align(ridx, (seqs[:n_par * L], off[:n_par + 1]), opt, ids[:n_par], n_threads=cores)
+        bad, msgs = parity.compare_prefix(res, exp, n_par)
+        out.update({"n": n_par, "mismatches": int(bad), "hits_compared": int(exp.hit_off[-1]), "reference_seconds": sec,
+                    "against": "oracle/_ref mem_align1 + mem_reg2aln on the same index arrays, %d threads" % cores,
+                    "messages": msgs[:3]})
+    return out
 
 
 def cpu_baseline_sample(ridx, seqs, off, read_len, opt, target_s, cores):
@@ -258,6 +283,7 @@ def main():
     L = args.read_len
     opt = capi.default_opt()
     cpu_line = None
+    ridx = None
     t_index = t_bcast = 0.0
 
     # ---- inputs: rank 0 generates reference + all reads, builds the index on its GPU ------------------
@@ -276,7 +302,6 @@ def main():
                 v, n_s, t_s = cpu_baseline_sample(ridx, seqs_all, off_all, L, opt, args.cpu_seconds, cores)
                 cpu_line = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
                             "sample": "%d of the same reads through mem_process_seqs (bwa/bwamem.c:1235-1264), %d threads, %.1f s" % (n_s, cores, t_s)}
-                del ridx
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 cpu_line = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
     if world > 1:
@@ -348,6 +373,10 @@ def main():
     res = batch.fetch()
     n_hits_dev = len(res.hits)
     mapped = float((np.diff(res.hit_off) > 0).mean())
+    par = None
+    if rank == 0 and world == 1:
+        par = parity_block(res, seqs, off, ids, ctg, ridx, opt, args.parity_reads, os.cpu_count() or 1)
+        ridx = None
     del res
     batch.close()
 
@@ -410,6 +439,8 @@ def main():
         }
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
+        if par is not None:
+            line["parity"] = par
         if world == 1 and not args.no_extra:
             try:
                 idx.close()

@@ -220,6 +220,9 @@ typedef struct b200_stage_stats {
     uint64_t n_ext, n_global; /* ksw_extend2 / ksw_global2 calls           */
     uint64_t n_overflow;      /* reads re-run with spill buffers           */
     int n_launches;
+    uint64_t tab_lookups_lo;  /* prefix-interval table lookups (16 B each), levels <= 10 (21 MB, L2 resident) */
+    uint64_t tab_lookups_hi;  /* ... levels 11..K (HBM gathers)             */
+    uint64_t ext_fallback;    /* extensions re-run by the row-synchronous kernel */
 } b200_stage_stats_t;
 int b200_last_stats(b200_stage_stats_t *out);
 

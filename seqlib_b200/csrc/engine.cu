@@ -28,14 +28,14 @@ using namespace b200;
 namespace b200 {
 
 static double wall_now();
-struct DevCounters { unsigned long long v[8]; };   // occ_blocks, sa_reads, ref_bytes, sw_cells, n_ext, n_global, n_ovf, pool_fail
+struct DevCounters { unsigned long long v[8]; };   // occ_blocks, sa_reads, ref_bytes, sw_cells, n_ext, n_global, tab_lo, tab_hi
 
 __device__ __forceinline__ void flush_counters(const CtrLocal &c, DevCounters *g)
 {
     // warp-aggregate, one atomic per warp and counter
-    unsigned long long v[6] = {c.occ_blocks, c.sa_reads, c.ref_bytes, c.sw_cells, c.n_ext, c.n_global};
+    unsigned long long v[8] = {c.occ_blocks, c.sa_reads, c.ref_bytes, c.sw_cells, c.n_ext, c.n_global, c.tab_lo, c.tab_hi};
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 8; ++k) {
         unsigned long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(&g->v[k], x);
@@ -57,6 +57,7 @@ struct KArgs {
     u8 *scratch; size_t scratch_stride;
     unsigned long long *work_ctr; DevCounters *ctrs;
     const double *log_tab; int n_log;
+    SeedTab tab;                            // prefix-interval tables of the index (seed2.cuh); K == 0: none
 };
 
 template <int STAGE>
@@ -95,6 +96,13 @@ struct SmemList {
 struct SmemQuery {
     const u32 *p;
     __device__ __forceinline__ int operator[](int i) const { return (int)((p[(i >> 4) * 128] >> ((i & 15) * 2)) & 3u); }
+    // bases [st, st + ln), ln <= 16, base t in bits 2t.. (the word after the read's last one is zero padding)
+    __device__ __forceinline__ u32 key(int st, int ln) const
+    {
+        const u32 lo = p[(st >> 4) * 128], hi = p[((st >> 4) + 1) * 128];
+        const u32 w = __funnelshift_r(lo, hi, (st & 15) * 2);
+        return ln >= 16 ? w : w & ((1u << (2 * ln)) - 1u);
+    }
 };
 
 // 2-bit words of every read (16 bases per word, base i in bits 2(i&15)..) + a flag for reads with a base > 3
@@ -139,6 +147,7 @@ __global__ void __launch_bounds__(128, 4) k_seed2(const __grid_constant__ KArgs 
     SmemList L; L.p = seed_smem + threadIdx.x;
     u32 *myq = (u32 *)(seed_smem + CAP * 128) + threadIdx.x;
     SmemQuery Q; Q.p = myq;
+    myq[qw * 128] = 0;
     SeedMachine<SmemList, SmemQuery> m;
     m.mode = 0; m.ovf = 0;
     CtrLocal ctr;
@@ -165,20 +174,42 @@ __global__ void __launch_bounds__(128, 4) k_seed2(const __grid_constant__ KArgs 
                     const u32 *src = packed + rid * qw;
                     for (int k = 0; k < qw; ++k) myq[k * 128] = src[k];
                     IntvSink out; out.a = A.B.pool.intv + rid * stride; out.n = 0; out.cap = stride; out.overflow = false;
-                    m.init(A.opt, len, CAP, L, Q, out);
+                    m.init(A.opt, len, CAP, L, Q, out, A.tab.K);
                     m.start(A.ix);
                 }
             }
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (m.mode != 0) {
-            u64 a, o, s, na, no, ns; int c;
-            m.request(a, o, s, c);
-            extend_lean(A.ix, a, o, s, c, na, no, ns, ctr);
+            u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
+            m.request(a, o, s, c, tl, key, fwd);
+            extend_or_lookup(A.ix, A.tab, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
             m.consume(A.ix, na, no, ns);
         }
     }
     flush_counters(ctr, A.ctrs);
+}
+
+// level j of the prefix-interval tables from level j-1: entry[key] = forward extension of entry[key's first j-1 bases]
+// by its last base, computed by the very code the seeding kernel runs (so a lookup returns what the iterated
+// bwt_extend would have, bwa/bwt.c:262-275, including the coordinates of empty intervals).
+__global__ void k_seedtab_level(const DevIndex ix, PIntv *__restrict__ base, int j)
+{
+    const u64 key = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= (1ull << (2 * j))) return;
+    PIntv *out = base + seedtab_level_off(j) + key;
+    if (j == 1) {
+        Intv t; set_intv(ix, (int)key, t);
+        *out = pintv_pack(t.x0, t.x1, t.x2, 0);
+        return;
+    }
+    const u64 parent = key & ((1ull << (2 * (j - 1))) - 1);
+    const int c = (int)(key >> (2 * (j - 1)));
+    u64 x0, x1, x2, na, no, ns; u32 e;
+    pintv_unpack(base[seedtab_level_off(j - 1) + parent], x0, x1, x2, e);
+    CtrLocal ctr;
+    extend_lean(ix, x1, x0, x2, 3 - c, na, no, ns, ctr);
+    *out = pintv_pack(no, na, ns, 0);
 }
 
 // order each read's intervals by (start, end) -- the ks_introsort of mem_collect_intv (bwa/bwamem.c:186); equal keys are identical intervals
@@ -493,7 +524,7 @@ static bool seed2_usable(const KArgs &A)
 template <int CAP>
 static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
 {
-    size_t smem = (size_t)128 * (CAP * 16 + qw * 4);
+    size_t smem = (size_t)128 * (CAP * 16 + (qw + 1) * 4);
     CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     int per = 0;
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP>, 128, smem));
@@ -518,6 +549,40 @@ static void launch_seed2(Engine &E, KArgs &A)
     k_sort_intv<<<(unsigned)((n + 127) / 128), 128, 0, E.st>>>(A.B.rec, A.B.ovf, n, A.B.pool.intv);
     CU_CHECK(cudaGetLastError());
     E.stats.n_launches += 3;
+}
+
+// Prefix-interval tables of an index (seed2.cuh): built once, on the first batch that can use them.
+// K = min(B200_SEED_TAB_K (default 15), floor(log4(seq_len)), what a third of the free HBM holds); 23 GB at K = 15.
+static SeedTab seed_tables(Engine &E, const b200_index *idx)
+{
+    SeedTab T; T.base = nullptr; T.K = 0;
+    std::lock_guard<std::mutex> g(idx->seedtab_mu);
+    if (idx->seedtab_K < 0) {
+        static const int want = getenv("B200_SEED_TAB_K") ? atoi(getenv("B200_SEED_TAB_K")) : 15;
+        int K = want > 16 ? 16 : want;
+        while (K > 0 && (1ull << (2 * K)) > idx->seq_len) --K;
+        size_t free_b = 0, total_b = 0;
+        CU_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        while (K > 0 && seedtab_entries(K) * sizeof(PIntv) > (free_b + dev_pool().pooled) / 3) --K;
+        if (idx->seq_len >= (1ull << 36)) K = 0;
+        if (K > 0) {
+            void *p = nullptr;
+            if (cudaMalloc(&p, seedtab_entries(K) * sizeof(PIntv)) != cudaSuccess) {
+                cudaGetLastError(); dev_pool().trim(0);
+                CU_CHECK(cudaMalloc(&p, seedtab_entries(K) * sizeof(PIntv)));
+            }
+            for (int j = 1; j <= K; ++j) {
+                const u64 n = 1ull << (2 * j);
+                k_seedtab_level<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(idx->dev, (PIntv *)p, j);
+            }
+            CU_CHECK(cudaGetLastError());
+            CU_CHECK(cudaStreamSynchronize(E.st));
+            idx->d_seedtab = p;
+        }
+        idx->seedtab_K = K;
+    }
+    T.base = (const PIntv *)idx->d_seedtab; T.K = idx->seedtab_K;
+    return T;
 }
 
 // Runs the four stages over `n_work` reads (all reads of the chunk, or the spill list).
@@ -664,6 +729,7 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         k_clear_u32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n);
         KArgs A; memset(&A, 0, sizeof(A));
         A.ix = idx->dev; A.opt = opt; A.caps = caps;
+        A.tab = seed_tables(E, idx);
         A.B.n_reads = n; A.B.seq = d_seq; A.B.seq_off = d_off; A.B.hash_id = d_ids; A.B.ovf = E.ovf.as<u32>(); A.B.rec = E.rec.as<ReadRec>();
         Pools &P = A.B.pool;
         P.intv = E.p_intv.as<Intv>(); P.chains = E.p_chain.as<Chain>(); P.seeds = E.p_seed.as<Seed>(); P.regs = E.p_reg.as<Reg>();
@@ -725,6 +791,7 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         E.stats.ms_seed += ms4[0]; E.stats.ms_chain += ms4[1]; E.stats.ms_extend += ms4[2]; E.stats.ms_finalize += ms4[3];
         const unsigned long long *c = h_small + 16;
         E.stats.occ_blocks += c[0]; E.stats.sa_reads += c[1]; E.stats.ref_bytes += c[2]; E.stats.sw_cells += c[3]; E.stats.n_ext += c[4]; E.stats.n_global += c[5];
+        E.stats.tab_lookups_lo += c[6]; E.stats.tab_lookups_hi += c[7];
         // compact in read order
         E.nh.reserve(n * 8 + 8); E.nc.reserve(n * 8 + 8); E.nm.reserve(n * 8 + 8); E.oh.reserve(n * 8 + 16); E.oc.reserve(n * 8 + 16); E.om.reserve(n * 8 + 16);
         k_counts<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.rec.as<ReadRec>(), n, E.nh.as<i64>(), E.nc.as<i64>(), E.nm.as<i64>());
@@ -1009,6 +1076,7 @@ int b200_debug_collect_intv(const b200_index_t *idx, const b200_mem_opt_t *opt, 
         KArgs A; memset(&A, 0, sizeof(A));
         unsigned long long *d_small = E.small.as<unsigned long long>();
         A.ix = idx->dev; A.opt = b->opt; A.caps = big;
+        A.tab = seed_tables(E, idx);
         A.B.n_reads = n; A.B.seq = b->d_seq.as<u8>(); A.B.seq_off = b->d_off.as<i64>(); A.B.hash_id = b->d_ids.as<i64>();
         A.B.ovf = E.ovf.as<u32>(); A.B.rec = E.rec.as<ReadRec>();
         A.B.pool.intv = E.p_intv.as<Intv>(); A.B.pool.cap[POOL_INTV] = cap; A.B.pool.used = d_small + 8;

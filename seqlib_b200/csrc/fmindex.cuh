@@ -8,23 +8,24 @@ namespace b200 {
 
 struct OccLoad { u32 c0, c1, c2, c3; u64 s0, s1; };
 
-HD OccLoad load_block(const DevIndex &ix, u64 blk)
+HD OccLoad load_block_at(const OccBlock *p)
 {
     OccLoad r;
 #if defined(__CUDA_ARCH__)
     // one 256-bit load (LDG.E.256 on sm_100a): the block is one 32-byte sector, so one request per rank query
     u32 a0, a1, a2, a3, b0, b1, b2, b3;
     asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "l"(ix.occ + blk));
+                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "l"(p));
     r.c0 = a0; r.c1 = a1; r.c2 = a2; r.c3 = a3;
     r.s0 = (u64)b0 | (u64)b1 << 32; r.s1 = (u64)b2 | (u64)b3 << 32;
 #else
-    const OccBlock &b = ix.occ[blk];
+    const OccBlock &b = *p;
     r.c0 = b.cnt[0]; r.c1 = b.cnt[1]; r.c2 = b.cnt[2]; r.c3 = b.cnt[3];
     r.s0 = b.sym[0]; r.s1 = b.sym[1];
 #endif
     return r;
 }
+HD OccLoad load_block(const DevIndex &ix, u64 blk) { return load_block_at(ix.occ + blk); }
 
 // counts of A,C,G,T in the first r (1..64) symbols of a loaded block, added to the block base.
 // s0 / s1 are the low / high bit planes of the 64 symbols: three popcounts under one mask give all four counts.

@@ -273,7 +273,7 @@ void host_copy_from_image(b200_index *idx)
 
 } // namespace b200
 
-b200_index::~b200_index() { if (owns_blob && d_blob) cudaFree(d_blob); }
+b200_index::~b200_index() { if (owns_blob && d_blob) cudaFree(d_blob); if (d_seedtab) cudaFree(d_seedtab); }
 
 // -------------------------------------------------------------------------
 // C ABI

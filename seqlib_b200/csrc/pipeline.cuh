@@ -70,8 +70,8 @@ struct Batch {
 };
 
 struct CtrLocal {
-    unsigned long long occ_blocks, sa_reads, ref_bytes, sw_cells, n_ext, n_global;
-    HD CtrLocal() : occ_blocks(0), sa_reads(0), ref_bytes(0), sw_cells(0), n_ext(0), n_global(0) {}
+    unsigned long long occ_blocks, sa_reads, ref_bytes, sw_cells, n_ext, n_global, tab_lo, tab_hi;
+    HD CtrLocal() : occ_blocks(0), sa_reads(0), ref_bytes(0), sw_cells(0), n_ext(0), n_global(0), tab_lo(0), tab_hi(0) {}
 };
 
 HD i64 pool_alloc(const Pools &P, int which, i64 n)
@@ -118,7 +118,8 @@ HD void stage_seed(const DevIndex &ix, const Opt &opt, const Caps &caps, const B
 
 // The single-extension-site machine of seed2.cuh with a `list_cap`-entry work list, falling back to the reference-shaped
 // loops when the read is not eligible or the list overflows: what k_seed2 + the spill pass compute together.
-HD void stage_seed_v2(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr, int list_cap)
+HD void stage_seed_v2(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr, int list_cap,
+                      const SeedTab *tab = nullptr)
 {
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
     const u8 *seq = B.seq + B.seq_off[rid];
@@ -128,7 +129,7 @@ HD void stage_seed_v2(const DevIndex &ix, const Opt &opt, const Caps &caps, cons
     Intv *prev = (Intv *)scratch, *curr = prev + (caps.maxlen + 1);
     IntvSink out; out.a = curr + (caps.maxlen + 1); out.n = 0; out.cap = caps.intv; out.overflow = false;
     if (list_cap > caps.maxlen + 1) list_cap = caps.maxlen + 1;
-    bool ok = seed2_eligible(ix, len, seq) && collect_intv_v2(ix, opt, len, seq, out, (PIntv *)prev, list_cap, ctr);
+    bool ok = seed2_eligible(ix, len, seq) && collect_intv_v2(ix, opt, len, seq, out, (PIntv *)prev, list_cap, ctr, tab);
     if (!ok && !out.overflow) { out.n = 0; if (len >= opt.min_seed_len) collect_intv(ix, opt, len, seq, out, prev, curr, ctr); }
     if (out.overflow) { B.ovf[rid] |= OVF_INTV; return; }
     i64 off = pool_alloc(B.pool, POOL_INTV, out.n);

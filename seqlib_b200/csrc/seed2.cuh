@@ -19,6 +19,15 @@
 //
 // Restrictions (the caller routes everything else to seed.cuh): no base > 3 in the read, len < 65536,
 // seq_len < 2^36, and the list capacity.
+//
+// Prefix-interval tables (SeedTab).  The bi-interval of a string is a pure function of the index, so for every
+// string of length j <= K the result of "extend to that string" is tabulated once per index: level j holds 4^j packed
+// 16-byte intervals, keyed by the string itself (base i in bits 2i..).  Every extension whose RESULT is a string of
+// length <= K -- the first K steps of each forward sweep, the short entries of every backward row, the first K steps
+// of every bwt_seed_strategy1 start -- becomes one 16-byte gather (L2-resident for the low levels) instead of two
+// dependent-free 32-byte Occ gathers.  The tables are produced by the same extend_lean code, level j from level
+// j-1 (k_seedtab_level, engine.cu), so they hold exactly what the iterated bwt_extend (bwa/bwt.c:262-275) computes,
+// and interval lists stay identical to the reference's.  With 180 GB of HBM, K = 15 (23 GB) fits next to a 3 Gb index.
 #pragma once
 #include "common.cuh"
 #include "fmindex.cuh"
@@ -43,21 +52,17 @@ HD void pintv_unpack(const PIntv &p, u64 &x0, u64 &x1, u64 &x2, u32 &end)
     end = p.w3 >> 16;
 }
 
+struct SeedTab { const PIntv *base; int K; };    // K == 0: no tables
+HD u64 seedtab_level_off(int j) { return ((1ull << (2 * j)) - 4) / 3; }      // entries of levels 1..j-1 (a multiple of 4)
+HD u64 seedtab_entries(int K) { return K > 0 ? seedtab_level_off(K + 1) : 0; }
+
 // bwt_extend (bwa/bwt.c:262-275) for the one child the callers use, on raw coordinates:
 //   a = the coordinate the Occ ranks are taken on (x[!is_back]), o = the other one, s = interval size.
 // Ranks a-1 and a-1+s are never -1 here (every interval starts at L2[c]+1 >= 1).
-template <class Ctr>
-HD void extend_lean(const DevIndex &ix, u64 a, u64 o, u64 s, int c, u64 &na, u64 &no, u64 &ns, Ctr &ctr)
+// the arithmetic of extend_lean on two loaded blocks (b1 holds rank kk, b2 rank ll)
+HD void extend_blocks(const DevIndex &ix, const OccLoad &b1, const OccLoad &b2, u64 kk, u64 ll, u32 dk, u32 dl, u64 o, int c,
+                      u64 &na, u64 &no, u64 &ns)
 {
-    const u64 k = a - 1, l = k + s;
-    const u32 dk = k >= ix.primary, dl = l >= ix.primary;
-    const u64 kk = k - dk, ll = l - dl;
-    const u64 bk = kk >> 6, bl = ll >> 6;
-    // both gathers are issued before either is used, unconditionally: when k and l share a block the second request
-    // merges with the first in L1, whereas a predicated second load would have to wait for the first to land
-    OccLoad b1 = load_block(ix, bk);
-    OccLoad b2 = load_block(ix, bl);
-    ctr.occ_blocks += bl != bk ? 2 : 1;
     const int rk = (int)(kk & 63), rl = (int)(ll & 63);          // ranks inside the block, minus one
     const u64 mk = (2ull << rk) - 1, ml = (2ull << rl) - 1;      // rk == 63: 2<<63 wraps to 0, minus 1 = all ones
     const u64 klo = b1.s0 & mk, khi = b1.s1 & mk, llo = b2.s0 & ml, lhi = b2.s1 & ml;
@@ -78,20 +83,68 @@ HD void extend_lean(const DevIndex &ix, u64 a, u64 o, u64 s, int c, u64 &na, u64
     ns = sc;
 }
 
+template <class Ctr>
+HD void extend_lean(const DevIndex &ix, u64 a, u64 o, u64 s, int c, u64 &na, u64 &no, u64 &ns, Ctr &ctr)
+{
+    const u64 k = a - 1, l = k + s;
+    const u32 dk = k >= ix.primary, dl = l >= ix.primary;
+    const u64 kk = k - dk, ll = l - dl;
+    const u64 bk = kk >> 6, bl = ll >> 6;
+    // both gathers are issued before either is used, unconditionally: when k and l share a block the second request
+    // merges with the first in L1, whereas a predicated second load would have to wait for the first to land
+    OccLoad b1 = load_block(ix, bk);
+    OccLoad b2 = load_block(ix, bl);
+    ctr.occ_blocks += bl != bk ? 2 : 1;
+    extend_blocks(ix, b1, b2, kk, ll, dk, dl, o, c, na, no, ns);
+}
+
+// One extension through the tables when the result string is short enough (tl = its length, key = the string), else
+// through the Occ blocks.  Written so that a warp issues ONE pair of 256-bit loads whatever its lanes need: a table
+// lane loads the 32-byte sector that holds its 16-byte entry (twice -- the second request merges in L1).
+// fwd: the caller extends forward (result coordinates swap roles, see SeedMachine::request).
+template <class Ctr>
+HD void extend_or_lookup(const DevIndex &ix, const SeedTab &tab, int tl, u32 key, bool fwd, u64 a, u64 o, u64 s, int c,
+                         u64 &na, u64 &no, u64 &ns, Ctr &ctr)
+{
+    const u64 k = a - 1, l = k + s;
+    const u32 dk = k >= ix.primary, dl = l >= ix.primary;
+    const u64 kk = k - dk, ll = l - dl;
+    u64 bk = kk >> 6, bl = ll >> 6;
+    const OccBlock *p1 = ix.occ + bk, *p2 = ix.occ + bl;
+    u32 half = 0;
+    if (tl) {
+        const PIntv *e = tab.base + seedtab_level_off(tl) + key;
+        half = (u32)(((uintptr_t)e >> 4) & 1);
+        p1 = p2 = (const OccBlock *)((uintptr_t)e & ~(uintptr_t)31);
+        if (tl <= 10) ctr.tab_lo++; else ctr.tab_hi++;
+    } else ctr.occ_blocks += bl != bk ? 2 : 1;
+    OccLoad b1 = load_block_at(p1);
+    OccLoad b2 = load_block_at(p2);
+    extend_blocks(ix, b1, b2, kk, ll, dk, dl, o, c, na, no, ns);
+    if (tl) {
+        PIntv t;
+        if (half) { t.w0 = (u32)b1.s0; t.w1 = (u32)(b1.s0 >> 32); t.w2 = (u32)b1.s1; t.w3 = (u32)(b1.s1 >> 32); }
+        else { t.w0 = b1.c0; t.w1 = b1.c1; t.w2 = b1.c2; t.w3 = b1.c3; }
+        u64 t0, t1, t2; u32 e_;
+        pintv_unpack(t, t0, t1, t2, e_);
+        na = fwd ? t1 : t0; no = fwd ? t0 : t1; ns = t2;
+    }
+}
+
 // One read's seeding as a resumable machine.  List: get(e) / set(e, PIntv) over `cap` entries; Query: operator[](i) in 0..3.
 template <class List, class Query>
 struct SeedMachine {
     enum { M_DONE = 0, M_FWD, M_BWD, M_P3, M_TASK, M_ENDFWD, M_LASTROW };
     int mode, pass, x, k2, old_n, sx, i, j, nprev, ncurr, top, ret, last_start, first, ovf;
-    int len, cap, min_seed_len, split_len, split_width, max_intv3, min_intv;
+    int len, cap, min_seed_len, split_len, split_width, max_intv3, min_intv, K;
     u64 x0, x1, x2, lastcurr;     // ik of the forward sweeps / last size pushed in this backward row
     u64 p0, p1, p2;               // the list entry being extended backwards
     u32 iend, pend;
     List L; Query q; IntvSink out;
 
-    HD void init(const Opt &opt, int len_, int cap_, const List &L_, const Query &q_, const IntvSink &out_)
+    HD void init(const Opt &opt, int len_, int cap_, const List &L_, const Query &q_, const IntvSink &out_, int K_ = 0)
     {
-        len = len_; cap = cap_; L = L_; q = q_; out = out_;
+        len = len_; cap = cap_; L = L_; q = q_; out = out_; K = K_;
         min_seed_len = opt.min_seed_len;
         split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
         split_width = opt.split_width;
@@ -189,6 +242,17 @@ struct SeedMachine {
         } else { a = x1; o = x0; s = x2; c = 3 - q[i]; }
     }
 
+    // the same, plus the string the extension produces: q[st, st + ln).  tl = ln when a table level holds it, else 0.
+    HD void request(u64 &a, u64 &o, u64 &s, int &c, int &tl, u32 &key, bool &fwd)
+    {
+        request(a, o, s, c);
+        fwd = mode != M_BWD;
+        const int st = mode == M_BWD ? i : (mode == M_FWD ? sx : x);
+        const int ln = mode == M_BWD ? (int)pend - i : i + 1 - st;
+        tl = ln <= K ? ln : 0;
+        key = tl ? q.key(st, ln) : 0u;
+    }
+
     HD void consume(const DevIndex &ix, u64 na, u64 no, u64 ns)
     {
         if (mode == M_BWD) {
@@ -236,7 +300,11 @@ struct SeedMachine {
 
 // plain-array list / byte query: the host emulation and the debug path
 struct ArrayList { PIntv *p; HD PIntv get(int e) const { return p[e]; } HD void set(int e, const PIntv &v) { p[e] = v; } };
-struct ByteQuery { const u8 *p; HD int operator[](int i) const { return p[i]; } };
+struct ByteQuery {
+    const u8 *p;
+    HD int operator[](int i) const { return p[i]; }
+    HD u32 key(int st, int ln) const { u32 k = 0; for (int t = 0; t < ln; ++t) k |= (u32)p[st + t] << (2 * t); return k; }
+};
 
 HD bool seed2_eligible(const DevIndex &ix, int len, const u8 *seq)
 {
@@ -257,17 +325,20 @@ HD void sort_intv_by_info(Intv *a, int n)
 
 // scalar driver: same results as collect_intv() for eligible reads; returns false when the list capacity was exceeded
 template <class Ctr>
-HD bool collect_intv_v2(const DevIndex &ix, const Opt &opt, int len, const u8 *seq, IntvSink &out, PIntv *list, int cap, Ctr &ctr)
+HD bool collect_intv_v2(const DevIndex &ix, const Opt &opt, int len, const u8 *seq, IntvSink &out, PIntv *list, int cap, Ctr &ctr,
+                        const SeedTab *tab = nullptr)
 {
     SeedMachine<ArrayList, ByteQuery> m;
     ArrayList L; L.p = list;
     ByteQuery q; q.p = seq;
-    m.init(opt, len, cap, L, q, out);
+    SeedTab none; none.base = nullptr; none.K = 0;
+    const SeedTab &T = tab ? *tab : none;
+    m.init(opt, len, cap, L, q, out, T.K);
     m.start(ix);
     while (m.mode != 0) {
-        u64 a, o, s, na, no, ns; int c;
-        m.request(a, o, s, c);
-        extend_lean(ix, a, o, s, c, na, no, ns, ctr);
+        u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
+        m.request(a, o, s, c, tl, key, fwd);
+        extend_or_lookup(ix, T, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
         m.consume(ix, na, no, ns);
     }
     out = m.out;

@@ -4,6 +4,7 @@
 #include <vector>
 #include <cstring>
 #include "../../seqlib_b200/csrc/hostutil.h"
+#include "../../seqlib_b200/csrc/seed2.cuh"
 
 namespace b200 {
 
@@ -13,6 +14,31 @@ struct HostIndex {
     std::vector<u64> sa, text;
     std::vector<i64> coff;
     std::vector<i32> calt;
+    std::vector<PIntv> tab_entries;      // prefix-interval tables (seed2.cuh), built like k_seedtab_level does
+    SeedTab tab;
+
+    struct NoCtr { unsigned long long occ_blocks = 0; };
+    void build_tab(int K)
+    {
+        while (K > 0 && (1ull << (2 * K)) > dev.seq_len) --K;
+        tab_entries.assign(seedtab_entries(K) + 2, PIntv());
+        // the device table is 32-byte aligned; keep the same sector arithmetic valid on the host
+        PIntv *base = tab_entries.data();
+        if ((uintptr_t)base & 31) ++base;
+        for (int j = 1; j <= K; ++j)
+            for (u64 key = 0; key < (1ull << (2 * j)); ++key) {
+                PIntv *out = base + seedtab_level_off(j) + key;
+                if (j == 1) { Intv t; set_intv(dev, (int)key, t); *out = pintv_pack(t.x0, t.x1, t.x2, 0); continue; }
+                u64 parent = key & ((1ull << (2 * (j - 1))) - 1);
+                int c = (int)(key >> (2 * (j - 1)));
+                u64 x0, x1, x2, na, no, ns; u32 e;
+                pintv_unpack(base[seedtab_level_off(j - 1) + parent], x0, x1, x2, e);
+                NoCtr ctr;
+                extend_lean(dev, x1, x0, x2, 3 - c, na, no, ns, ctr);
+                *out = pintv_pack(no, na, ns, 0);
+            }
+        tab.base = base; tab.K = K;
+    }
 
     HostIndex(const b200_index_view_t &v, int sa_shift)
     {
@@ -52,6 +78,7 @@ struct HostIndex {
         coff[v.n_seqs] = v.l_pac;
         dev.occ = occ.data(); dev.n_occ = nblk; dev.sa = sa.data(); dev.n_sa = sa.size(); dev.text = text.data();
         dev.n_seqs = v.n_seqs; dev.contig_off = coff.data(); dev.contig_alt = calt.data();
+        tab.base = nullptr; tab.K = 0;
     }
 };
 

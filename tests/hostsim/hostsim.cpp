@@ -73,6 +73,9 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
     B.pool.cap[POOL_REG] = p_reg.size(); B.pool.cap[POOL_HIT] = p_hit.size(); B.pool.cap[POOL_CIGAR] = p_cig.size(); B.pool.cap[POOL_MD] = p_md.size();
     bool dbg = getenv("HOSTSIM_DEBUG") != 0;
     int seed_v2 = getenv("HOSTSIM_SEED_V2") ? atoi(getenv("HOSTSIM_SEED_V2")) : 0;   // list capacity of the seed2.cuh machine, 0 = seed_fsm
+    int tab_K = getenv("HOSTSIM_SEED_TAB_K") ? atoi(getenv("HOSTSIM_SEED_TAB_K")) : 0;   // prefix-interval tables for the seed2 machine
+    if (seed_v2 && tab_K > 0 && hi->tab.K != tab_K) hi->build_tab(tab_K);
+    const SeedTab *tabp = seed_v2 && tab_K > 0 ? &hi->tab : nullptr;
     bool ext_lane = getenv("HOSTSIM_EXTEND_LANE") && lane_extend_eligible(opt, maxlen);   // the one-lane-per-read machine of extend_lane.cuh
     std::vector<u32> lane_cols((size_t)maxlen + 2 * LANE_U + 2), lane_q((size_t)maxlen / 8 + 8);
     std::vector<std::vector<Reg> > raws(n);
@@ -83,7 +86,7 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
             std::vector<u8> s1(seed_scratch_bytes(c) + 64), s2(chain_scratch_bytes(c) + 64), s3(extend_scratch_bytes(c) + 64), s4(finalize_scratch_bytes(c) + 64);
             ovf[r] = 0;
             if (dbg) fprintf(stderr, "read %ld pass %d\n", (long)r, pass);
-            if (seed_v2) stage_seed_v2(ix, opt, c, B, r, s1.data(), ctr, seed_v2);
+            if (seed_v2) stage_seed_v2(ix, opt, c, B, r, s1.data(), ctr, seed_v2, tabp);
             else stage_seed(ix, opt, c, B, r, s1.data(), ctr);
             stage_chain(ix, opt, c, B, r, s2.data(), ctr, logtab.data(), (int)logtab.size());
             if (ext_lane) {

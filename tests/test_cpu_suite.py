@@ -47,17 +47,21 @@ def _sim_index_for_tiny():
     return simlib.SimIndex(tidx.view(), keep=tidx), tidx
 
 
-@pytest.mark.parametrize("name,small,seed_v2", [("sim1_5k", False, 0), ("bcr_2k", False, 0), ("bcr_2k", True, 0),
-                                                ("sim1_5k", False, 24), ("bcr_2k", False, 24), ("bcr_2k", False, 7)])
-def test_stage_functions_on_cpu_vs_golden(name, small, seed_v2, monkeypatch):
+@pytest.mark.parametrize("name,small,seed_v2,tab_k", [("sim1_5k", False, 0, 0), ("bcr_2k", False, 0, 0), ("bcr_2k", True, 0, 0),
+                                                      ("sim1_5k", False, 24, 0), ("bcr_2k", False, 24, 0), ("bcr_2k", False, 7, 0),
+                                                      ("sim1_5k", False, 24, 8), ("bcr_2k", False, 24, 8), ("bcr_2k", False, 24, 3),
+                                                      ("bcr_2k", False, 7, 6)])
+def test_stage_functions_on_cpu_vs_golden(name, small, seed_v2, tab_k, monkeypatch):
     """The per-read device functions, compiled for the host (tests/hostsim), reproduce the golden vectors;
     `small` forces every read through the spill path; seed_v2 = work-list capacity of the single-extension-site
     seeding machine (seed2.cuh) the GPU kernel runs (0: the reference-shaped loops; 7: most reads overflow the list
-    and fall back, as in the kernel's spill pass)."""
+    and fall back, as in the kernel's spill pass); tab_k = levels of the prefix-interval tables that replace the
+    extensions to strings of at most tab_k bases (interval lists must stay identical)."""
     if seed_v2:
         monkeypatch.setenv("HOSTSIM_SEED_V2", str(seed_v2))
     else:
         monkeypatch.delenv("HOSTSIM_SEED_V2", raising=False)
+    monkeypatch.setenv("HOSTSIM_SEED_TAB_K", str(tab_k))
     from oracle import pyref
     if not pyref.have_ref():
         pytest.skip("needs oracle/_ref to parse the bwa index for the host harness")
