@@ -436,6 +436,7 @@ def main():
             "wall_s_timed_region": wall_s, "mapped_fraction": mapped, "hits_per_step": n_hits_dev,
             "index_build_s": t_index, "index_bcast_s": t_bcast, "spill_reads_per_step": stats["n_overflow"],
             "sw_cells_per_step": stats["sw_cells"], "occ_blocks_per_read": occ_per_step / n_per,
+            "seed_table_lookups_per_read": {"levels_le_10": stats.get("tab_lookups_lo", 0) / n_per, "levels_11_to_K": stats.get("tab_lookups_hi", 0) / n_per},
         }
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line

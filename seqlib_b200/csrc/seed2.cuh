@@ -210,6 +210,15 @@ struct SeedMachine {
                 }
                 if (pass == 3) {
                     if (x >= len) { mode = M_DONE; return; }
+                    // the first min(K, min_seed_len) - 1 extensions of a bwt_seed_strategy1 start (bwa/bwt.c:355-379) can
+                    // neither report nor stop (i - x < min_seed_len): one table lookup of q[x, x + jump) replaces them
+                    const int jump = K < min_seed_len ? K : min_seed_len;
+                    if (jump >= 2 && x + jump <= len) {
+                        x0 = x1 = 1; x2 = 0;             // placeholders: the lookup result overwrites them
+                        i = x + jump - 1;
+                        mode = M_P3;
+                        return;
+                    }
                     Intv t; set_intv(ix, q[x], t);
                     x0 = t.x0; x1 = t.x1; x2 = t.x2;
                     i = x + 1;
