@@ -226,35 +226,75 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def run_ksw(args):
-    """Config 3: ksw_extend2 1M x (150 q, 300 r) microbenchmark, GCUPS."""
+WAVE_INSTR_PER_CELL = 33.0     # SASS instructions of one wavefront step (66, profiles/r02_sass_extend_wave.txt) / 2 cells per step
+
+
+def int_peak():
+    """Measured integer-ALU issue rate (thread-instructions/s) of the kinds the wavefront is made of:
+    profiles/r02_int_peak.json (scripts/microbench/int_peak.cu on this pool's B200s); nominal fallback otherwise."""
+    p = os.path.join(ROOT, "profiles", "r02_int_peak.json")
+    try:
+        rows = [json.loads(l) for l in open(p) if l.strip().startswith("{")]
+        alu = [r["thread_instr_per_s"] for r in rows if r["kind"] in ("VIMNMX3.S16x2", "VIADDMNMX.S16x2.RELU", "VIADD.16x2", "PRMT+LOP3")]
+        return float(np.median(alu)), "measured: ALU-pipe issue rate (median of VIMNMX3 / VIADDMNMX / VIADD.16x2 / PRMT+LOP3 chains) in profiles/r02_int_peak.json"
+    except Exception:
+        return 148 * 4 * 16 * 1.965e9, "nominal: 148 SMs x 4 schedulers x 16 ALU lanes x 1.965 GHz"
+
+
+def ksw_measure(args, n, with_cpu):
+    """Config 3: ksw_extend2 n x (150 q, 300 r) microbenchmark through b200_ksw_extend2_batch (the packed 16-bit wavefront kernel,
+    then the row-synchronous kernel over whatever it hands back)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cases
     from seqlib_b200 import capi
-    capi.set_device(0)
-    n = int(os.environ.get("B200_BENCH_KSW_PAIRS", 1_000_000))
     jobs, qp, tp = cases.c3_tuples_fast(n)
     opt = capi.default_opt()
     mat = np.array(list(opt.mat), dtype=np.int8)
-    for _ in range(args.warmup):
+    # the reference's band-trimmed cell count, from the row-synchronous kernel (untimed): the wavefront streams ~2 % more
+    os.environ["B200_KSW_WAVE"] = "0"
+    out0, cells, _ = capi.ksw_extend2_batch(jobs, qp, tp, mat)
+    del os.environ["B200_KSW_WAVE"]
+    for _ in range(max(1, args.warmup)):
         capi.ksw_extend2_batch(jobs, qp, tp, mat)
-    ms, cells = [], 0
-    for _ in range(args.steps):
-        out, cells, t = capi.ksw_extend2_batch(jobs, qp, tp, mat)
+    ms = []
+    out = None
+    for _ in range(max(1, args.steps)):
+        out, _, t = capi.ksw_extend2_batch(jobs, qp, tp, mat)
         ms.append(t)
-    gcups = cells / (np.mean(ms) * 1e-3) / 1e9
-    line = {"metric": "ksw_extend2 GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": {"workload": "ksw_extend2 %d x (150q,300r) pairs" % n, "cells_per_step": int(cells)},
-            "gpu_launches": args.steps}
-    if not args.no_cpu_baseline:
+    t_s = float(np.mean(ms)) * 1e-3
+    gcups = cells / t_s / 1e9
+    peak, how = int_peak()
+    achieved = cells * WAVE_INSTR_PER_CELL / t_s
+    res = {"value": gcups, "unit": "GCUPS", "ms_per_step": float(np.mean(ms)), "cells_per_step": int(cells), "pairs": int(n),
+           "kernels_agree": bool(out.tobytes() == out0.tobytes()),
+           "roofline": {"bound": "int-alu", "kernel": "k_ext_wave (packed s16x2 anti-diagonal wavefront)", "achieved": achieved / 1e9,
+                        "peak": peak / 1e9, "unit": "G thread-instr/s", "frac": achieved / peak, "traffic": None,
+                        "instr_per_cell": WAVE_INSTR_PER_CELL, "peak_source": how,
+                        "note": "cells = the reference's band-trimmed count; instr_per_cell = SASS of the step loop only (pipeline fill/drain, "
+                                "row commits and lane idling are the gap between frac and 1)"}}
+    if with_cpu:
         from oracle import pyref
         m = min(n, 20000)
         cores = os.cpu_count() or 1
-        _, sec = pyref.ksw_extend2_batch(jobs[:m], qp, tp, mat, n_threads=cores)
-        # cells of the sample: proportional share
-        line["cpu_baseline"] = {"value": cells * (m / n) / sec / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
-                                "sample": "%d pairs, scalar ksw_extend2 (bwa/ksw.c:416-515) on %d threads" % (m, cores)}
+        exp, sec = pyref.ksw_extend2_batch(jobs[:m], qp, tp, mat, n_threads=cores)
+        res["parity"] = {"n": int(m), "mismatches": int(np.sum(exp != out[:m])), "against": "oracle/_ref ksw_extend2 (bwa/ksw.c:416-515)"}
+        res["cpu_baseline"] = {"value": cells * (m / n) / sec / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                               "sample": "%d pairs, scalar ksw_extend2 (bwa/ksw.c:416-515) on %d threads" % (m, cores)}
+    return res
+
+
+def run_ksw(args):
+    from seqlib_b200 import capi
+    capi.set_device(0)
+    n = int(os.environ.get("B200_BENCH_KSW_PAIRS", 1_000_000))
+    r = ksw_measure(args, n, not args.no_cpu_baseline)
+    line = {"metric": "ksw_extend2 GCUPS", "value": r["value"], "unit": "GCUPS", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2",
+            "data": "synthetic", "config": {"workload": "ksw_extend2 %d x (150q,300r) pairs" % n, "cells_per_step": r["cells_per_step"]},
+            "gpu_launches": 2 * args.steps, "roofline": r["roofline"], "kernels_agree": r["kernels_agree"]}
+    for k in ("cpu_baseline", "parity"):
+        if k in r:
+            line[k] = r[k]
     print(json.dumps(line), flush=True)
 
 
@@ -305,38 +345,24 @@ def main():
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 cpu_line = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
     if world > 1:
-        # one NCCL broadcast of the index image, one NCCL scatter of the read shards
-        nb = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            nb[0] = idx.blob_bytes()
-        dist.broadcast(nb, 0)
-        blob = torch.empty(int(nb.item()), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idx.export_blob(blob.data_ptr())
-            idx.close()
-        torch.cuda.synchronize()
+        # the product's own multi-GPU entry points (include/seqlib_b200.h, csrc/dist.cu): ONE NCCL broadcast of the index image,
+        # one scatter of the read batch by contiguous shard.  torch.distributed only carries the 128-byte NCCL id,
+        # the barriers and the max-over-ranks reduction of the timings.
+        uid = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = capi.Comm(uid[0], rank, world)
         dist.barrier()
-        t0 = time.time()
-        dist.broadcast(blob, 0)
-        torch.cuda.synchronize()
-        t_bcast = time.time() - t0
-        idx = capi.Index.attach_blob(blob.data_ptr(), blob.numel(), keep=blob)
-        shard = torch.empty(n_per * L, dtype=torch.uint8, device=dev)
+        idx = comm.index_bcast(idx if rank == 0 else None, 0)
+        t_bcast = comm.last_bcast_ms() / 1e3
+        seqs, sb, se = comm.reads_scatter(seqs_all if rank == 0 else None, n_per * world, L, 0)
+        assert se - sb == n_per
         if rank == 0:
-            full = torch.from_numpy(seqs_all).pin_memory()
-            parts = [full[r * n_per * L:(r + 1) * n_per * L].to(dev, non_blocking=True) for r in range(world)]
-            torch.cuda.synchronize()
-            dist.scatter(shard, parts, src=0)
-            del parts
-        else:
-            dist.scatter(shard, None, src=0)
-        torch.cuda.synchronize()
-        seqs = shard.cpu().numpy()
-        del shard
+            del seqs_all
     else:
         seqs = seqs_all
     off = np.arange(n_per + 1, dtype=np.int64) * L
-    ids = (np.arange(n_per, dtype=np.int64) + rank * n_per) * 7919 + 13
+    from seqlib_b200 import shard
+    ids = shard.read_ids(rank * n_per, (rank + 1) * n_per)          # a function of the GLOBAL read index (tests/test_dist_cpu.py)
 
     def barrier():
         if world > 1:
@@ -448,6 +474,10 @@ def main():
                 line["extra"] = {"config4_fermi_assemble": fermi_extra(args, not args.no_cpu_baseline)}
             except Exception as e:   # secondary numbers never fail the headline line
                 line["extra"] = {"config4_fermi_assemble": {"error": str(e)}}
+            try:
+                line["extra"]["config3_ksw"] = ksw_measure(args, int(os.environ.get("B200_BENCH_KSW_PAIRS", 1_000_000)), not args.no_cpu_baseline)
+            except Exception as e:
+                line["extra"]["config3_ksw"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

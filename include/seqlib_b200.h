@@ -209,6 +209,26 @@ int b200_batch_run(b200_batch_t *b, int *n_launches);
 int b200_batch_fetch(b200_batch_t *b, b200_results_t **out);
 void b200_batch_destroy(b200_batch_t *b);
 
+/* ------------------------------------------------------------------ */
+/* Multi-GPU: one process per GPU.  The index image is   */
+/* replicated by ONE NCCL broadcast (the analogue of shipping the single */
+/* block of bwa_idx2mem, bwa/bwa.c:362-401); a read batch is sharded by  */
+/* contiguous read index and scattered over NVLink; after that every     */
+/* rank calls b200_mem_align_batch on its shard -- no collective in the  */
+/* data path.  NCCL is bound at run time (dlopen).                       */
+/* ------------------------------------------------------------------ */
+typedef struct b200_comm b200_comm_t;
+/* reads [*beg, *end) of rank: contiguous, sizes differ by at most one */
+void b200_shard_bounds(int64_t n_total, int world, int rank, int64_t *beg, int64_t *end);
+int b200_comm_unique_id(char id[128]);      /* rank 0 makes it, the caller ships it to the other ranks (any channel) */
+int b200_comm_init(const char id[128], int rank, int world, b200_comm_t **out);   /* on the calling thread's current device */
+void b200_comm_destroy(b200_comm_t *c);
+/* root passes its index and gets it back; the other ranks get a replica that owns its device memory */
+int b200_index_bcast(b200_comm_t *c, const b200_index_t *root_idx, int root, b200_index_t **out);
+float b200_comm_last_bcast_ms(const b200_comm_t *c);   /* device time of the image broadcast */
+/* fixed-length reads held by root (host, n_total * read_len bytes) -> this rank's shard (host, (end - beg) * read_len bytes) */
+int b200_reads_scatter(b200_comm_t *c, int root, int64_t n_total, int read_len, const char *seqs, char *shard);
+
 /* Per-stage device timings (ms, CUDA events on the launching stream) and
  * work counters of the last b200_batch_run / b200_mem_align_batch. */
 typedef struct b200_stage_stats {
@@ -222,7 +242,8 @@ typedef struct b200_stage_stats {
     int n_launches;
     uint64_t tab_lookups_lo;  /* prefix-interval table lookups (16 B each), levels <= 10 (21 MB, L2 resident) */
     uint64_t tab_lookups_hi;  /* ... levels 11..K (HBM gathers)             */
-    uint64_t ext_fallback;    /* extensions re-run by the row-synchronous kernel */
+    uint64_t ext_fallback;    /* reads whose extensions were re-run by the row-synchronous kernel */
+    uint64_t n_failed;        /* reads beyond every working-set limit: reported without hits (b200_last_error says so) */
 } b200_stage_stats_t;
 int b200_last_stats(b200_stage_stats_t *out);
 

@@ -86,7 +86,7 @@ class StageStats(C.Structure):
         ("occ_blocks", C.c_uint64), ("sa_reads", C.c_uint64), ("ref_bytes", C.c_uint64),
         ("sw_cells", C.c_uint64), ("n_ext", C.c_uint64), ("n_global", C.c_uint64),
         ("n_overflow", C.c_uint64), ("n_launches", C.c_int),
-        ("tab_lookups_lo", C.c_uint64), ("tab_lookups_hi", C.c_uint64), ("ext_fallback", C.c_uint64),
+        ("tab_lookups_lo", C.c_uint64), ("tab_lookups_hi", C.c_uint64), ("ext_fallback", C.c_uint64), ("n_failed", C.c_uint64),
     ]
 
 

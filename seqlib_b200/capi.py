@@ -23,6 +23,8 @@ EXPORTS = [
     "b200_index_l_pac", "b200_mem_align_batch", "b200_results_view", "b200_results_free", "b200_batch_create",
     "b200_batch_run", "b200_batch_fetch", "b200_batch_destroy", "b200_last_stats", "b200_debug_collect_intv",
     "b200_ksw_extend2_batch", "b200_set_device", "b200_device_count",
+    "b200_shard_bounds", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy", "b200_index_bcast", "b200_comm_last_bcast_ms",
+    "b200_reads_scatter",
     "b200_fml_opt_init", "b200_fml_opt_adjust", "b200_fml_opt_adjust_lens", "b200_fml_correct", "b200_fml_fltuniq",
     "b200_fml_correct_flat", "b200_fml_count", "b200_kmer_table_hist", "b200_kmer_table_size", "b200_kmer_table_lookup",
     "b200_kmer_correct_flat", "b200_kmer_table_destroy", "b200_fml_last_stats",
@@ -103,6 +105,16 @@ def lib():
         L.b200_fmd_destroy.argtypes = [C.c_void_p]
         L.b200_fml_mag_text.argtypes = [C.POINTER(FmlOpt), C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+        L.b200_shard_bounds.restype = None
+        L.b200_shard_bounds.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.b200_comm_unique_id.argtypes = [C.c_char_p]
+        L.b200_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.b200_comm_destroy.restype = None
+        L.b200_comm_destroy.argtypes = [C.c_void_p]
+        L.b200_index_bcast.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.b200_comm_last_bcast_ms.restype = C.c_float
+        L.b200_comm_last_bcast_ms.argtypes = [C.c_void_p]
+        L.b200_reads_scatter.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -127,6 +139,51 @@ def default_opt(softclip=True):
 
 def set_device(i):
     _check(lib().b200_set_device(i))
+
+
+def shard_bounds(n_total, world, rank):
+    """Reads [b, e) of `rank`: contiguous shards by global read index (b200_shard_bounds)."""
+    b, e = C.c_int64(), C.c_int64()
+    lib().b200_shard_bounds(n_total, world, rank, C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
+def comm_unique_id():
+    """128-byte NCCL id made by rank 0; ship it to the other ranks over any channel, then Comm(id, rank, world) everywhere."""
+    buf = C.create_string_buffer(128)
+    _check(lib().b200_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """One process per GPU: the index image is replicated by one NCCL broadcast, read batches are scattered by contiguous shard."""
+
+    def __init__(self, uid, rank, world):
+        self.h = C.c_void_p()
+        self.rank, self.world = rank, world
+        _check(lib().b200_comm_init(C.c_char_p(uid), rank, world, C.byref(self.h)))
+
+    def index_bcast(self, idx, root=0):
+        """root passes its Index and gets it back; the other ranks pass None and get a replica."""
+        out = C.c_void_p()
+        _check(lib().b200_index_bcast(self.h, idx.h if idx is not None else None, root, C.byref(out)))
+        return idx if self.rank == root else Index(out)
+
+    def last_bcast_ms(self):
+        return float(lib().b200_comm_last_bcast_ms(self.h))
+
+    def reads_scatter(self, seqs, n_total, read_len, root=0):
+        """seqs: uint8 array of n_total * read_len bases on root (None elsewhere) -> this rank's shard (uint8), b, e."""
+        b, e = shard_bounds(n_total, self.world, self.rank)
+        shard = np.empty((e - b) * read_len, dtype=np.uint8)
+        src = np.ascontiguousarray(seqs, dtype=np.uint8) if seqs is not None else None
+        _check(lib().b200_reads_scatter(self.h, root, n_total, read_len, _p(src), _p(shard)))
+        return shard, b, e
+
+    def close(self):
+        if self.h:
+            lib().b200_comm_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class Index:

@@ -58,6 +58,7 @@ struct KArgs {
     unsigned long long *work_ctr; DevCounters *ctrs;
     const double *log_tab; int n_log;
     SeedTab tab;                            // prefix-interval tables of the index (seed2.cuh); K == 0: none
+    const unsigned long long *n_work_dev;   // when set: the number of work items lives on the device (retry lists)
 };
 
 template <int STAGE>
@@ -141,9 +142,13 @@ __global__ void k_pack_reads4(const u8 *__restrict__ seq, const i64 *__restrict_
 }
 
 template <int CAP>
-__global__ void __launch_bounds__(128, 4) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride)
+__global__ void __launch_bounds__(128, 4) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride,
+                                                  int keep_level)
 {
     extern __shared__ uint4 seed_smem[];
+    LoadPol pol; pol.keep_level = keep_level;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol.stream));
     SmemList L; L.p = seed_smem + threadIdx.x;
     u32 *myq = (u32 *)(seed_smem + CAP * 128) + threadIdx.x;
     SmemQuery Q; Q.p = myq;
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(128, 4) k_seed2(const __grid_constant__ KArgs 
         if (m.mode != 0) {
             u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
             m.request(a, o, s, c, tl, key, fwd);
-            extend_or_lookup(A.ix, A.tab, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
+            extend_or_lookup(A.ix, A.tab, tl, key, fwd, a, o, s, c, na, no, ns, ctr, keep_level >= 0 ? &pol : nullptr);
             m.consume(A.ix, na, no, ns);
         }
     }
@@ -236,6 +241,38 @@ __global__ void __launch_bounds__(128, REG ? 4 : 3) k_extend_group(const __grid_
     g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     u8 *smem = REG ? smem_raw : smem_raw + (size_t)gib * group_smem_bytes(A.caps.maxlen);
     u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
+    const i64 n_work = A.n_work_dev ? (i64)*A.n_work_dev : A.n_work;
+    CtrLocal ctr;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)(32 / G));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((i64)base >= n_work) break;
+        i64 w = (i64)base + lane / G;
+        if (w < n_work) {
+            i64 rid = A.order ? A.order[w] : w;
+            stage_extend_group<G, REG>(g, A.ix, A.opt, A.caps, A.B, rid, scr, smem, smat, ctr);
+        }
+        __syncwarp();
+    }
+    flush_counters(ctr, A.ctrs);
+}
+
+// stage 2 as a packed 16-bit anti-diagonal wavefront (ksw_wave.cuh): G lanes per read, two target rows per lane, the
+// column state streamed lane to lane by warp shuffles.  Shared memory: (maxlen + 2) stream words per group.  Reads it
+// cannot finish exactly (gap events, N bases, scores beyond 13 bits) are appended to B.retry_list for k_extend_group.
+__host__ __device__ inline size_t wave_smem_bytes(int maxlen) { return ((size_t)(maxlen + 2) * 4 + 15) & ~(size_t)15; }
+template <int G>
+__global__ void __launch_bounds__(128, 6) k_extend_wave(const __grid_constant__ KArgs A)
+{
+    extern __shared__ __align__(16) u8 smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int gib = threadIdx.x / G;
+    GroupCtx<G> g;
+    g.gl = threadIdx.x % G;
+    g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    u8 *smem = smem_raw + (size_t)gib * wave_smem_bytes(A.caps.maxlen);
+    u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
     CtrLocal ctr;
     for (;;) {
         unsigned long long base = 0;
@@ -245,7 +282,7 @@ __global__ void __launch_bounds__(128, REG ? 4 : 3) k_extend_group(const __grid_
         i64 w = (i64)base + lane / G;
         if (w < A.n_work) {
             i64 rid = A.order ? A.order[w] : w;
-            stage_extend_group<G, REG>(g, A.ix, A.opt, A.caps, A.B, rid, scr, smem, smat, ctr);
+            stage_extend_group<G, 2>(g, A.ix, A.opt, A.caps, A.B, rid, scr, smem, nullptr, ctr);
         }
         __syncwarp();
     }
@@ -360,6 +397,13 @@ __global__ void k_list_ovf(const u32 *__restrict__ ovf, i64 n, u32 mask, i32 *__
     if (ovf[i] & mask) { unsigned long long o = atomicAdd(cnt, 1ull); list[o] = (i32)i; }
 }
 
+// reads that could not be processed: no hits
+__global__ void k_drop_reads(ReadRec *__restrict__ rec, const i32 *__restrict__ list, i64 n)
+{
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { ReadRec &R = rec[list[i]]; R.n_hits = R.n_cigar = R.n_md = 0; R.hit_off = 0; }
+}
+
 __global__ void k_counts(const ReadRec *__restrict__ rec, i64 n, i64 *__restrict__ nh, i64 *__restrict__ nc, i64 *__restrict__ nm)
 {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,10 +507,11 @@ struct Engine {
     cudaStream_t st = nullptr, st_copy = nullptr;      // kernels / result copies that overlap the next chunk's kernels
     cudaEvent_t ev[8], ev_copy, ev_up;
     // chunk buffers
-    DevBuf packed, packed4, seedflag, seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
+    DevBuf wave_scratch, retry_list, packed, packed4, seedflag, seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
     DevBuf p_intv, p_chain, p_seed, p_reg, p_hit, p_cigar, p_md;
     DevBuf nh, nc, nm, oh, oc, om, cubtmp, o_hit_off, o_hits, o_cigar, o_md;
     double pool_scale = 1.0;
+    i64 pool_min[N_POOLS] = {0, 0, 0, 0, 0, 0, 0};       // per-pool capacity floor learnt from failed attempts (kept for later chunks)
     b200_stage_stats_t stats;
 
     void init()
@@ -506,10 +551,10 @@ struct ChunkCtx {
 static size_t max4(size_t a, size_t b, size_t c, size_t d) { return std::max(std::max(a, b), std::max(c, d)); }
 
 template <int STAGE>
-static void launch_stage(Engine &E, KArgs &A, int grid)
+static void launch_stage(Engine &E, KArgs &A, int grid, int tpb = 128)
 {
     CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
-    k_stage<STAGE><<<grid, 128, 0, E.st>>>(A);
+    k_stage<STAGE><<<grid, tpb, 0, E.st>>>(A);
     CU_CHECK(cudaGetLastError());
 }
 
@@ -530,7 +575,9 @@ static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP>, 128, smem));
     if (per < 1) per = 1;
     { static const int occ = getenv("B200_OCC_SEED") ? atoi(getenv("B200_OCC_SEED")) : 0; if (occ > 0 && occ < per) per = occ; }
-    k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
+    // levels <= keep_level of the tables are loaded with an evict_last L2 policy, everything else evict_first (-1: no hints)
+    static const int keep_level = getenv("B200_SEED_KEEP") ? atoi(getenv("B200_SEED_KEEP")) : -1;   // measured: no effect on the L2 hit rate or the kernel time (profiles/r02_seed_l2hint_ab.txt)
+    k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE, keep_level);
 }
 static void launch_seed2(Engine &E, KArgs &A)
 {
@@ -585,33 +632,48 @@ static SeedTab seed_tables(Engine &E, const b200_index *idx)
     return T;
 }
 
+// the wavefront kernel computes scores as (match ? a : -b): the matrix must be what bwa_fill_scmat(a, b) makes (bwa/bwa.c:64-77)
+static bool wave_opt_ok(const Opt &o)
+{
+    if (o.a <= 0 || o.b < 0 || o.e_del <= 0 || o.e_ins <= 0 || o.o_del < 0 || o.o_ins < 0) return false;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (o.mat[i * 5 + j] != (i == j ? o.a : -o.b)) return false;
+    return o.a + o.b < 256 && o.o_del + o.e_del < 4000 && o.o_ins + o.e_ins < 4000;
+}
+
+static double scratch_budget_bytes()
+{
+    static const double budget_gb = getenv("B200_SCRATCH_GB") ? atof(getenv("B200_SCRATCH_GB")) : 16.0;
+    return budget_gb * (double)(1ull << 30);
+}
+
 // Runs the four stages over `n_work` reads (all reads of the chunk, or the spill list).
-static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
+// spill: 0 = main pass, 1 = spill pass (big slots, few blocks), 2 = last-resort pass (huge slots, one warp per block)
+static void run_stages(Engine &E, KArgs A, int spill, float *ms4)
 {
     int g[4];
+    const int tpb = spill >= 2 ? 32 : 128;            // threads per block of the thread-per-read kernels
     if (!spill) { g[0] = stage_grid<0>(E.sms); g[1] = stage_grid<1>(E.sms); g[2] = stage_grid<2>(E.sms); g[3] = stage_grid<3>(E.sms); }
-    else g[0] = g[1] = g[2] = g[3] = std::max<int>(1, (int)std::min<i64>((A.n_work + 127) / 128, 8));
+    else g[0] = g[1] = g[2] = g[3] = std::max<int>(1, (int)std::min<i64>((A.n_work + tpb - 1) / tpb, 8));
     Caps tc = A.caps;
     if (A.B.dp_jobs) tc.z = 64;          // gapped hits go to k_finalize_dp, the thread-per-read stage needs no direction matrix
     size_t stride = max4(seed_scratch_bytes(tc), chain_scratch_bytes(tc), extend_scratch_bytes(tc), finalize_scratch_bytes(tc));
     stride = (stride + 63) & ~(size_t)63;
     {   // long reads: the per-thread slot grows with the read length (hundreds of KB in the main pass, up to ~100 MB in the
         // spill pass), so the number of resident threads is bounded by a scratch budget instead of by occupancy alone
-        static const double budget_gb = getenv("B200_SCRATCH_GB") ? atof(getenv("B200_SCRATCH_GB")) : 16.0;
-        i64 fit = (i64)(budget_gb * (double)(1ull << 30) / (double)(stride * 128));
+        i64 fit = (i64)(scratch_budget_bytes() / (double)(stride * tpb));
         if (fit < 1) fit = 1;
         for (int i = 0; i < 4; ++i) if (g[i] > fit) g[i] = (int)fit;
     }
     int gmax = std::max(std::max(g[0], g[1]), std::max(g[2], g[3]));
     DevBuf &S = spill ? E.spill_scratch : E.scratch;
-    S.reserve(stride * (size_t)gmax * 128);
+    S.reserve(stride * (size_t)gmax * tpb);
     A.scratch = S.as<u8>(); A.scratch_stride = stride;
     cudaEvent_t *ev = E.ev;
     CU_CHECK(cudaEventRecord(ev[0], E.st));
     if (!spill && seed2_usable(A)) launch_seed2(E, A);
-    else launch_stage<0>(E, A, g[0]);
+    else launch_stage<0>(E, A, g[0], tpb);
     CU_CHECK(cudaEventRecord(ev[1], E.st));
-    launch_stage<1>(E, A, g[1]); CU_CHECK(cudaEventRecord(ev[2], E.st));
+    launch_stage<1>(E, A, g[1], tpb); CU_CHECK(cudaEventRecord(ev[2], E.st));
     {
         const int G = 8;
         static int reg_ok = getenv("B200_EXTEND_SMEM") ? 0 : 1;
@@ -653,6 +715,43 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
             E.stats.n_launches += 1;
             CU_CHECK(cudaGetLastError());
         } else if (group_ok && smem <= 200 * 1024) {
+            // reads ordered by estimated work: heaviest first, equal work side by side in a warp
+            const i32 *order = A.order;
+            if (!spill && A.B.work && !A.order) {
+                i64 n = A.n_work;
+                E.sort_keys.reserve(n * 4 + 64); E.sort_vals.reserve(n * 4 + 64); E.sort_vals2.reserve(n * 4 + 64);
+                k_iota32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.sort_vals.as<i32>(), n);
+                size_t tb = 0;
+                cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 20, E.st);
+                E.cubtmp.reserve(tb);
+                CU_CHECK(cub::DeviceRadixSort::SortPairsDescending(E.cubtmp.p, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 20, E.st));
+                order = E.sort_vals2.as<i32>();
+            }
+            // main pass: the packed 16-bit wavefront kernel; what it hands back goes through the row-synchronous kernel below
+            static const int wave_g = getenv("B200_WAVE_G") ? atoi(getenv("B200_WAVE_G")) : 8;
+            const bool use_wave = !spill && wave_g > 0 && wave_opt_ok(A.opt) && A.caps.maxlen <= WAVE_MAXQ && A.B.retry_list &&
+                                  (long)A.caps.maxlen * A.opt.a * 2 + std::max(A.opt.pen_clip5, A.opt.pen_clip3) + 16 < 8000;
+            if (use_wave) {
+                const int WG = wave_g == 8 ? 8 : wave_g == 2 ? 2 : 4;
+                size_t wsmem = (size_t)(128 / WG) * wave_smem_bytes(A.caps.maxlen);
+                int per = 0;
+                if (WG == 8) { CU_CHECK(cudaFuncSetAttribute(k_extend_wave<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_wave<8>, 128, wsmem)); }
+                else if (WG == 2) { CU_CHECK(cudaFuncSetAttribute(k_extend_wave<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_wave<2>, 128, wsmem)); }
+                else { CU_CHECK(cudaFuncSetAttribute(k_extend_wave<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_wave<4>, 128, wsmem)); }
+                if (per < 1) per = 1;
+                { static const int occ = getenv("B200_OCC_WAVE") ? atoi(getenv("B200_OCC_WAVE")) : 0; if (occ > 0 && occ < per) per = occ; }
+                int grid = (int)std::min<i64>((i64)E.sms * per, std::max<i64>(1, (A.n_work + (128 / WG) - 1) / (128 / WG)));
+                size_t gstride = (extend_group_scratch_bytes(A.caps) + 63) & ~(size_t)63;
+                E.wave_scratch.reserve(gstride * (size_t)grid * (128 / WG));
+                KArgs A2 = A; A2.scratch = E.wave_scratch.as<u8>(); A2.scratch_stride = gstride; A2.order = order;
+                CU_CHECK(cudaMemsetAsync(A2.work_ctr, 0, 8, E.st));
+                CU_CHECK(cudaMemsetAsync(A.B.n_retry, 0, 8, E.st));
+                if (WG == 8) k_extend_wave<8><<<grid, 128, wsmem, E.st>>>(A2);
+                else if (WG == 2) k_extend_wave<2><<<grid, 128, wsmem, E.st>>>(A2);
+                else k_extend_wave<4><<<grid, 128, wsmem, E.st>>>(A2);
+                CU_CHECK(cudaGetLastError());
+                E.stats.n_launches += 1;
+            }
             int per = 0;
             if (use_reg) CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_group<G, true>, 128, 0));
             else {
@@ -662,27 +761,20 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
             if (per < 1) per = 1;
             { static const int occ = getenv("B200_OCC_EXT") ? atoi(getenv("B200_OCC_EXT")) : 0; if (occ > 0 && occ < per) per = occ; }
             int grid = (int)std::min<i64>((i64)E.sms * per, std::max<i64>(1, (A.n_work + (128 / G) - 1) / (128 / G)));
+            if (use_wave) grid = std::min(grid, E.sms);       // the retry list is short
             size_t gstride = (extend_group_scratch_bytes(A.caps) + 63) & ~(size_t)63;
+            if (spill) grid = (int)std::max<i64>(1, std::min<i64>(grid, (i64)(scratch_budget_bytes() / (double)(gstride * (128 / G)))));
             (spill ? E.group_scratch2 : E.group_scratch).reserve(gstride * (size_t)grid * (128 / G));
-            KArgs A2 = A; A2.scratch = (spill ? E.group_scratch2 : E.group_scratch).as<u8>(); A2.scratch_stride = gstride;
-            if (!spill && A.B.work && !A.order) {       // heaviest reads first, equal work side by side in a warp
-                i64 n = A.n_work;
-                E.sort_keys.reserve(n * 4 + 64); E.sort_vals.reserve(n * 4 + 64); E.sort_vals2.reserve(n * 4 + 64);
-                k_iota32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.sort_vals.as<i32>(), n);
-                size_t tb = 0;
-                cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 20, E.st);
-                E.cubtmp.reserve(tb);
-                CU_CHECK(cub::DeviceRadixSort::SortPairsDescending(E.cubtmp.p, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 20, E.st));
-                A2.order = E.sort_vals2.as<i32>();
-            }
+            KArgs A2 = A; A2.scratch = (spill ? E.group_scratch2 : E.group_scratch).as<u8>(); A2.scratch_stride = gstride; A2.order = order;
+            if (use_wave) { A2.order = A.B.retry_list; A2.n_work_dev = A.B.n_retry; A2.B.retry_list = nullptr; }
             CU_CHECK(cudaMemsetAsync(A2.work_ctr, 0, 8, E.st));
             if (use_reg) k_extend_group<G, true><<<grid, 128, 0, E.st>>>(A2);
             else k_extend_group<G, false><<<grid, 128, smem, E.st>>>(A2);
             CU_CHECK(cudaGetLastError());
-        } else launch_stage<2>(E, A, g[2]);
+        } else launch_stage<2>(E, A, g[2], tpb);
     }
     CU_CHECK(cudaEventRecord(ev[3], E.st));
-    { KArgs At = A; At.caps = tc; launch_stage<3>(E, At, g[3]); }
+    { KArgs At = A; At.caps = tc; launch_stage<3>(E, At, g[3], tpb); }
     if (A.B.dp_jobs) {
         const int G = 8;
         size_t smem = (size_t)(128 / G) * findp_smem_bytes(A.caps.maxlen);
@@ -692,6 +784,7 @@ static void run_stages(Engine &E, KArgs A, bool spill, float *ms4)
         if (per < 1) per = 1;
         int grid = spill ? std::min(E.sms * per, 64) : E.sms * per;
         size_t gstride = (findp_scratch_bytes(A.caps) + 63) & ~(size_t)63;
+        if (spill) grid = (int)std::max<i64>(1, std::min<i64>(grid, (i64)(scratch_budget_bytes() / (double)(gstride * (128 / G)))));
         (spill ? E.dp_scratch2 : E.dp_scratch).reserve(gstride * (size_t)grid * (128 / G));
         KArgs A3 = A; A3.scratch = (spill ? E.dp_scratch2 : E.dp_scratch).as<u8>(); A3.scratch_stride = gstride;
         CU_CHECK(cudaMemsetAsync(A3.work_ctr, 0, 8, E.st));
@@ -718,10 +811,11 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
     Caps caps = default_caps(maxlen), big = big_caps(maxlen, opt);
     E.ovf.reserve(n * 4 + 64); E.rec.reserve(n * sizeof(ReadRec) + 64); E.list.reserve(n * 4 + 64); E.small.reserve(4096);
     unsigned long long *d_small = E.small.as<unsigned long long>();   // [0]=work ctr, [1]=list count, [8..15]=pool used, [16..]=DevCounters
-    for (int attempt = 0; attempt < 6; ++attempt) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
         double sc = E.pool_scale;
         i64 cap[N_POOLS] = {(i64)(n * (seed2_enabled() ? SEED2_STRIDE + 8 : 24) * sc) + 65536, (i64)(n * 6 * sc) + 65536, (i64)(n * 24 * sc) + 65536, (i64)(n * 6 * sc) + 65536,
                             (i64)(n * 3 * sc) + 65536, (i64)(n * 12 * sc) + 65536, (i64)(n * 48 * sc) + 65536};
+        for (int k = 0; k < N_POOLS; ++k) cap[k] = std::max(cap[k], E.pool_min[k]);      // demand seen by an earlier, failed attempt
         E.p_intv.reserve(cap[POOL_INTV] * sizeof(Intv)); E.p_chain.reserve(cap[POOL_CHAIN] * sizeof(Chain)); E.p_seed.reserve(cap[POOL_SEED] * sizeof(Seed));
         E.p_reg.reserve(cap[POOL_REG] * sizeof(Reg)); E.p_hit.reserve(cap[POOL_HIT] * sizeof(b200_hit_t)); E.p_cigar.reserve(cap[POOL_CIGAR] * 4);
         E.p_md.reserve(cap[POOL_MD]);
@@ -738,6 +832,8 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         P.used = d_small + 8;
         { static int bal = getenv("B200_NO_BALANCE") ? 0 : 1; if (bal) { E.work.reserve(n * 4 + 64); A.B.work = E.work.as<u32>(); } }
         A.order = nullptr; A.n_work = n; A.work_ctr = d_small; A.ctrs = (DevCounters *)(d_small + 16);
+        E.retry_list.reserve(n * 4 + 64);
+        A.B.retry_list = E.retry_list.as<i32>(); A.B.n_retry = d_small + 3;
         {   // queue of hits that need a banded global alignment (drained by k_finalize_dp)
             size_t smem = (size_t)(128 / 8) * findp_smem_bytes(maxlen);
             static int dp_ok = getenv("B200_SCALAR_FINALIZE") ? 0 : 1;
@@ -750,7 +846,7 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         float ms4[4] = {0, 0, 0, 0};
         static int trace = getenv("B200_TRACE") ? 1 : 0;
         double tw0 = wall_now();
-        run_stages(E, A, false, ms4);
+        run_stages(E, A, 0, ms4);
         double tw1 = wall_now();
         // spill pass for reads that overflowed their scratch slot
         const u32 SCR = OVF_INTV | OVF_SEED | OVF_CHAIN | OVF_REG | OVF_OUT | OVF_SCRATCH;
@@ -759,21 +855,30 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         CU_CHECK(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, E.st));
         CU_CHECK(cudaStreamSynchronize(E.st));
         i64 n_sp = (i64)h_small[1];
-        if (n_sp) {
-            E.stats.n_overflow += (u64)n_sp;
-            KArgs S = A; S.caps = big; S.order = E.list.as<i32>(); S.n_work = n_sp;
-            CU_CHECK(cudaMemsetAsync(d_small + 2, 0, 8, E.st));       // the main pass's DP queue has been drained
+        for (int tier = 1; tier <= 2 && n_sp; ++tier) {
+            // tier 1: the spill pass (big slots); tier 2: reads that overflow even those (repeat-saturated: up to max_occ seeds
+            // per interval) get slots sized for the worst case the reference accepts, a warp at a time
+            if (tier == 1) E.stats.n_overflow += (u64)n_sp;
+            KArgs S = A; S.caps = tier == 1 ? big : big_caps(maxlen, opt, 2); S.order = E.list.as<i32>(); S.n_work = n_sp;
+            CU_CHECK(cudaMemsetAsync(d_small + 2, 0, 8, E.st));       // the previous pass's DP queue has been drained
             if (trace) {
                 std::vector<i32> lst(n_sp); std::vector<u32> fl(n);
                 CU_CHECK(cudaMemcpy(lst.data(), E.list.p, n_sp * 4, cudaMemcpyDeviceToHost));
                 CU_CHECK(cudaMemcpy(fl.data(), E.ovf.p, n * 4, cudaMemcpyDeviceToHost));
                 int cnt[8] = {0};
                 for (i64 k = 0; k < n_sp; ++k) for (int b = 0; b < 8; ++b) if (fl[lst[k]] >> b & 1) ++cnt[b];
-                fprintf(stderr, "[b200 trace] spill reasons: intv %d seed %d chain %d reg %d out %d scratch %d pool %d\n", cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], cnt[6]);
+                fprintf(stderr, "[b200 trace] spill tier %d reasons: intv %d seed %d chain %d reg %d out %d scratch %d pool %d\n", tier, cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], cnt[6]);
             }
             k_clear_list<<<(unsigned)((n_sp + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), E.list.as<i32>(), n_sp);
-            run_stages(E, S, true, ms4);
+            run_stages(E, S, tier, ms4);
             E.stats.n_launches += 1;
+            if (tier == 1) {        // anything left that is not a pool problem?
+                CU_CHECK(cudaMemsetAsync(d_small + 1, 0, 8, E.st));
+                k_list_ovf<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n, SCR, E.list.as<i32>(), d_small + 1);
+                CU_CHECK(cudaMemcpyAsync(h_small, d_small, sizeof(h_small), cudaMemcpyDeviceToHost, E.st));
+                CU_CHECK(cudaStreamSynchronize(E.st));
+                n_sp = (i64)h_small[1];
+            }
         }
         double tw2 = wall_now();
         // any read still flagged?  pool exhaustion => retry the chunk with larger pools; anything else is a hard limit
@@ -784,14 +889,22 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         E.stats.n_launches += 4;
         if (h_small[1]) {
             bool pool_full = false;
-            for (int k = 0; k < N_POOLS; ++k) if ((i64)h_small[8 + k] > cap[k]) pool_full = true;
-            if (pool_full) { E.pool_scale *= 2.0; continue; }
-            throw std::runtime_error("a read exceeds the supported working-set limits (seeds/chains/regions)");
+            // a full pool: the bump counter kept counting, so it tells what this attempt would have needed
+            for (int k = 0; k < N_POOLS; ++k)
+                if ((i64)h_small[8 + k] > cap[k]) { pool_full = true; E.pool_min[k] = std::max<i64>(2 * cap[k], (i64)h_small[8 + k] + (i64)h_small[8 + k] / 4 + 65536); }
+            if ((i64)h_small[2] > cap[POOL_HIT]) { pool_full = true; E.pool_min[POOL_HIT] = std::max<i64>(2 * cap[POOL_HIT], (i64)h_small[2] + 65536); }   // the DP job queue is sized like the hit pool
+            if (pool_full && attempt < 7) continue;
+            // A read that still does not fit (more than 2^22 seeds, or a pool that six doublings did not satisfy) is
+            // reported without hits instead of failing the whole batch: the other reads of the chunk are unaffected.
+            k_drop_reads<<<(unsigned)((h_small[1] + 255) / 256), 256, 0, E.st>>>(E.rec.as<ReadRec>(), E.list.as<i32>(), (i64)h_small[1]);
+            E.stats.n_failed += h_small[1];
+            set_error("b200_mem_align_batch: " + std::to_string((unsigned long long)h_small[1]) + " read(s) exceeded the working-set limits and are reported unaligned");
         }
         E.stats.ms_seed += ms4[0]; E.stats.ms_chain += ms4[1]; E.stats.ms_extend += ms4[2]; E.stats.ms_finalize += ms4[3];
         const unsigned long long *c = h_small + 16;
         E.stats.occ_blocks += c[0]; E.stats.sa_reads += c[1]; E.stats.ref_bytes += c[2]; E.stats.sw_cells += c[3]; E.stats.n_ext += c[4]; E.stats.n_global += c[5];
         E.stats.tab_lookups_lo += c[6]; E.stats.tab_lookups_hi += c[7];
+        E.stats.ext_fallback += h_small[3];
         // compact in read order
         E.nh.reserve(n * 8 + 8); E.nc.reserve(n * 8 + 8); E.nm.reserve(n * 8 + 8); E.oh.reserve(n * 8 + 16); E.oc.reserve(n * 8 + 16); E.om.reserve(n * 8 + 16);
         k_counts<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.rec.as<ReadRec>(), n, E.nh.as<i64>(), E.nc.as<i64>(), E.nm.as<i64>());
@@ -918,12 +1031,25 @@ int b200_batch_run(b200_batch_t *b, int *n_launches)
         memset(&E.stats, 0, sizeof(E.stats));
         CU_CHECK(cudaEventRecord(E.ev[6], E.st));
         i64 CH = chunk_reads(), bh = 0, bc = 0, bm = 0;
+        // Chunk plan: a quarter-size first chunk (the kernels start after a quarter of the first transfer) and a tapering tail
+        // (the result copy of the last chunk is the only one no kernel overlaps), full chunks in between.
+        std::vector<i64> plan;
+        {
+            i64 rem = b->n;
+            const i64 q = std::max<i64>(CH / 4, 1024);
+            static const int taper = getenv("B200_CHUNK_TAPER") ? atoi(getenv("B200_CHUNK_TAPER")) : 1;
+            if (!taper) { while (rem > 0) { i64 t = std::min(CH, rem); plan.push_back(t); rem -= t; } }
+            if (rem > CH) { plan.push_back(q); rem -= q; }
+            while (rem > CH + CH / 2) { plan.push_back(CH); rem -= CH; }
+            while (rem > q) { i64 t = std::max(q, (rem / 2 + 1023) & ~(i64)1023); if (t > rem) t = rem; plan.push_back(t); rem -= t; }
+            if (rem > 0) plan.push_back(rem);
+        }
         size_t ci = 0;
-        for (i64 r0 = 0; r0 < b->n; r0 += CH, ++ci) {
-            i64 n = std::min(CH, b->n - r0);
+        for (i64 r0 = 0; r0 < b->n; r0 += plan[ci], ++ci) {
+            i64 n = plan[ci];
             if (b->lazy) {
                 // issue the transfer of this chunk AND the next one (so the next one overlaps this chunk's kernels), encode this one
-                i64 upto = b->h_off[std::min(b->n, r0 + 2 * CH)] - b->h_off[0];
+                i64 upto = b->h_off[std::min(b->n, r0 + n + (ci + 1 < plan.size() ? plan[ci + 1] : 0))] - b->h_off[0];
                 if (upto > b->uploaded) {
                     CU_CHECK(cudaMemcpyAsync(b->lazy_ascii.as<u8>() + b->uploaded, b->lazy_src + b->uploaded, upto - b->uploaded, cudaMemcpyHostToDevice, E.st_copy));
                     b->uploaded = upto;

@@ -6,18 +6,23 @@
 #include "pipeline.cuh"
 #include "ksw_group.cuh"
 #include "ksw_reg.cuh"
+#include "ksw_wave.cuh"
 
 namespace b200 {
 
 // per-group shared memory: H[maxlen+2], E[maxlen+2] ints, then the read as bytes (maxlen, padded to 4)
 __host__ __device__ inline size_t group_smem_bytes(int maxlen) { return (size_t)(maxlen + 2) * 8 + (size_t)((maxlen + 4) & ~3); }
 
-// REG: the DP state lives in registers (ksw_reg.cuh; reads of at most G * EXT_REG_CMAX - 1 bases), else in shared memory (ksw_group.cuh)
+// MODE 0: DP state in shared memory (ksw_group.cuh); 1: in registers, row-synchronous (ksw_reg.cuh; reads of at most
+// G * EXT_REG_CMAX - 1 bases); 2: the packed 16-bit anti-diagonal wavefront (ksw_wave.cuh; H = the group's stream words;
+// *retry is set when an extension must be re-run by the row-synchronous kernel, the read is then abandoned)
 #define EXT_REG_CMAX 19
-template <int G, bool REG, class Ctr>
+template <int G, int MODE, class Ctr>
 __device__ void chain2aln_group(const GroupCtx<G> &g, const DevIndex &ix, const Opt &opt, const i8 *smat, int l_query, const u8 *query,
-                                const Seed *cs, int cn, int c_rid, float c_frac_rep, RegSink &av, u64 *srt, int *H, int *E, Ctr &ctr)
+                                const Seed *cs, int cn, int c_rid, float c_frac_rep, RegSink &av, u64 *srt, int *H, int *E, Ctr &ctr,
+                                bool *retry = nullptr)
 {
+    const bool REG = MODE != 0;
     int i, k, max_off[2], aw[2];
     i64 l_pac = ix.l_pac, rmax[2], tmp, max = 0;
     if (cn == 0) return;
@@ -112,7 +117,14 @@ __device__ void chain2aln_group(const GroupCtx<G> &g, const DevIndex &ix, const 
                     int prev = a.score;
                     aw[side] = opt.w << i;
                     TextSeqC rc(&ix, side ? rmax[0] + re : s.rbeg - 1, side ? 1 : -1);
-                    ExtResult r = extend2_reg<G, EXT_REG_CMAX>(g, ql, qs, tl, rc, smat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[side], pen, opt.zdrop, sc0, ctr);
+                    ExtResult r;
+                    if (MODE == 2) {
+                        if (!wave_eligible(ql, tl, sc0, opt.a, pen) ||
+                            !extend2_wave<G>(g, ql, qs, tl, rc, opt.a, opt.b, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[side], pen, opt.zdrop, sc0, (u32 *)H, r, ctr)) {
+                            *retry = true;
+                            return;
+                        }
+                    } else r = extend2_reg<G, EXT_REG_CMAX>(g, ql, qs, tl, rc, smat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[side], pen, opt.zdrop, sc0, ctr);
                     a.score = r.score; qle = r.qle; tle = r.tle; gtle = r.gtle; gscore = r.gscore; max_off[side] = r.max_off;
                     if (a.score == prev || max_off[side] < (aw[side] >> 1) + (aw[side] >> 2)) break;
                 }
@@ -175,10 +187,11 @@ __device__ void chain2aln_group(const GroupCtx<G> &g, const DevIndex &ix, const 
 }
 
 // One group handles read `rid`.  scratch: per-group slot in HBM (srt + region list); smem: per-group shared memory.
-template <int G, bool REG>
+template <int G, int MODE>
 __device__ void stage_extend_group(const GroupCtx<G> &g, const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid,
                                    u8 *scratch, u8 *smem, const i8 *smat, CtrLocal &ctr)
 {
+    const bool REG = MODE != 0;
     ReadRec &R = B.rec[rid];
     if (B.ovf[rid]) { if (g.gl == 0) { R.n_regs = 0; R.reg_off = 0; } return; }
     int len = (int)(B.seq_off[rid + 1] - B.seq_off[rid]);
@@ -198,8 +211,13 @@ __device__ void stage_extend_group(const GroupCtx<G> &g, const DevIndex &ix, con
     const Seed *os = B.pool.seeds + R.seed_off;
     int n_chains = R.n_chains;
     float frac = R.frac_rep;
+    bool retry = false;
     for (int i = 0; i < n_chains; ++i) {
-        chain2aln_group<G, REG>(g, ix, opt, smat, len, q, os + oc[i].head, oc[i].n, oc[i].rid, frac, av, srt, H, E, ctr);
+        chain2aln_group<G, MODE>(g, ix, opt, smat, len, q, os + oc[i].head, oc[i].n, oc[i].rid, frac, av, srt, H, E, ctr, &retry);
+        if (MODE == 2 && retry) {       // hand the read to the row-synchronous kernel (k_extend_group over B.retry_list)
+            if (g.gl == 0) { R.n_regs = 0; R.reg_off = 0; B.retry_list[atomicAdd(B.n_retry, 1ull)] = (i32)rid; }
+            return;
+        }
         if (av.overflow) { if (g.gl == 0) { B.ovf[rid] |= OVF_REG; R.n_regs = 0; R.reg_off = 0; } return; }
     }
     i64 off = 0;

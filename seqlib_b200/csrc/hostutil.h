@@ -42,16 +42,19 @@ inline Caps default_caps(int maxlen, bool tiny = false)
     return c;
 }
 
-inline Caps big_caps(int maxlen, const Opt &opt)
+// tier: 1 = the spill pass proper (up to 64 seeds per interval: every read of ordinary genomes), 2 = the last resort for
+// repeat-saturated reads (every interval may contribute opt.max_occ seeds, bwa/bwamem.c:300-313), run with a handful of threads
+inline Caps big_caps(int maxlen, const Opt &opt, int tier = 1)
 {
     Caps c;
     c.maxlen = maxlen;
     c.intv = 4 * maxlen + 64;
-    i64 ws = (i64)c.intv * std::min(opt.max_occ, 64) + 1024;
-    c.wseeds = (int)std::min<i64>(ws, 1 << 20);
+    i64 per = tier >= 2 ? std::max(opt.max_occ, 1) : std::min(std::max(opt.max_occ, 1), 64);
+    i64 ws = (i64)c.intv * per + 1024;
+    c.wseeds = (int)std::min<i64>(ws, tier >= 2 ? (1 << 22) : (1 << 20));
     c.wchains = c.wseeds;
     c.seeds = c.wseeds;
-    c.regs = std::min(c.seeds, 8192);
+    c.regs = std::min(c.seeds, tier >= 2 ? (1 << 20) : 8192);
     c.cigar = 2 * maxlen + 8;
     c.md = 4 * maxlen + 64;
     int w4 = opt.w << 2;

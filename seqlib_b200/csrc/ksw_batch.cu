@@ -11,6 +11,8 @@ namespace b200 {
 struct ExtArgs {
     const b200_ext_job_t *jobs; i64 n; const u8 *qp, *tp; i8 mat[25]; int o_del, e_del, o_ins, e_ins;
     b200_ext_out_t *out; EH *eh; int eh_stride; unsigned long long *cells; unsigned long long *work;
+    u8 *redo;          // wavefront kernel: jobs it hands back (1); group kernel: when set, only those jobs are run
+    int a, b;          // match / mismatch score when the matrix is bwa_fill_scmat(a, b), else a == 0
 };
 
 struct CellCtr { unsigned long long sw_cells, n_ext; };
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(128) k_ext_group(const __grid_constant__ ExtAr
         base = __shfl_sync(0xffffffffu, base, 0);
         if ((i64)base >= A.n) break;
         i64 i = (i64)base + lane / G;
-        if (i < A.n) {
+        if (i < A.n && (!A.redo || A.redo[i])) {
             const b200_ext_job_t j = A.jobs[i];
             for (int k = g.gl; k < j.qlen; k += G) q[k] = A.qp[j.q_off + k];
             g.sync();
@@ -76,6 +78,51 @@ __global__ void __launch_bounds__(128) k_ext_group(const __grid_constant__ ExtAr
     unsigned long long x = c.sw_cells;
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if (lane == 0) atomicAdd(A.cells, x);
+}
+
+// v3: the packed 16-bit anti-diagonal wavefront (ksw_wave.cuh), G lanes per job; jobs it cannot finish exactly are flagged in A.redo
+template <int G>
+__global__ void __launch_bounds__(128, 6) k_ext_wave(const __grid_constant__ ExtArgs A, int maxq)
+{
+    extern __shared__ __align__(16) u8 smem_raw[];
+    const int lane = threadIdx.x & 31, gib = threadIdx.x / G;
+    GroupCtx<G> g; g.gl = threadIdx.x % G;
+    g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    u32 *ehs = (u32 *)(smem_raw + (size_t)gib * (((size_t)(maxq + 2) * 4 + 15) & ~(size_t)15));
+    CellCtr c; c.sw_cells = 0; c.n_ext = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(A.work, (unsigned long long)(32 / G));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((i64)base >= A.n) break;
+        i64 i = (i64)base + lane / G;
+        if (i < A.n) {
+            const b200_ext_job_t j = A.jobs[i];
+            BytesSeq qs; qs.p = A.qp + j.q_off; qs.step = 1;
+            BytesSeq ts; ts.p = A.tp + j.t_off; ts.step = 1;
+            ExtResult r;
+            bool ok = A.a > 0 && wave_eligible(j.qlen, j.tlen, j.h0, A.a, j.end_bonus);
+            if (ok) ok = extend2_wave<G>(g, j.qlen, qs, j.tlen, ts, A.a, A.b, A.o_del, A.e_del, A.o_ins, A.e_ins, j.w, j.end_bonus, j.zdrop, j.h0, ehs, r, c);
+            if (g.gl == 0) {
+                A.redo[i] = ok ? 0 : 1;
+                if (ok) { b200_ext_out_t o; o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore; o.max_off = r.max_off; A.out[i] = o; }
+            }
+        }
+        __syncwarp();
+    }
+    unsigned long long x = c.sw_cells;
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) atomicAdd(A.cells, x);
+}
+
+template <int G>
+static void launch_ext_wave(const ExtArgs &A, int maxq, int sms)
+{
+    size_t smem = (size_t)(128 / G) * (((size_t)(maxq + 2) * 4 + 15) & ~(size_t)15);
+    CU_CHECK(cudaFuncSetAttribute(k_ext_wave<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per = 1;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ext_wave<G>, 128, smem));
+    k_ext_wave<G><<<sms * (per < 1 ? 1 : per), 128, smem>>>(A, maxq);
 }
 
 template <int G>
@@ -120,7 +167,20 @@ extern "C" int b200_ksw_extend2_batch(int64_t n, const b200_ext_job_t *jobs, con
         CU_CHECK(cudaEventRecord(e0));
         int G = getenv("B200_KSW_G") ? atoi(getenv("B200_KSW_G")) : 16;
         size_t need = (size_t)(128 / (G > 0 ? G : 1)) * group_smem_bytes(maxq);
-        if (G == 0 || need > 200 * 1024) k_ext_scalar<<<grid, 128>>>(A);
+        // default: the wavefront kernel first, then the row-synchronous group kernel over what it handed back
+        // (B200_KSW_WAVE=0: group kernel only -- its cell count is the reference's band-trimmed count)
+        const int WG = getenv("B200_KSW_WAVE") ? atoi(getenv("B200_KSW_WAVE")) : 4;
+        bool fill = mat[0] > 0 && mat[1] <= 0;
+        for (int x = 0; x < 4 && fill; ++x) for (int y = 0; y < 4; ++y) if (mat[x * 5 + y] != (x == y ? mat[0] : mat[1])) fill = false;
+        if (WG > 0 && fill && maxq <= WAVE_MAXQ && G != 0 && need <= 200 * 1024 && -mat[1] + mat[0] < 256) {
+            DevBuf dredo; dredo.reserve(n + 64);
+            A.redo = dredo.as<u8>(); A.a = mat[0]; A.b = -mat[1];
+            if (WG == 8) launch_ext_wave<8>(A, maxq, sms); else if (WG == 2) launch_ext_wave<2>(A, maxq, sms); else launch_ext_wave<4>(A, maxq, sms);
+            CU_CHECK(cudaMemsetAsync(A.work, 0, 8));
+            launch_ext_group<16>(A, maxq, sms);
+            CU_CHECK(cudaDeviceSynchronize());
+        }
+        else if (G == 0 || need > 200 * 1024) k_ext_scalar<<<grid, 128>>>(A);
         else if (G == 4) launch_ext_group<4>(A, maxq, sms);
         else if (G == 8) launch_ext_group<8>(A, maxq, sms);
         else if (G == 32) launch_ext_group<32>(A, maxq, sms);

@@ -214,12 +214,14 @@ struct WaveAcc {
     }
 };
 
+// the band adjustment of bwa/ksw.c:437-442.  (int)((double)x / e + 1.) == x / e + 1 in integers wherever the result exceeds 1
+// (they differ only for -1 < x / e < 0, where both are clamped to 1), so no double-precision division is needed.
 HD int wave_band(int qlen, int maxsc, int end_bonus, int o_del, int e_del, int o_ins, int e_ins, int w)
 {
-    int max_ins = (int)((double)(qlen * maxsc + end_bonus - o_ins) / e_ins + 1.);
+    int max_ins = (qlen * maxsc + end_bonus - o_ins) / e_ins + 1;
     max_ins = max_ins > 1 ? max_ins : 1;
     w = w < max_ins ? w : max_ins;
-    int max_del = (int)((double)(qlen * maxsc + end_bonus - o_del) / e_del + 1.);
+    int max_del = (qlen * maxsc + end_bonus - o_del) / e_del + 1;
     max_del = max_del > 1 ? max_del : 1;
     return w < max_del ? w : max_del;
 }
@@ -236,46 +238,53 @@ HD bool wave_eligible(int qlen, int tlen, int h0, int a, int end_bonus)
 // G lanes (GroupCtx<G>) run one extension; every lane returns the same result.  ehs: qlen + 2 words of shared memory owned
 // by the group.  Returns false on a gap event (result invalid, re-run with extend2_reg).
 template <int G, class GCtx, class QSeq, class TSeq, class Ctr>
-__device__ bool extend2_wave(const GCtx &g, int qlen, const QSeq &query, int tlen, const TSeq &target, int a, int b,
+__device__ __noinline__ bool extend2_wave(const GCtx &g, int qlen, const QSeq &query, int tlen, const TSeq &target, int a, int b,
                              int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
                              u32 *ehs, ExtResult &R, Ctr &ctr)
 {
     const int gl = g.gl;
     const WaveConst K = wave_const(a, b, o_del, e_del, o_ins, e_ins);
     w = wave_band(qlen, a, end_bonus, o_del, e_del, o_ins, e_ins, w);
+    u32 gapped = 0;
     for (int j = gl; j <= qlen; j += G) {        // eh[] after the reference's initialisation (bwa/ksw.c:428-432)
         int v = h0 - (o_ins + e_ins) - (j - 1) * e_ins;
         v = j == 0 ? h0 : (v > 0 ? v : 0);
-        ehs[j] = wave_word(v, 0, j < qlen ? (int)query[j] : 0, true);
+        const int q = j < qlen ? (int)query[j] : 0;
+        gapped |= q > 3 ? 1u : 0u;                // ambiguous bases score -1 against everything: not a match / mismatch matrix
+        ehs[j] = wave_word(v, 0, q & 3, true);
     }
     WaveAcc acc; acc.init(h0);
     int cb = 0, xprev = qlen;
     unsigned long long cells = 0;
-    u32 gapped = 0;
     g.sync();
     for (int r0 = 0; r0 < tlen && !acc.broke; r0 += 2 * G) {
         const int rl = r0 + 2 * gl;
         WaveLane L;
-        L.setup(rl, tlen, rl < tlen ? (int)target[rl] : 0, rl + 1 < tlen ? (int)target[rl + 1] : 0, cb, gl, w, qlen,
+        const int tb0 = rl < tlen ? (int)target[rl] : 0, tb1 = rl + 1 < tlen ? (int)target[rl + 1] : 0;
+        gapped |= (tb0 | tb1) > 3 ? 1u : 0u;
+        L.setup(rl, tlen, tb0 & 3, tb1 & 3, cb, gl, w, qlen,
                 cb == 0 ? wave_h1_init(h0, o_del, e_del, rl) : 0, cb == 0 ? wave_h1_init(h0, o_del, e_del, rl + 1) : 0);
         u32 oh = 0;
-        int cbn = 1 << 20;
-        for (int s = 0, smax = qlen + 2 - cb + 2 * G; s <= smax; ++s) {
-            u32 win = (u32)g.up((int)oh, 1);
-            if (gl == 0) {
-                const int j = L.jl;
-                win = (j >= cb && j <= qlen) ? ehs[j] : 0u;
-                win = j <= xprev ? win | 0x8000u : win & ~0x8000u;
-            }
-            const int jh = L.jl - 1;
-            oh = L.step(K, win);
-            if (gl == G - 1 && jh >= cb && jh <= qlen) {
-                ehs[jh] = oh;
-                if ((oh & 0x1fff3fffu) != 0 && jh < cbn) cbn = jh;
+        const int j0 = cb - 2 * gl;                      // column of this lane's low row at step 0
+        const bool first = gl == 0, last = gl == G - 1;
+        for (int s = 0, smax = qlen + 2 - cb + 2 * G; s <= smax; s += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + s + u;
+                u32 win = (u32)g.up((int)oh, 1);
+                // lane 0 takes the word of column j from shared memory; it is valid up to the previous row's last column
+                const u32 w0 = (ehs[j < qlen + 1 ? (j < 0 ? 0 : j) : qlen + 1] & ~0x8000u) | (j <= xprev ? 0x8000u : 0u);
+                win = first ? w0 : win;
+                oh = L.step(K, win);
+                if (last && j - 1 >= cb && j - 1 <= qlen) ehs[j - 1] = oh;
             }
             if (__all_sync(g.mask, L.DONE == 0xffffffffu)) break;
         }
         g.sync();
+        // the next block starts at the first non-zero column of the stream the last row left behind
+        int cbn = 1 << 20;
+        for (int j = cb + gl; j <= qlen; j += G) if ((ehs[j] & 0x1fff3fffu) != 0) { cbn = j; break; }
+        cbn = g.rmin(cbn);
         // commit the block's rows in order
         const u32 P2 = (u32)(u16)L.mj_lo | (u32)(u16)L.mj_hi << 16;
         gapped |= L.gap;
@@ -294,7 +303,6 @@ __device__ bool extend2_wave(const GCtx &g, int qlen, const QSeq &query, int tle
             }
         }
         xprev = (int)(((u32)g.bcast((int)L.XC, G - 1) >> 16) & 0xffffu);
-        cbn = g.bcast(cbn, G - 1);
         if (cbn < (1 << 20) && cbn > cb) cb = cbn;
     }
     gapped = (u32)g.rmax((int)(gapped != 0));

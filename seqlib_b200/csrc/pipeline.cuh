@@ -65,6 +65,7 @@ struct Batch {
     const i64 *hash_id;      // n_reads
     u32 *ovf;                // per read overflow bits
     u32 *work;               // optional: per read estimate of extension work (for load-balanced scheduling)
+    i32 *retry_list; unsigned long long *n_retry;    // reads the wavefront extension kernel hands to the row-synchronous one
     ReadRec *rec;            // per read
     Pools pool;
 };

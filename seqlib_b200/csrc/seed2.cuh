@@ -102,9 +102,11 @@ HD void extend_lean(const DevIndex &ix, u64 a, u64 o, u64 s, int c, u64 &na, u64
 // through the Occ blocks.  Written so that a warp issues ONE pair of 256-bit loads whatever its lanes need: a table
 // lane loads the 32-byte sector that holds its 16-byte entry (twice -- the second request merges in L1).
 // fwd: the caller extends forward (result coordinates swap roles, see SeedMachine::request).
+struct LoadPol { u64 keep, stream; int keep_level; };      // L2 eviction policies of the seeding kernel (device only)
+
 template <class Ctr>
 HD void extend_or_lookup(const DevIndex &ix, const SeedTab &tab, int tl, u32 key, bool fwd, u64 a, u64 o, u64 s, int c,
-                         u64 &na, u64 &no, u64 &ns, Ctr &ctr)
+                         u64 &na, u64 &no, u64 &ns, Ctr &ctr, const LoadPol *pol = nullptr)
 {
     const u64 k = a - 1, l = k + s;
     const u32 dk = k >= ix.primary, dl = l >= ix.primary;
@@ -118,8 +120,15 @@ HD void extend_or_lookup(const DevIndex &ix, const SeedTab &tab, int tl, u32 key
         p1 = p2 = (const OccBlock *)((uintptr_t)e & ~(uintptr_t)31);
         if (tl <= 10) ctr.tab_lo++; else ctr.tab_hi++;
     } else ctr.occ_blocks += bl != bk ? 2 : 1;
-    OccLoad b1 = load_block_at(p1);
-    OccLoad b2 = load_block_at(p2);
+    OccLoad b1, b2;
+    if (pol) {
+        const u64 py = tl && tl <= pol->keep_level ? pol->keep : pol->stream;
+        b1 = load_block_hint(p1, py);
+        b2 = load_block_hint(p2, py);
+    } else {
+        b1 = load_block_at(p1);
+        b2 = load_block_at(p2);
+    }
     extend_blocks(ix, b1, b2, kk, ll, dk, dl, o, c, na, no, ns);
     if (tl) {
         PIntv t;

@@ -223,6 +223,16 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
 
 } // namespace
 
+namespace detail {
+// test seam: the record assembly of alignSequence on regions that are already computed (tests/cxx/wraptest.cpp feeds it the
+// reference's own regions and compares the records with oracle/oracle_wrap.cpp)
+void RecordsFromRegions(const std::string &seq, const std::string &name, const b200_results_view_t &v, int64_t read, bool hardclip,
+                        double keepSecFrac, int maxSecondary, BamRecordPtrVector &out)
+{
+    emit_records(seq, name, v, read, hardclip, keepSecFrac, maxSecondary, false, out);
+}
+} // namespace detail
+
 void BWAAligner::alignSequence(const std::string &seq, const std::string &name, BamRecordPtrVector &out, bool hardclip,
                                double keepSecFrac, int maxSecondary) const
 {

@@ -9,7 +9,9 @@ import torch.distributed as dist
 
 
 def shard_bounds(n_total, world, rank):
-    """Contiguous shard [b, e) of rank; the first n_total % world ranks get one extra read."""
+    """Contiguous shard [b, e) of rank; the first n_total % world ranks get one extra read.
+    The same rule as b200_shard_bounds in the C ABI (seqlib_b200/csrc/dist.cu), which b200_reads_scatter and bench.py use;
+    tests/test_dist_cpu.py checks the two against each other."""
     q, r = divmod(n_total, world)
     b = rank * q + min(rank, r)
     return b, b + q + (1 if rank < r else 0)

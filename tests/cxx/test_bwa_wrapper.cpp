@@ -61,11 +61,12 @@ int main(int argc, char **argv)
     CHECK(!brv.empty());
     if (!brv.empty()) {
         CHECK(brv[0].Qname() == "name");
-        // equal-score hits on ref3 (forward) and ref5 (reverse): which one is primary is decided by hash_64(lrand48()+i);
-        // the reference test expects ChrID 2 on its own RNG stream, so accept either primary but require consistency
-        CHECK(brv[0].ChrID() == 2 || brv[0].ChrID() == 0);
-        if (brv[0].ChrID() == 2) CHECK(brv[0].Sequence() == "CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGCCATGT");
-        else CHECK(brv[0].Sequence() == "ACATGGCGAGCACTTCTAGCATCAGCTAGCTACGATCG");
+        // equal-score hits on ref3 (forward) and ref5 (reverse): which one is primary is decided by hash_64(lrand48()+i).
+        // This binary is a fresh process whose first lrand48() draws are those of ConstructIndex (one per N base and pass,
+        // src/BWAIndex.cpp:217) followed by mem_align1's (bwa/bwamem_extra.c:112) -- the stream on which the reference
+        // library, run the same way, makes ref5 the primary (checked with oracle/_ref), as seq_test/seq_test.cpp:898 asserts.
+        CHECK(brv[0].ChrID() == 2);
+        CHECK(brv[0].Sequence() == "CGATCGTAGCTAGCTGATGCTAGAAGTGCTCGCCATGT");
         CHECK(!brv[0].SecondaryFlag());
         CHECK(brv[0].GetCigar()[0].Type() == 'M');
         CHECK(brv[0].GetCigar()[0].Length() == 38);

@@ -43,21 +43,19 @@ static bool extend2_wave_emul(int G, int qlen, const u8 *query, int tlen, const 
             for (int gl = G - 1; gl >= 1; --gl) win[gl] = oh[gl - 1];          // shfl_up by one lane
             {
                 const int j = L[0].jl;
-                u32 v = (j >= cb && j <= qlen) ? ehs[j] : 0u;
-                win[0] = j <= xprev ? v | 0x8000u : v & ~0x8000u;
+                const u32 v = ehs[j < qlen + 1 ? (j < 0 ? 0 : j) : qlen + 1];
+                win[0] = (v & ~0x8000u) | (j <= xprev ? 0x8000u : 0u);
             }
             bool all_done = true;
             for (int gl = 0; gl < G; ++gl) {
                 const int jh = L[gl].jl - 1;
                 oh[gl] = L[gl].step(K, win[gl]);
-                if (gl == G - 1 && jh >= cb && jh <= qlen) {
-                    ehs[jh] = oh[gl];
-                    if ((oh[gl] & 0x1fff3fffu) != 0 && jh < cbn) cbn = jh;
-                }
+                if (gl == G - 1 && jh >= cb && jh <= qlen) ehs[jh] = oh[gl];
                 all_done = all_done && L[gl].DONE == 0xffffffffu;
             }
             if (all_done) break;
         }
+        for (int j = cb; j <= qlen; ++j) if ((ehs[j] & 0x1fff3fffu) != 0) { cbn = j; break; }
         for (int gl = 0; gl < G; ++gl) gapped |= L[gl].gap;
         for (int k = 0; k < 2 * G; ++k) {
             const WaveLane &S = L[k >> 1];

@@ -250,9 +250,9 @@ def _emul_lib():
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     so = os.path.join(here, "hostsim", "libemul.so")
-    srcs = [os.path.join(here, "hostsim", f) for f in ("group_emul.cpp", "reg_emul.cpp")]
+    srcs = [os.path.join(here, "hostsim", f) for f in ("group_emul.cpp", "reg_emul.cpp", "wave_emul.cpp")]
     csrc = os.path.join(here, "..", "seqlib_b200", "csrc")
-    deps = srcs + [os.path.join(csrc, f) for f in ("ksw.cuh", "ksw_reg.cuh", "common.cuh", "fmindex.cuh")]
+    deps = srcs + [os.path.join(csrc, f) for f in ("ksw.cuh", "ksw_reg.cuh", "ksw_wave.cuh", "common.cuh", "fmindex.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", so] + srcs)
     return C.CDLL(so)
@@ -285,3 +285,51 @@ def test_lane_cooperative_extend_equals_scalar(fn, G):
                              h0.ctypes.data_as(C.c_void_p), mat.ctypes.data_as(C.c_void_p), C.c_int(6), C.c_int(1), C.c_int(6), C.c_int(1), C.c_int(5),
                              C.c_int(zd), C.byref(first))
         assert bad == 0, (fn, G, zd, first.value)
+
+
+@pytest.mark.parametrize("G", [4, 8, 2])
+def test_wavefront_extend_equals_scalar(G):
+    """ksw_wave.cuh (packed 16-bit anti-diagonal wavefront: two target rows per lane, the column state streamed lane to
+    lane) emulated in lock step on the CPU with the kernel's own lane-step and commit code: every job it accepts gives the
+    scalar recurrence's six outputs; the jobs it hands back to the row-synchronous kernel (gap events) stay rare."""
+    import ctypes as C
+    L = _emul_lib()
+    mat = np.array(list(_opt_default().mat), dtype=np.int8)
+    sets = []
+    j, q, t = cases.c3_tuples_fast(4000)
+    sets.append((j, q, t, 100))
+    j, q, t = cases.mixed_tuples(30000)
+    q = np.minimum(q, 3).astype(np.uint8)
+    t = np.minimum(t, 3).astype(np.uint8)
+    for zd in (100, 0, 20):
+        sets.append((j[j["zdrop"] == zd], q, t, zd))
+    tot_run = tot_gap = 0
+    for jobs, qp, tp, zd in sets:
+        n = len(jobs)
+        ql = np.ascontiguousarray(jobs["qlen"], dtype=np.int32); tl = np.ascontiguousarray(jobs["tlen"], dtype=np.int32)
+        qo = np.ascontiguousarray(jobs["q_off"], dtype=np.int64); to = np.ascontiguousarray(jobs["t_off"], dtype=np.int64)
+        ws = np.ascontiguousarray(jobs["w"], dtype=np.int32); h0 = np.ascontiguousarray(jobs["h0"], dtype=np.int32)
+        first = C.c_long(-1); ngap = C.c_long(0); nrun = C.c_long(0); ratio = C.c_double(0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        bad = L.wave_emul_check(C.c_int(G), C.c_long(n), p(ql), p(tl), p(qo), p(to), p(qp), p(tp), p(ws), p(h0), p(mat),
+                                6, 1, 6, 1, 5, int(zd), C.byref(first), C.byref(ngap), C.byref(nrun), C.byref(ratio))
+        assert bad == 0, "first wrong job %d (zdrop %d)" % (first.value, zd)
+        assert 1.0 <= ratio.value < 1.25          # cells streamed vs the reference's band-trimmed cells
+        tot_run += nrun.value; tot_gap += ngap.value
+    assert tot_run > 30000 and tot_gap <= tot_run // 500
+
+
+def test_compare_prefix_detects_changes():
+    """parity.compare_prefix (the vectorised checker bench.py runs inside the headline measurement) agrees with the field-by-field one."""
+    import copy
+    gold, z = goldenlib.load("bcr_2k")
+    n = len(gold.hit_off) - 1
+    assert parity.compare_prefix(gold, gold, n) == (0, [])
+    g2 = copy.deepcopy(gold)
+    g2.cigar = g2.cigar.copy(); g2.cigar[5] ^= 16
+    bad, msgs = parity.compare_prefix(g2, gold, n)
+    assert bad == 1 and "cigar" in msgs[0]
+    g3 = copy.deepcopy(gold)
+    g3.hits = g3.hits.copy(); g3.hits["mapq"][7] += 1
+    bad, msgs = parity.compare_prefix(g3, gold, n)
+    assert bad == 1 and "mapq" in msgs[0]

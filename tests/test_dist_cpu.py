@@ -55,3 +55,12 @@ def test_shard_bounds_cover():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_c_abi_shard_bounds_match_python():
+    """b200_shard_bounds (the rule b200_reads_scatter and bench.py shard by) == seqlib_b200.shard.shard_bounds; no CUDA needed."""
+    from seqlib_b200 import shard, capi
+    for n in (0, 1, 7, 1000, 1001, 10_000_000, 100_000_003):
+        for w in (1, 2, 3, 4, 8):
+            for r in range(w):
+                assert capi.shard_bounds(n, w, r) == shard.shard_bounds(n, w, r)

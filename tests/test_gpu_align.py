@@ -242,3 +242,37 @@ def test_cxx_dropin_kat(capi, tmp_path):
                                "-Wl,-rpath," + os.path.join(root, "seqlib_b200")])
     r = subprocess.run([exe, str(tmp_path / "kat")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_tandem_repeat_reads_do_not_fail_the_batch(capi):
+    """Reads from a 700-copy tandem repeat: every SMEM interval holds more than max_occ = 500 positions, so a read makes
+    tens of thousands of seeds (bwa/bwamem.c:300-313) -- far beyond the main-pass slots.  They must go through the
+    spill pass (sized from opt.max_occ), give the reference's hits, and never fail the unique reads next to them."""
+    from oracle import pyref
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.Generator(np.random.PCG64(77))
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    unit = acgt[rng.integers(0, 4, 300)]
+    left = acgt[rng.integers(0, 4, 20000)]
+    right = acgt[rng.integers(0, 4, 20000)]
+    ref = np.concatenate([left, np.tile(unit, 700), right])
+    ref_ascii = ref.tobytes().decode()
+    reads = []
+    for k in range(24):                                   # inside the repeat, 2 % substitutions
+        p = 20000 + int(rng.integers(0, 300 * 699))
+        r = ref[p:p + 150].copy()
+        for q in np.nonzero(rng.random(150) < 0.02)[0]:
+            r[q] = acgt[(int(np.nonzero(acgt == r[q])[0][0]) + 1 + int(rng.integers(0, 3))) & 3]
+        reads.append(r.tobytes().decode())
+    for k in range(24):                                   # unique flanks and repeat boundaries
+        p = int(rng.choice([rng.integers(0, 19800), 19900 + rng.integers(0, 120), 20000 + 210000 - 80 + rng.integers(0, 60), 230000 + rng.integers(100, 19800)]))
+        reads.append(ref[p:p + 150].tobytes().decode())
+    ids = cases.ids_for(len(reads))
+    ridx = pyref.RefIndex.construct(["rep"], [ref_ascii])
+    exp, _ = pyref.align(ridx, reads, pyref.default_opt(), ids)
+    idx = capi.Index.construct(["rep"], [ref_ascii])
+    got = capi.align(idx, reads, capi.default_opt(), ids)
+    assert parity.compare_results(got, exp) == []
+    st = capi.last_stats()
+    assert st["n_overflow"] >= 20 and st["n_failed"] == 0
