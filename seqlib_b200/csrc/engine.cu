@@ -93,6 +93,7 @@ struct SmemList {
     uint4 *p;
     __device__ __forceinline__ PIntv get(int e) const { uint4 v = p[e * 128]; PIntv r; r.w0 = v.x; r.w1 = v.y; r.w2 = v.z; r.w3 = v.w; return r; }
     __device__ __forceinline__ void set(int e, const PIntv &r) { p[e * 128] = make_uint4(r.w0, r.w1, r.w2, r.w3); }
+    __device__ __forceinline__ u32 end(int e) const { return p[e * 128].w >> 16; }
 };
 struct SmemQuery {
     const u32 *p;
@@ -145,6 +146,9 @@ template <int CAP>
 __global__ void __launch_bounds__(128, 4) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride,
                                                   int keep_level)
 {
+    // Tried and dropped (round 2): keeping only the entries' ends in shared memory and the 16-byte intervals in an L2-resident
+    // global slot lifts the occupancy from 16 to 24 warps per SM -- and changes nothing (270 vs 264 ms per 10 M reads): the
+    // kernel is bound by the rate at which HBM serves random 128-byte line fills, not by the number of warps waiting for them.
     extern __shared__ uint4 seed_smem[];
     LoadPol pol; pol.keep_level = keep_level;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol.keep));
@@ -504,7 +508,7 @@ struct HostResults {
 
 struct Engine {
     int device = -1, sms = 148;
-    cudaStream_t st = nullptr, st_copy = nullptr;      // kernels / result copies that overlap the next chunk's kernels
+    cudaStream_t st = nullptr, st_copy = nullptr, st_up = nullptr;      // kernels / result copies (D2H) / read uploads (H2D) that overlap the kernels
     cudaEvent_t ev[8], ev_copy, ev_up;
     // chunk buffers
     DevBuf wave_scratch, retry_list, packed, packed4, seedflag, seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
@@ -523,6 +527,7 @@ struct Engine {
         CU_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
         CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CU_CHECK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+        CU_CHECK(cudaStreamCreateWithFlags(&st_up, cudaStreamNonBlocking));
         CU_CHECK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
         CU_CHECK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
         if (const char *g = getenv("B200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
@@ -943,7 +948,7 @@ static double wall_now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &t
 static i64 chunk_reads()
 {
     const char *e = getenv("B200_CHUNK");
-    i64 v = e ? atoll(e) : (1 << 20);
+    i64 v = e ? atoll(e) : (1 << 21);       // 2 M reads: ~3 ms of kernel tails per chunk argue for few, large chunks
     return v < 1024 ? 1024 : v;
 }
 
@@ -1037,7 +1042,7 @@ int b200_batch_run(b200_batch_t *b, int *n_launches)
         {
             i64 rem = b->n;
             const i64 q = std::max<i64>(CH / 4, 1024);
-            static const int taper = getenv("B200_CHUNK_TAPER") ? atoi(getenv("B200_CHUNK_TAPER")) : 1;
+            static const int taper = getenv("B200_CHUNK_TAPER") ? atoi(getenv("B200_CHUNK_TAPER")) : 0;   // measured: every extra chunk costs ~3 ms of kernel tails, more than the shorter head / tail copies save
             if (!taper) { while (rem > 0) { i64 t = std::min(CH, rem); plan.push_back(t); rem -= t; } }
             if (rem > CH) { plan.push_back(q); rem -= q; }
             while (rem > CH + CH / 2) { plan.push_back(CH); rem -= CH; }
@@ -1048,16 +1053,21 @@ int b200_batch_run(b200_batch_t *b, int *n_launches)
         for (i64 r0 = 0; r0 < b->n; r0 += plan[ci], ++ci) {
             i64 n = plan[ci];
             if (b->lazy) {
-                // issue the transfer of this chunk AND the next one (so the next one overlaps this chunk's kernels), encode this one
-                i64 upto = b->h_off[std::min(b->n, r0 + n + (ci + 1 < plan.size() ? plan[ci + 1] : 0))] - b->h_off[0];
+                // this chunk's bases must have been issued (chunk 0: now; later chunks: while the previous one ran); the kernels
+                // wait for exactly those copies -- the event is recorded BEFORE the next chunk's transfer is queued behind it
+                const i64 lo = b->h_off[r0] - b->h_off[0], hi = b->h_off[r0 + n] - b->h_off[0];
+                if (hi > b->uploaded) {
+                    CU_CHECK(cudaMemcpyAsync(b->lazy_ascii.as<u8>() + b->uploaded, b->lazy_src + b->uploaded, hi - b->uploaded, cudaMemcpyHostToDevice, E.st_up));
+                    b->uploaded = hi;
+                }
+                CU_CHECK(cudaEventRecord(E.ev_up, E.st_up));
+                CU_CHECK(cudaStreamWaitEvent(E.st, E.ev_up, 0));
+                // the next chunk's bases travel while this chunk's kernels run
+                const i64 upto = b->h_off[std::min(b->n, r0 + n + (ci + 1 < plan.size() ? plan[ci + 1] : 0))] - b->h_off[0];
                 if (upto > b->uploaded) {
-                    CU_CHECK(cudaMemcpyAsync(b->lazy_ascii.as<u8>() + b->uploaded, b->lazy_src + b->uploaded, upto - b->uploaded, cudaMemcpyHostToDevice, E.st_copy));
+                    CU_CHECK(cudaMemcpyAsync(b->lazy_ascii.as<u8>() + b->uploaded, b->lazy_src + b->uploaded, upto - b->uploaded, cudaMemcpyHostToDevice, E.st_up));
                     b->uploaded = upto;
                 }
-                i64 lo = b->h_off[r0] - b->h_off[0], hi = b->h_off[r0 + n] - b->h_off[0];
-                // the copy stream is in order: an event recorded now covers every piece issued so far
-                CU_CHECK(cudaEventRecord(E.ev_up, E.st_copy));
-                CU_CHECK(cudaStreamWaitEvent(E.st, E.ev_up, 0));
                 if (hi > lo) k_encode<<<E.sms * 4, 256, 0, E.st>>>(b->lazy_ascii.as<u8>() + lo, b->d_seq.as<u8>() + lo, hi - lo);
             }
             b200_batch::Chunk *c = ci < b->chunks.size() ? b->chunks[ci] : nullptr;
@@ -1156,6 +1166,11 @@ int b200_mem_align_batch(const b200_index_t *idx, const b200_mem_opt_t *opt, int
         b->sink = &H;
     } catch (const std::exception &e) { delete R; b200_batch_destroy(b); return fail(B200_ERR_NOMEM, e.what()); }
     rc = b200_batch_run(b, nullptr);
+    if (rc != B200_OK) {
+        // a failure in the middle of the stream: copies into R's pinned buffers / the batch's device buffers may still be
+        // in flight, and both go back to their pools below
+        try { Engine &E = engine(); cudaStreamSynchronize(E.st_up); cudaStreamSynchronize(E.st_copy); cudaStreamSynchronize(E.st); } catch (...) {}
+    }
     double t2 = wall_now();
     b->sink = nullptr;
     b200_batch_destroy(b);

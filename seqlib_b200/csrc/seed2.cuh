@@ -149,6 +149,7 @@ struct SeedMachine {
     u64 x0, x1, x2, lastcurr;     // ik of the forward sweeps / last size pushed in this backward row
     u64 p0, p1, p2;               // the list entry being extended backwards
     u32 iend, pend;
+    bool have_p;                  // p0..p2 hold the entry's interval (false: only its end was read)
     List L; Query q; IntvSink out;
 
     HD void init(const Opt &opt, int len_, int cap_, const List &L_, const Query &q_, const IntvSink &out_, int K_ = 0)
@@ -256,17 +257,32 @@ struct SeedMachine {
     {
         if (mode == M_BWD) {
             pintv_unpack(L.get(top + j), p0, p1, p2, pend);
+            have_p = true;
             a = p0; o = p1; s = p2; c = q[i];
         } else { a = x1; o = x0; s = x2; c = 3 - q[i]; }
     }
 
     // the same, plus the string the extension produces: q[st, st + ln).  tl = ln when a table level holds it, else 0.
+    // A backward step that a table answers needs only the END of its list entry (the string is q[i, end)): the entry's
+    // interval is fetched lazily, when the entry dies as an SMEM -- lists that keep intervals outside shared memory
+    // (k_seed2's HybridList) then touch them in a third of the steps only.
     HD void request(u64 &a, u64 &o, u64 &s, int &c, int &tl, u32 &key, bool &fwd)
     {
-        request(a, o, s, c);
         fwd = mode != M_BWD;
-        const int st = mode == M_BWD ? i : (mode == M_FWD ? sx : x);
-        const int ln = mode == M_BWD ? (int)pend - i : i + 1 - st;
+        if (mode == M_BWD) {
+            pend = L.end(top + j);
+            const int ln = (int)pend - i;
+            tl = ln <= K ? ln : 0;
+            c = q[i];
+            if (tl) { have_p = false; a = 1; o = 1; s = 0; key = q.key(i, ln); return; }
+            pintv_unpack(L.get(top + j), p0, p1, p2, pend);
+            have_p = true;
+            a = p0; o = p1; s = p2; key = 0u;
+            return;
+        }
+        a = x1; o = x0; s = x2; c = 3 - q[i];
+        const int st = mode == M_FWD ? sx : x;
+        const int ln = i + 1 - st;
         tl = ln <= K ? ln : 0;
         key = tl ? q.key(st, ln) : 0u;
     }
@@ -277,7 +293,11 @@ struct SeedMachine {
             if (ns < (u64)min_intv) {
                 if (ncurr == 0 && (first || i + 1 < last_start)) {
                     first = 0; last_start = i + 1;
-                    if ((int)pend - (i + 1) >= min_seed_len) { emit(p0, p1, p2, (u64)(i + 1) << 32 | pend); if (ovf) return; }
+                    if ((int)pend - (i + 1) >= min_seed_len) {
+                        if (!have_p) { u32 e_; pintv_unpack(L.get(top + j), p0, p1, p2, e_); have_p = true; }
+                        emit(p0, p1, p2, (u64)(i + 1) << 32 | pend);
+                        if (ovf) return;
+                    }
                 }
             } else if (ncurr == 0 || ns != lastcurr) {
                 L.set(top + ncurr, pintv_pack(na, no, ns, pend));
@@ -317,7 +337,12 @@ struct SeedMachine {
 };
 
 // plain-array list / byte query: the host emulation and the debug path
-struct ArrayList { PIntv *p; HD PIntv get(int e) const { return p[e]; } HD void set(int e, const PIntv &v) { p[e] = v; } };
+struct ArrayList {
+    PIntv *p;
+    HD PIntv get(int e) const { return p[e]; }
+    HD void set(int e, const PIntv &v) { p[e] = v; }
+    HD u32 end(int e) const { return p[e].w3 >> 16; }
+};
 struct ByteQuery {
     const u8 *p;
     HD int operator[](int i) const { return p[i]; }

@@ -1,5 +1,6 @@
 // Throughput of the drop-in C++ batch path: BWAAligner::alignSequences (b200_mem_align_batch + bam1_t packing on all host
 // threads, src/BWAAligner.cpp:151-247) next to the bare ABI call on the same reads.  usage: bench_align_sequences [ref_mb] [n_reads]
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -17,8 +18,13 @@ int main(int argc, char **argv)
     const size_t ref_len = (size_t)(argc > 1 ? atof(argv[1]) : 50.0) * 1000000, n = argc > 2 ? (size_t)atol(argv[2]) : 1000000, L = 150;
     std::string ref(ref_len, 'A');
     for (size_t i = 0; i < ref_len; ++i) ref[i] = "ACGT"[rnd() & 3];
+    // contigs of at most 125 Mb (bntann1_t.len is a 32-bit int, bwa/bntseq.h:38-46): 24 of them for the 3 Gb reference
     UnalignedSequenceVector refs;
-    refs.push_back(UnalignedSequence("chrS", ref));
+    const size_t n_ctg = std::max<size_t>(1, (ref_len + 124999999) / 125000000), per = ref_len / n_ctg;
+    for (size_t c = 0; c < n_ctg; ++c) {
+        const size_t b = c * per, e = c + 1 < n_ctg ? b + per : ref_len;
+        refs.push_back(UnalignedSequence("chrS" + std::to_string(c + 1), ref.substr(b, e - b)));
+    }
     BWAIndexPtr idx(new BWAIndex());
     auto t0 = std::chrono::steady_clock::now();
     idx->ConstructIndex(refs);
@@ -29,6 +35,7 @@ int main(int argc, char **argv)
     (void)comp;
     for (size_t i = 0; i < n; ++i) {
         size_t p = rnd() % (ref_len - L);
+        if (p / per != (p + L - 1) / per && p / per < n_ctg - 1) p -= L;      // keep the read inside one contig
         std::string s = ref.substr(p, L);
         for (size_t k = 0; k < L; ++k) if (rnd() % 100 == 0) s[k] = "ACGT"[(std::string("ACGT").find(s[k]) + 1 + rnd() % 3) & 3];
         if (rnd() & 1) {                // reverse complement

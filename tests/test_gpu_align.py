@@ -235,7 +235,8 @@ def test_cxx_dropin_kat(capi, tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "tests", "cxx", "test_bwa_wrapper")
-    if not os.path.exists(exe):
+    lib = os.path.join(root, "seqlib_b200", "libSeqLibB200.so")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(exe + ".cpp") or (os.path.exists(lib) and os.path.getmtime(exe) < os.path.getmtime(lib)):
         subprocess.check_call(["make", "-s", "-C", os.path.join(root, "seqlib_b200", "cxx")])
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(root, "include"), "-o", exe, exe + ".cpp",
                                "-L" + os.path.join(root, "seqlib_b200"), "-lSeqLibB200", "-lseqlib_b200",
