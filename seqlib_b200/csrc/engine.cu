@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(128, REG ? 4 : 3) k_extend_group(const __grid_
 // stage 2 as a packed 16-bit anti-diagonal wavefront (ksw_wave.cuh): G lanes per read, two target rows per lane, the
 // column state streamed lane to lane by warp shuffles.  Shared memory: (maxlen + 2) stream words per group.  Reads it
 // cannot finish exactly (gap events, N bases, scores beyond 13 bits) are appended to B.retry_list for k_extend_group.
-__host__ __device__ inline size_t wave_smem_bytes(int maxlen) { return ((size_t)(maxlen + 2) * 4 + 15) & ~(size_t)15; }
+static size_t wave_smem_bytes(int maxlen, int G) { return ((size_t)WAVE_WORDS(maxlen, G) * 4 + 15) & ~(size_t)15; }
 template <int G>
 __global__ void __launch_bounds__(128, 6) k_extend_wave(const __grid_constant__ KArgs A)
 {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(128, 6) k_extend_wave(const __grid_constant__ 
     GroupCtx<G> g;
     g.gl = threadIdx.x % G;
     g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    u8 *smem = smem_raw + (size_t)gib * wave_smem_bytes(A.caps.maxlen);
+    u8 *smem = smem_raw + (size_t)gib * ((((size_t)WAVE_WORDS(A.caps.maxlen, G) * 4) + 15) & ~(size_t)15);
     u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
     CtrLocal ctr;
     for (;;) {
@@ -581,7 +581,19 @@ static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
     if (per < 1) per = 1;
     { static const int occ = getenv("B200_OCC_SEED") ? atoi(getenv("B200_OCC_SEED")) : 0; if (occ > 0 && occ < per) per = occ; }
     // levels <= keep_level of the tables are loaded with an evict_last L2 policy, everything else evict_first (-1: no hints)
-    static const int keep_level = getenv("B200_SEED_KEEP") ? atoi(getenv("B200_SEED_KEEP")) : -1;   // measured: no effect on the L2 hit rate or the kernel time (profiles/r02_seed_l2hint_ab.txt)
+    static const int keep_level = getenv("B200_SEED_KEEP") ? atoi(getenv("B200_SEED_KEEP")) : -1;
+    {   // evict_last lines live in the persisting part of L2, which is empty unless a size is set for it
+        static bool once = false;
+        if (!once && keep_level >= 0) {
+            once = true;
+            int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, E.device);
+            size_t want = getenv("B200_L2_PERSIST_MB") ? (size_t)atol(getenv("B200_L2_PERSIST_MB")) << 20 : (size_t)maxp;
+            if (want > (size_t)maxp) want = (size_t)maxp;
+            cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            if (getenv("B200_TRACE")) fprintf(stderr, "[b200 trace] persisting L2: max %d MB, set %zu MB (%s)\n", maxp >> 20, want >> 20, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }   // measured: no effect on the L2 hit rate or the kernel time (profiles/r02_seed_l2hint_ab.txt)
     k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE, keep_level);
 }
 static void launch_seed2(Engine &E, KArgs &A)
@@ -640,7 +652,7 @@ static SeedTab seed_tables(Engine &E, const b200_index *idx)
 // the wavefront kernel computes scores as (match ? a : -b): the matrix must be what bwa_fill_scmat(a, b) makes (bwa/bwa.c:64-77)
 static bool wave_opt_ok(const Opt &o)
 {
-    if (o.a <= 0 || o.b < 0 || o.e_del <= 0 || o.e_ins <= 0 || o.o_del < 0 || o.o_ins < 0) return false;
+    if (o.a <= 0 || o.b < 1 || o.e_del <= 0 || o.e_ins <= 0 || o.o_del < 0 || o.o_ins < 0) return false;
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (o.mat[i * 5 + j] != (i == j ? o.a : -o.b)) return false;
     return o.a + o.b < 256 && o.o_del + o.e_del < 4000 && o.o_ins + o.e_ins < 4000;
 }
@@ -727,18 +739,18 @@ static void run_stages(Engine &E, KArgs A, int spill, float *ms4)
                 E.sort_keys.reserve(n * 4 + 64); E.sort_vals.reserve(n * 4 + 64); E.sort_vals2.reserve(n * 4 + 64);
                 k_iota32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.sort_vals.as<i32>(), n);
                 size_t tb = 0;
-                cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 20, E.st);
+                cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 24, E.st);
                 E.cubtmp.reserve(tb);
-                CU_CHECK(cub::DeviceRadixSort::SortPairsDescending(E.cubtmp.p, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 20, E.st));
+                CU_CHECK(cub::DeviceRadixSort::SortPairsDescending(E.cubtmp.p, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 24, E.st));
                 order = E.sort_vals2.as<i32>();
             }
             // main pass: the packed 16-bit wavefront kernel; what it hands back goes through the row-synchronous kernel below
-            static const int wave_g = getenv("B200_WAVE_G") ? atoi(getenv("B200_WAVE_G")) : 8;
+            static const int wave_g = getenv("B200_WAVE_G") ? atoi(getenv("B200_WAVE_G")) : 4;
             const bool use_wave = !spill && wave_g > 0 && wave_opt_ok(A.opt) && A.caps.maxlen <= WAVE_MAXQ && A.B.retry_list &&
                                   (long)A.caps.maxlen * A.opt.a * 2 + std::max(A.opt.pen_clip5, A.opt.pen_clip3) + 16 < 8000;
             if (use_wave) {
                 const int WG = wave_g == 8 ? 8 : wave_g == 2 ? 2 : 4;
-                size_t wsmem = (size_t)(128 / WG) * wave_smem_bytes(A.caps.maxlen);
+                size_t wsmem = (size_t)(128 / WG) * wave_smem_bytes(A.caps.maxlen, WG);
                 int per = 0;
                 if (WG == 8) { CU_CHECK(cudaFuncSetAttribute(k_extend_wave<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_wave<8>, 128, wsmem)); }
                 else if (WG == 2) { CU_CHECK(cudaFuncSetAttribute(k_extend_wave<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_wave<2>, 128, wsmem)); }

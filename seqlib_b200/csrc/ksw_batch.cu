@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128, 6) k_ext_wave(const __grid_constant__ Ext
     const int lane = threadIdx.x & 31, gib = threadIdx.x / G;
     GroupCtx<G> g; g.gl = threadIdx.x % G;
     g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    u32 *ehs = (u32 *)(smem_raw + (size_t)gib * (((size_t)(maxq + 2) * 4 + 15) & ~(size_t)15));
+    u32 *ehs = (u32 *)(smem_raw + (size_t)gib * (((size_t)WAVE_WORDS(maxq, G) * 4 + 15) & ~(size_t)15));
     CellCtr c; c.sw_cells = 0; c.n_ext = 0;
     for (;;) {
         unsigned long long base = 0;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128, 6) k_ext_wave(const __grid_constant__ Ext
 template <int G>
 static void launch_ext_wave(const ExtArgs &A, int maxq, int sms)
 {
-    size_t smem = (size_t)(128 / G) * (((size_t)(maxq + 2) * 4 + 15) & ~(size_t)15);
+    size_t smem = (size_t)(128 / G) * (((size_t)WAVE_WORDS(maxq, G) * 4 + 15) & ~(size_t)15);
     CU_CHECK(cudaFuncSetAttribute(k_ext_wave<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per = 1;
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ext_wave<G>, 128, smem));
@@ -170,7 +170,7 @@ extern "C" int b200_ksw_extend2_batch(int64_t n, const b200_ext_job_t *jobs, con
         // default: the wavefront kernel first, then the row-synchronous group kernel over what it handed back
         // (B200_KSW_WAVE=0: group kernel only -- its cell count is the reference's band-trimmed count)
         const int WG = getenv("B200_KSW_WAVE") ? atoi(getenv("B200_KSW_WAVE")) : 4;
-        bool fill = mat[0] > 0 && mat[1] <= 0;
+        bool fill = mat[0] > 0 && mat[1] <= -1;
         for (int x = 0; x < 4 && fill; ++x) for (int y = 0; y < 4; ++y) if (mat[x * 5 + y] != (x == y ? mat[0] : mat[1])) fill = false;
         if (WG > 0 && fill && maxq <= WAVE_MAXQ && G != 0 && need <= 200 * 1024 && -mat[1] + mat[0] < 256) {
             DevBuf dredo; dredo.reserve(n + 64);

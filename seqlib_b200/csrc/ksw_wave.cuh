@@ -31,6 +31,8 @@
 namespace b200 {
 
 #define WAVE_MAXQ 1023        // columns: stream words of one extension live in shared memory
+#define WAVE_PAD(G) (2 * (G) + 2)                 // guard words in front of column 0 (and, plus 8, behind column qlen)
+#define WAVE_WORDS(maxq, G) ((maxq) + 2 + 2 * WAVE_PAD(G) + 8)
 
 namespace wv {
 
@@ -90,12 +92,21 @@ HD u32 bmax(u32 a, u32 b, bool &ph, bool &pl)
     return pack16(pl ? lo16(a) : lo16(b), ph ? hi16(a) : hi16(b));
 #endif
 }
+HD u32 min2s(u32 a, u32 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vmins2(a, b);
+#else
+    return pack16(lo16(a) < lo16(b) ? lo16(a) : lo16(b), hi16(a) < hi16(b) ? hi16(a) : hi16(b));
+#endif
+}
 HD u32 sel(u32 m, u32 a, u32 b) { return (a & m) | (b & ~m); }     // one LOP3
 
 } // namespace wv
 
 struct WaveConst {           // per extension, the same in all lanes
-    u32 AB, NB;              // (a + b), (-b) in both halves
+    u32 A2, CSC;             // a in both halves; 65536 - (a + b): score = A2 + mismatch * CSC per half, one 32-bit IMAD (no carry crosses
+                             // the halves because b >= 1)
     u32 NOED, NED, NOEI, NEI;    // -(o_del + e_del), -e_del, -(o_ins + e_ins), -e_ins in both halves
 };
 
@@ -104,7 +115,7 @@ HD u32 wave_rep(int v) { return (u32)(u16)(i16)v * 0x00010001u; }
 HD WaveConst wave_const(int a, int b, int o_del, int e_del, int o_ins, int e_ins)
 {
     WaveConst K;
-    K.AB = wave_rep(a + b); K.NB = wave_rep(-b);
+    K.A2 = wave_rep(a); K.CSC = (u32)(65536 - (a + b));
     K.NOED = wave_rep(-(o_del + e_del)); K.NED = wave_rep(-e_del);
     K.NOEI = wave_rep(-(o_ins + e_ins)); K.NEI = wave_rep(-e_ins);
     return K;
@@ -161,10 +172,10 @@ struct WaveLane {
         WATCH |= TERM & ~AFT & INV & NFZ;
         GH = LEGIT & ~SURE;
         // the cell (bwa/ksw.c:455-482)
-        const u32 MATCH = signmask(add2(Q ^ T, 0xffffffffu));
-        const u32 SC = add2(MATCH & K.AB, K.NB);
-        const u32 ZH = signmask(add2(HIN, 0xffffffffu));
-        const u32 M = add2(HIN, SC) & ~ZH;
+        // score = a or -b per half; M = H(i-1,j-1) + score where H(i-1,j-1) != 0, else min(score, 0) -- a non-positive M is
+        // as good as the reference's 0 everywhere it is used (max with E, F >= 0; the relu of the E / F updates)
+        const u32 SC = min2s(Q ^ T, 0x00010001u) * K.CSC + K.A2;
+        const u32 M = min2s(add2(HIN, SC), min2s(HIN, 0x00010001u) * 0x7fffu);
         const u32 H = max3s(M, EIN, F);
         const u32 En = addmax_relu(M, K.NOED, add2(EIN, K.NED));
         const u32 Fn = addmax_relu(M, K.NOEI, add2(F, K.NEI));
@@ -174,7 +185,8 @@ struct WaveLane {
         mj_hi = ph ? jl - 1 : mj_hi;
         // outputs: computed cell -> {h1, E'}; terminal -> {h1, 0}; otherwise the incoming word (valid bit dropped once done)
         const u32 WR = LEGIT | TERMW;
-        const u32 OA = sel(WR, H1 | 0x80008000u, A & ~(DONE | TERM) & 0x80008000u | (A & 0x7fff7fffu));
+        // (the valid bit of a word is exactly "this row wrote it": columns left of a row's start are never examined by the rows below)
+        const u32 OA = (sel(WR, H1, A) & 0x7fff7fffu) | (WR & 0x80008000u);
         const u32 OB = sel(LEGIT, En, EIN & ~TERMW) | (B & 0xe000e000u);
         XC = sel(WR, J, XC);
         H1 = sel(LEGIT, H, H1);
@@ -231,7 +243,7 @@ HD int wave_h1_init(int h0, int o_del, int e_del, int row) { int v = h0 - (o_del
 // can this extension run on the wavefront kernel?  (a, b: match / mismatch of the matrix)
 HD bool wave_eligible(int qlen, int tlen, int h0, int a, int end_bonus)
 {
-    return qlen >= 1 && qlen <= WAVE_MAXQ && tlen < 30000 && a > 0 && h0 + qlen * a + end_bonus < 8000;
+    return qlen >= 1 && qlen <= WAVE_MAXQ && tlen < 30000 && a > 0 && h0 + qlen * a + end_bonus < 8000;      // (b >= 1: checked once per batch)
 }
 
 #if defined(__CUDACC__)
@@ -246,12 +258,13 @@ __device__ __noinline__ bool extend2_wave(const GCtx &g, int qlen, const QSeq &q
     const WaveConst K = wave_const(a, b, o_del, e_del, o_ins, e_ins);
     w = wave_band(qlen, a, end_bonus, o_del, e_del, o_ins, e_ins, w);
     u32 gapped = 0;
-    for (int j = gl; j <= qlen; j += G) {        // eh[] after the reference's initialisation (bwa/ksw.c:428-432)
+    u32 *const E = ehs + WAVE_PAD(G);             // column j at E[j]; guard words on both sides (pipeline fill / drain touches them)
+    for (int j = gl - WAVE_PAD(G); j <= qlen + WAVE_PAD(G) + 8; j += G) {        // eh[] after the reference's initialisation (bwa/ksw.c:428-432)
         int v = h0 - (o_ins + e_ins) - (j - 1) * e_ins;
         v = j == 0 ? h0 : (v > 0 ? v : 0);
-        const int q = j < qlen ? (int)query[j] : 0;
+        const int q = j >= 0 && j < qlen ? (int)query[j] : 0;
         gapped |= q > 3 ? 1u : 0u;                // ambiguous bases score -1 against everything: not a match / mismatch matrix
-        ehs[j] = wave_word(v, 0, q & 3, true);
+        E[j] = j >= 0 && j <= qlen ? wave_word(v, 0, q & 3, true) : 0u;
     }
     WaveAcc acc; acc.init(h0);
     int cb = 0, xprev = qlen;
@@ -265,25 +278,27 @@ __device__ __noinline__ bool extend2_wave(const GCtx &g, int qlen, const QSeq &q
         L.setup(rl, tlen, tb0 & 3, tb1 & 3, cb, gl, w, qlen,
                 cb == 0 ? wave_h1_init(h0, o_del, e_del, rl) : 0, cb == 0 ? wave_h1_init(h0, o_del, e_del, rl + 1) : 0);
         u32 oh = 0;
-        const int j0 = cb - 2 * gl;                      // column of this lane's low row at step 0
         const bool first = gl == 0, last = gl == G - 1;
+        u32 *pj = E + (cb - 2 * gl);                     // the word of this lane's low-row column
         for (int s = 0, smax = qlen + 2 - cb + 2 * G; s <= smax; s += 4) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int j = j0 + s + u;
                 u32 win = (u32)g.up((int)oh, 1);
-                // lane 0 takes the word of column j from shared memory; it is valid up to the previous row's last column
-                const u32 w0 = (ehs[j < qlen + 1 ? (j < 0 ? 0 : j) : qlen + 1] & ~0x8000u) | (j <= xprev ? 0x8000u : 0u);
+                const u32 w0 = *pj;                      // lane 0 takes its word from shared memory (valid bits are kept right there)
                 win = first ? w0 : win;
                 oh = L.step(K, win);
-                if (last && j - 1 >= cb && j - 1 <= qlen) ehs[j - 1] = oh;
+                if (last) pj[-1] = oh;
+                ++pj;
             }
             if (__all_sync(g.mask, L.DONE == 0xffffffffu)) break;
         }
         g.sync();
+        xprev = (int)(((u32)g.bcast((int)L.XC, G - 1) >> 16) & 0xffffu);
+        // words beyond the last row's extent that this block did not stream keep an old valid bit: drop it
+        for (int j = xprev + 1 + gl; j <= qlen; j += G) E[j] &= ~0x8000u;
         // the next block starts at the first non-zero column of the stream the last row left behind
         int cbn = 1 << 20;
-        for (int j = cb + gl; j <= qlen; j += G) if ((ehs[j] & 0x1fff3fffu) != 0) { cbn = j; break; }
+        for (int j = cb + gl; j <= qlen; j += G) if ((E[j] & 0x1fff3fffu) != 0) { cbn = j; break; }
         cbn = g.rmin(cbn);
         // commit the block's rows in order
         const u32 P2 = (u32)(u16)L.mj_lo | (u32)(u16)L.mj_hi << 16;
@@ -302,8 +317,8 @@ __device__ __noinline__ bool extend2_wave(const GCtx &g, int qlen, const QSeq &q
                 acc.commit(row, lo, m, mj, x, h1, qlen, zdrop, e_del, e_ins);
             }
         }
-        xprev = (int)(((u32)g.bcast((int)L.XC, G - 1) >> 16) & 0xffffu);
         if (cbn < (1 << 20) && cbn > cb) cb = cbn;
+        g.sync();
     }
     gapped = (u32)g.rmax((int)(gapped != 0));
     if (gl == 0) { ctr.sw_cells += cells; ctr.n_ext++; }

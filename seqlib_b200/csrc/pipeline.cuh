@@ -219,9 +219,10 @@ HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const 
     R.n_chains = n; R.n_seeds = ns; R.chain_off = coff; R.seed_off = soff;
     R.frac_rep = (float)l_rep / len;
     if (B.work) {
-        // Scheduling hint only (20 bits, sorted descending): the extension kernel runs four reads per warp in lock step
-        // and a row costs what the widest of the four queries costs, so reads are grouped by the column counts of the
-        // first seed chain2aln will extend (left side first, then right), then by the query bases left over all seeds.
+        // Scheduling hint only (24 bits, sorted descending): the extension kernel runs several reads per warp in lock step, and
+        // its groups stay together only while their DP problems have the same shape.  The shape of an extension is its query
+        // length (the target window follows from it), so reads are grouped by the EXACT query lengths of the first seed
+        // chain2aln will extend (left side first, then right), then by the query bases left over all seeds.
         u32 est = 0;
         for (int i = 0; i < ns; ++i) est += (u32)(len - os[i].len);
         u32 first = 0, second = 0;
@@ -230,13 +231,12 @@ HD void stage_chain(const DevIndex &ix, const Opt &opt, const Caps &caps, const 
             int best = 0;
             for (int i = 1; i < oc[0].n; ++i) if (cs[i].score >= cs[best].score) best = i;
             u32 ql = (u32)cs[best].qbeg, qr = (u32)(len - cs[best].qbeg - cs[best].len);
-            u32 cl = ql ? (ql + 8) >> 3 : 0, cr = qr ? (qr + 8) >> 3 : 0;
-            first = cl ? cl : cr; second = cl ? cr : 0;
-            if (first > 31) first = 31;
-            if (second > 31) second = 31;
+            first = ql ? ql : qr; second = ql ? qr : 0;
+            if (first > 255) first = 255;
+            if (second > 255) second = 255;
         }
         est >>= 2;
-        B.work[rid] = first << 15 | second << 10 | (est < 1023u ? est : 1023u);
+        B.work[rid] = first << 16 | second << 8 | (est < 255u ? est : 255u);
     }
 }
 

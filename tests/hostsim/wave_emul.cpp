@@ -19,7 +19,9 @@ static bool extend2_wave_emul(int G, int qlen, const u8 *query, int tlen, const 
 {
     const WaveConst K = wave_const(a, b, o_del, e_del, o_ins, e_ins);
     w = wave_band(qlen, a, end_bonus, o_del, e_del, o_ins, e_ins, w);
-    std::vector<u32> ehs(qlen + 2);
+    const int PAD = WAVE_PAD(G);
+    std::vector<u32> ehs_store(WAVE_WORDS(qlen, G), 0u);
+    u32 *const ehs = ehs_store.data() + PAD;                 // column j at ehs[j], guard words on both sides
     for (int j = 0; j <= qlen; ++j) {
         int v = h0 - (o_ins + e_ins) - (j - 1) * e_ins;
         v = j == 0 ? h0 : (v > 0 ? v : 0);
@@ -41,20 +43,18 @@ static bool extend2_wave_emul(int G, int qlen, const u8 *query, int tlen, const 
         int cbn = 1 << 20;
         for (int s = 0, smax = qlen + 2 - cb + 2 * G; s <= smax; ++s) {
             for (int gl = G - 1; gl >= 1; --gl) win[gl] = oh[gl - 1];          // shfl_up by one lane
-            {
-                const int j = L[0].jl;
-                const u32 v = ehs[j < qlen + 1 ? (j < 0 ? 0 : j) : qlen + 1];
-                win[0] = (v & ~0x8000u) | (j <= xprev ? 0x8000u : 0u);
-            }
+            win[0] = ehs[L[0].jl];
             bool all_done = true;
             for (int gl = 0; gl < G; ++gl) {
                 const int jh = L[gl].jl - 1;
                 oh[gl] = L[gl].step(K, win[gl]);
-                if (gl == G - 1 && jh >= cb && jh <= qlen) ehs[jh] = oh[gl];
+                if (gl == G - 1) ehs[jh] = oh[gl];
                 all_done = all_done && L[gl].DONE == 0xffffffffu;
             }
             if (all_done) break;
         }
+        const int xnew = (int)((L[G - 1].XC >> 16) & 0xffffu);
+        for (int j = xnew + 1; j <= qlen; ++j) ehs[j] &= ~0x8000u;
         for (int j = cb; j <= qlen; ++j) if ((ehs[j] & 0x1fff3fffu) != 0) { cbn = j; break; }
         for (int gl = 0; gl < G; ++gl) gapped |= L[gl].gap;
         for (int k = 0; k < 2 * G; ++k) {
