@@ -20,7 +20,6 @@
 #include <time.h>
 #include "engine.cuh"
 #include "extend_group.cuh"
-#include "extend_lane.cuh"
 #include "finalize_group.cuh"
 
 using namespace b200;
@@ -124,22 +123,6 @@ __global__ void k_pack_reads(const u8 *__restrict__ seq, const i64 *__restrict__
     }
     packed[t] = v;
     if (n_base || (w == 0 && len > (i64)qw * 16)) atomicOr(bad + r, 1u);
-}
-
-// 4-bit codes of every read, 8 per word, qw4 words per read (extend_lane.cuh copies them to shared memory at claim time)
-__global__ void k_pack_reads4(const u8 *__restrict__ seq, const i64 *__restrict__ off, i64 n, int qw4, u32 *__restrict__ packed)
-{
-    i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * qw4) return;
-    i64 r = t / qw4; int w = (int)(t - r * qw4);
-    i64 b = off[r], len = off[r + 1] - b;
-    u32 v = 0;
-    for (int k = 0; k < 8; ++k) {
-        i64 i = (i64)w * 8 + k;
-        if (i >= len) break;
-        v |= (u32)(seq[b + i] & 7) << (4 * k);
-    }
-    packed[t] = v;
 }
 
 template <int CAP>
@@ -290,57 +273,6 @@ __global__ void __launch_bounds__(128, 6) k_extend_wave(const __grid_constant__ 
         }
         __syncwarp();
     }
-    flush_counters(ctr, A.ctrs);
-}
-
-// stage 2 with ONE lane per read (extend_lane.cuh): blocks of one warp; shared memory = (maxlen + 2) column words per lane,
-// then the lanes' control state.  Every lane runs its own read/problem/row; the loop body is "one band cell" for whoever
-// has one.  Lanes that need a row change wait until `batch` of them do, lanes that need the (global-memory bound)
-// mem_chain2aln control step until `cbatch` of them do -- or until nothing else can make progress.
-#define LANE_CTL_WORDS ((((int)((sizeof(LaneCtl) + 7) / 8)) | 1) * 2)      // an odd number of 8-byte units: aligned, and at most 2-way bank conflicts
-static int lane_qw4(int maxlen) { return (((maxlen + 7) / 8) + 3) & ~3; }
-static int lane_cols(int maxlen) { return maxlen + 2 * LANE_U; }     // the look-ahead loads reach column qlen + 2 * LANE_U - 2
-static size_t lane_smem_bytes(int maxlen) { return ((size_t)lane_cols(maxlen) * 32 + (size_t)lane_qw4(maxlen) * 32 + (size_t)LANE_CTL_WORDS * 32) * sizeof(u32); }
-
-__global__ void __maxnreg__(168) k_extend_lane(const __grid_constant__ KArgs A, const u32 *__restrict__ packed4, const int batch, const int cbatch)
-{
-    extern __shared__ __align__(16) u32 lane_smem[];
-    __shared__ u32 rows[8];
-    if (threadIdx.x == 0) lane_fill_rows(A.opt, rows);
-    __syncwarp();
-    const int lane = threadIdx.x;
-    const int ncols = A.caps.maxlen + 2 * LANE_U, qw4 = (((A.caps.maxlen + 7) / 8) + 3) & ~3;
-    LaneEnv E; E.ix = &A.ix; E.opt = &A.opt; E.caps = &A.caps; E.B = &A.B; E.work_ctr = A.work_ctr; E.n_work = A.n_work; E.order = A.order;
-    E.packed4 = packed4; E.qw4 = qw4;
-    u32 *qwords = lane_smem + (size_t)ncols * 32;
-    LaneCtl &c = *reinterpret_cast<LaneCtl *>(qwords + (size_t)qw4 * 32 + (size_t)lane * LANE_CTL_WORDS);
-    c.setup(E, A.scratch + (size_t)(blockIdx.x * 32 + lane) * A.scratch_stride);
-    LaneDP<32> d;
-    d.cbase = (u32)__cvta_generic_to_shared(lane_smem + lane);
-    d.cols = nullptr;
-    d.q.qbase = (u32)__cvta_generic_to_shared(qwords + lane); d.q.qbuf = nullptr;
-    d.setup(A.opt, A.ix.text, (i64)A.ix.seq_len, rows);
-    for (;;) {
-        if (d.st == LS_CELL) d.cell_step();
-        else if (d.st == LS_INIT) d.init_step();
-        const unsigned rowm = __ballot_sync(0xffffffffu, d.st == LS_ROW);
-        const unsigned ctlm = __ballot_sync(0xffffffffu, d.st == LS_CTL);
-        if (rowm | ctlm) {
-            const bool idle = !__any_sync(0xffffffffu, d.st < LS_ROW);
-            if (rowm && (__popc(rowm) >= batch || idle)) {
-                if (d.st == LS_ROW) d.row_step();
-            } else if (ctlm && (__popc(ctlm) >= cbatch || (idle && rowm == 0))) {
-                if (d.st == LS_CTL) {
-                    DpIn in;
-                    if (c.advance(E, d.q, d.out(), in)) d.start(in);
-                    else d.st = LS_DEAD;
-                }
-                if (__all_sync(0xffffffffu, d.st == LS_DEAD)) break;
-            }
-        }
-    }
-    CtrLocal ctr;
-    ctr.sw_cells = d.cells; ctr.n_ext = c.n_ext; ctr.ref_bytes = c.ref_bytes;
     flush_counters(ctr, A.ctrs);
 }
 
@@ -511,7 +443,7 @@ struct Engine {
     cudaStream_t st = nullptr, st_copy = nullptr, st_up = nullptr;      // kernels / result copies (D2H) / read uploads (H2D) that overlap the kernels
     cudaEvent_t ev[8], ev_copy, ev_up;
     // chunk buffers
-    DevBuf wave_scratch, retry_list, packed, packed4, seedflag, seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
+    DevBuf wave_scratch, retry_list, packed, seedflag, seq_ascii, seq, seq_off, ids, ovf, rec, list, log_tab, scratch, spill_scratch, group_scratch, group_scratch2, dp_scratch, dp_scratch2, dp_jobs, sort_keys, sort_vals, sort_vals2, work, small;
     DevBuf p_intv, p_chain, p_seed, p_reg, p_hit, p_cigar, p_md;
     DevBuf nh, nc, nm, oh, oc, om, cubtmp, o_hit_off, o_hits, o_cigar, o_md;
     double pool_scale = 1.0;
@@ -594,6 +526,21 @@ static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
             cudaGetLastError();
         }
     }   // measured: no effect on the L2 hit rate or the kernel time (profiles/r02_seed_l2hint_ab.txt)
+    static const int win_level = getenv("B200_SEED_WINDOW") ? atoi(getenv("B200_SEED_WINDOW")) : 0;
+    if (win_level > 0 && A.tab.K > 0) {      // experiment: an access-policy window that makes the low table levels persisting L2 lines
+        int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, E.device);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
+        cudaStreamAttrValue attr; memset(&attr, 0, sizeof(attr));
+        const int lv = std::min(win_level, A.tab.K);
+        attr.accessPolicyWindow.base_ptr = (void *)A.tab.base;
+        attr.accessPolicyWindow.num_bytes = (size_t)seedtab_level_off(lv + 1) * sizeof(PIntv);
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaError_t e = cudaStreamSetAttribute(E.st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        if (getenv("B200_TRACE")) fprintf(stderr, "[b200 trace] access policy window: %zu MB persisting (%s)\n", attr.accessPolicyWindow.num_bytes >> 20, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
     k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE, keep_level);
 }
 static void launch_seed2(Engine &E, KArgs &A)
@@ -697,41 +644,7 @@ static void run_stages(Engine &E, KArgs A, int spill, float *ms4)
         const bool use_reg = reg_ok && A.caps.maxlen + 1 <= G * EXT_REG_CMAX;      // DP state in registers (ksw_reg.cuh)
         size_t smem = use_reg ? 0 : (size_t)(128 / G) * group_smem_bytes(A.caps.maxlen);
         static int group_ok = getenv("B200_SCALAR_EXTEND") ? 0 : 1;
-        // opt-in: measured 37.7-40 ms per 10^6 reads against 35.5 ms for the group kernel (profiles/r01_ncu_full_extend_lane_v1.txt)
-        static int lane_ok = getenv("B200_EXTEND_LANE") ? 1 : 0;
-        if (group_ok && lane_ok && lane_extend_eligible(A.opt, A.caps.maxlen)) {
-            // one lane per read (extend_lane.cuh); longer reads / larger scores take the group kernel below
-            static const int batch = getenv("B200_LANE_BATCH") ? atoi(getenv("B200_LANE_BATCH")) : 4;
-            static const int cbatch = getenv("B200_LANE_CBATCH") ? atoi(getenv("B200_LANE_CBATCH")) : 4;
-            size_t lsmem = lane_smem_bytes(A.caps.maxlen);
-            int per = 0;
-            CU_CHECK(cudaFuncSetAttribute(k_extend_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
-            CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_extend_lane, 32, lsmem));
-            if (per < 1) per = 1;
-            { static const int occ = getenv("B200_OCC_EXT") ? atoi(getenv("B200_OCC_EXT")) : 0; if (occ > 0 && occ < per) per = occ; }
-            int grid = (int)std::min<i64>((i64)E.sms * per, std::max<i64>(1, (A.n_work + 31) / 32));
-            size_t gstride = (extend_lane_scratch_bytes(A.caps) + 63) & ~(size_t)63;
-            (spill ? E.group_scratch2 : E.group_scratch).reserve(gstride * (size_t)grid * 32);
-            KArgs A2 = A; A2.scratch = (spill ? E.group_scratch2 : E.group_scratch).as<u8>(); A2.scratch_stride = gstride;
-            static const int lane_sort = getenv("B200_LANE_NOSORT") ? 0 : 1;
-            if (lane_sort && !spill && A.B.work && !A.order) {       // heaviest reads first: lanes claim reads one by one, so this only shortens the tail
-                i64 n = A.n_work;
-                E.sort_keys.reserve(n * 4 + 64); E.sort_vals.reserve(n * 4 + 64); E.sort_vals2.reserve(n * 4 + 64);
-                k_iota32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.sort_vals.as<i32>(), n);
-                size_t tb = 0;
-                cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 10, E.st);
-                E.cubtmp.reserve(tb);
-                CU_CHECK(cub::DeviceRadixSort::SortPairsDescending(E.cubtmp.p, tb, A.B.work, E.sort_keys.as<u32>(), E.sort_vals.as<i32>(), E.sort_vals2.as<i32>(), (int)n, 0, 10, E.st));
-                A2.order = E.sort_vals2.as<i32>();
-            }
-            CU_CHECK(cudaMemsetAsync(A2.work_ctr, 0, 8, E.st));
-            const int qw4 = lane_qw4(A.caps.maxlen);
-            E.packed4.reserve((size_t)A.B.n_reads * qw4 * 4 + 64);
-            k_pack_reads4<<<(unsigned)((A.B.n_reads * qw4 + 255) / 256), 256, 0, E.st>>>(A.B.seq, A.B.seq_off, A.B.n_reads, qw4, E.packed4.as<u32>());
-            k_extend_lane<<<grid, 32, lsmem, E.st>>>(A2, E.packed4.as<u32>(), batch, cbatch);
-            E.stats.n_launches += 1;
-            CU_CHECK(cudaGetLastError());
-        } else if (group_ok && smem <= 200 * 1024) {
+        if (group_ok && smem <= 200 * 1024) {
             // reads ordered by estimated work: heaviest first, equal work side by side in a warp
             const i32 *order = A.order;
             if (!spill && A.B.work && !A.order) {

@@ -18,7 +18,6 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "seed.cuh"
-#include "seed_fsm.cuh"
 #include "seed2.cuh"
 #include "chain.cuh"
 #include "seedsw.cuh"
@@ -102,8 +101,7 @@ HD void stage_seed_t(const DevIndex &ix, const Opt &opt, const Caps &caps, const
     Intv *prev = (Intv *)scratch, *curr = prev + (caps.maxlen + 1);
     IntvSink out; out.a = curr + (caps.maxlen + 1); out.n = 0; out.cap = caps.intv; out.overflow = false;
     if (len >= opt.min_seed_len) {
-        if (LOOPS) collect_intv(ix, opt, len, seq, out, prev, curr, ctr);        // the reference's loop nest (seed.cuh)
-        else collect_intv_fsm(ix, opt, len, seq, out, prev, curr, ctr);        // the same, as the state machine the GPU kernel uses
+        collect_intv(ix, opt, len, seq, out, prev, curr, ctr);        // the reference's loop nest (seed.cuh)
     }
     if (out.overflow) { B.ovf[rid] |= OVF_INTV; return; }
     i64 off = pool_alloc(B.pool, POOL_INTV, out.n);
@@ -114,7 +112,7 @@ HD void stage_seed_t(const DevIndex &ix, const Opt &opt, const Caps &caps, const
 
 HD void stage_seed(const DevIndex &ix, const Opt &opt, const Caps &caps, const Batch &B, i64 rid, u8 *scratch, CtrLocal &ctr)
 {
-    stage_seed_t<false>(ix, opt, caps, B, rid, scratch, ctr);
+    stage_seed_t<true>(ix, opt, caps, B, rid, scratch, ctr);
 }
 
 // The single-extension-site machine of seed2.cuh with a `list_cap`-entry work list, falling back to the reference-shaped

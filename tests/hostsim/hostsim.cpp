@@ -9,7 +9,6 @@
 #include <vector>
 #include <string>
 #include "../../seqlib_b200/csrc/pipeline.cuh"
-#include "../../seqlib_b200/csrc/extend_lane.cuh"
 #include "hostindex.h"
 
 using namespace b200;
@@ -76,8 +75,6 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
     int tab_K = getenv("HOSTSIM_SEED_TAB_K") ? atoi(getenv("HOSTSIM_SEED_TAB_K")) : 0;   // prefix-interval tables for the seed2 machine
     if (seed_v2 && tab_K > 0 && hi->tab.K != tab_K) hi->build_tab(tab_K);
     const SeedTab *tabp = seed_v2 && tab_K > 0 ? &hi->tab : nullptr;
-    bool ext_lane = getenv("HOSTSIM_EXTEND_LANE") && lane_extend_eligible(opt, maxlen);   // the one-lane-per-read machine of extend_lane.cuh
-    std::vector<u32> lane_cols((size_t)maxlen + 2 * LANE_U + 2), lane_q((size_t)maxlen / 8 + 8);
     std::vector<std::vector<Reg> > raws(n);
     for (int64_t r = 0; r < n; ++r) {
         for (int pass = 0; pass < 2; ++pass) {
@@ -89,10 +86,7 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
             if (seed_v2) stage_seed_v2(ix, opt, c, B, r, s1.data(), ctr, seed_v2, tabp);
             else stage_seed(ix, opt, c, B, r, s1.data(), ctr);
             stage_chain(ix, opt, c, B, r, s2.data(), ctr, logtab.data(), (int)logtab.size());
-            if (ext_lane) {
-                std::vector<u8> s3l(extend_lane_scratch_bytes(c) + 64);
-                stage_extend_lane_host(ix, opt, c, B, r, s3l.data(), lane_cols.data(), lane_q.data(), ctr);
-            } else stage_extend(ix, opt, c, B, r, s3.data(), ctr);
+            stage_extend(ix, opt, c, B, r, s3.data(), ctr);
             raws[r].assign(B.pool.regs + rec[r].reg_off, B.pool.regs + rec[r].reg_off + rec[r].n_regs);
             stage_finalize(ix, opt, c, B, r, s4.data(), logtab.data(), (int)logtab.size(), ctr);
             if (ovf[r] && pass == 0) { R->ovf[r] = ovf[r]; continue; }

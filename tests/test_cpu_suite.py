@@ -83,31 +83,6 @@ def test_stage_functions_on_cpu_vs_golden(name, small, seed_v2, tab_k, monkeypat
         assert np.array_equal(got.intv_off, z["intv_off"]) and np.array_equal(got.intv, z["intv"])
 
 
-@pytest.mark.parametrize("name,small", [("sim1_5k", False), ("bcr_2k", False), ("bcr_2k", True)])
-def test_lane_extension_machine_on_cpu_vs_golden(name, small, monkeypatch):
-    """extend_lane.cuh (one lane per read, mem_chain2aln as a resumable machine around a flattened ksw_extend2 with the
-    (h, e, query code) column words) compiled for the host gives the golden regions, hits, CIGARs and MAPQs."""
-    monkeypatch.delenv("HOSTSIM_SEED_V2", raising=False)
-    monkeypatch.setenv("HOSTSIM_EXTEND_LANE", "1")
-    from oracle import pyref
-    if not pyref.have_ref():
-        pytest.skip("needs oracle/_ref to parse the bwa index for the host harness")
-    import simlib
-    gold, z = goldenlib.load(name)
-    sidx, _keep = _sim_index_for_tiny()
-    reads = cases.read_lines(goldenlib.path(name + ".txt"))
-    if small:
-        reads = reads[:600]
-    got = simlib.align(sidx, reads, pyref.default_opt(), cases.ids_for(len(reads)), small)
-    n = len(reads)
-    assert np.array_equal(got.hit_off, gold.hit_off[:n + 1])
-    k = int(gold.hit_off[n])
-    for f in parity.REG_FIELDS + parity.ALN_FIELDS:
-        assert np.array_equal(got.hits[f], gold.hits[f][:k]), f
-    if not small:
-        assert parity.compare_results(got, gold) == []
-
-
 def test_long_reads_seed_sw_filter_on_cpu_vs_reference(monkeypatch):
     """Contig-like queries (0.8-4 kb) activate mem_flt_chained_seeds / mem_seed_sw -> ksw_i16 (bwa/bwamem.c:597-641): the host
     build of the stage functions (seedsw.cuh replays the striped kernel) gives the reference's hits, CIGARs and MAPQs; with

@@ -207,9 +207,10 @@ def test_long_reads_vs_live_reference(capi):
 
 
 @pytest.mark.parametrize("name", ["sim1_5k", "bcr_2k"])
-def test_lane_extension_kernel_opt_in(name):
-    """B200_EXTEND_LANE=1 selects k_extend_lane (one lane per read, extend_lane.cuh) instead of the group kernel; the choice is
-    latched at the first call, so the run happens in a fresh process.  Same golden hits, CIGARs and MAPQs."""
+def test_row_synchronous_extension_kernel_alone(name):
+    """B200_WAVE_G=0 switches the wavefront extension kernel off, so every read goes through the row-synchronous kernel that
+    otherwise only sees what the wavefront hands back (gap events, N bases); the choice is latched at the first call, so the run
+    happens in a fresh process.  Same golden hits, CIGARs and MAPQs."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -225,7 +226,7 @@ def test_lane_extension_kernel_opt_in(name):
         "bad = parity.compare_results(got, gold)\n"
         "assert bad == [], bad[:5]\n"
         "print('lane ok', len(got.hits))\n") % (root, os.path.join(root, "tests"), name, name)
-    env = dict(os.environ, B200_EXTEND_LANE="1")
+    env = dict(os.environ, B200_WAVE_G="0")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "lane ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
