@@ -88,11 +88,28 @@ __global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
 //   (read r owns [r * stride, (r+1) * stride)), in production order; k_sort_intv orders them afterwards.
 //   Reads the machine does not take (N bases, list or slot overflow) get OVF_INTV and go through the spill pass,
 //   i.e. the reference-shaped k_stage<0>.
+// The work list of k_seed2 in shared memory: 12 bytes per entry (word k of entry e of thread t at [(3 e + k) * 128 + t], conflict
+// free): x0, x1 low words; x0 / x1 high nibbles | size (16 bits) | end (8 bits).  Entries whose size does not fit 16 bits are
+// strings of at most ~8 bases: a table answers every extension of them and they can never be reported as seeds, so their interval
+// is not kept (take() says so, and the machine sends the read to the spill path if it ever asks for one).  336 bytes of shared
+// memory per thread instead of 432: five blocks per SM instead of four.
 struct SmemList {
-    uint4 *p;
-    __device__ __forceinline__ PIntv get(int e) const { uint4 v = p[e * 128]; PIntv r; r.w0 = v.x; r.w1 = v.y; r.w2 = v.z; r.w3 = v.w; return r; }
-    __device__ __forceinline__ void set(int e, const PIntv &r) { p[e * 128] = make_uint4(r.w0, r.w1, r.w2, r.w3); }
-    __device__ __forceinline__ u32 end(int e) const { return p[e * 128].w >> 16; }
+    u32 *p;
+    __device__ __forceinline__ void put(int e, u64 x0, u64 x1, u64 x2, u32 end)
+    {
+        u32 *q = p + e * 384;
+        q[0] = (u32)x0; q[128] = (u32)x1;
+        q[256] = (u32)(x0 >> 32) | (u32)(x1 >> 32) << 4 | (x2 < 0xffffull ? (u32)x2 : 0xffffu) << 8 | end << 24;
+    }
+    __device__ __forceinline__ bool take(int e, u64 &x0, u64 &x1, u64 &x2, u32 &end) const
+    {
+        const u32 *q = p + e * 384;
+        const u32 w = q[256];
+        x0 = (u64)q[0] | (u64)(w & 15u) << 32; x1 = (u64)q[128] | (u64)((w >> 4) & 15u) << 32;
+        x2 = (w >> 8) & 0xffffu; end = w >> 24;
+        return x2 != 0xffffull;
+    }
+    __device__ __forceinline__ u32 end(int e) const { return p[e * 384 + 256] >> 24; }
 };
 struct SmemQuery {
     const u32 *p;
@@ -126,18 +143,18 @@ __global__ void k_pack_reads(const u8 *__restrict__ seq, const i64 *__restrict__
 }
 
 template <int CAP>
-__global__ void __launch_bounds__(128, 4) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride,
+__global__ void __launch_bounds__(128, 5) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride,
                                                   int keep_level)
 {
     // Tried and dropped (round 2): keeping only the entries' ends in shared memory and the 16-byte intervals in an L2-resident
     // global slot lifts the occupancy from 16 to 24 warps per SM -- and changes nothing (270 vs 264 ms per 10 M reads): the
     // kernel is bound by the rate at which HBM serves random 128-byte line fills, not by the number of warps waiting for them.
-    extern __shared__ uint4 seed_smem[];
+    extern __shared__ u32 seed_smem[];
     LoadPol pol; pol.keep_level = keep_level;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol.keep));
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol.stream));
     SmemList L; L.p = seed_smem + threadIdx.x;
-    u32 *myq = (u32 *)(seed_smem + CAP * 128) + threadIdx.x;
+    u32 *myq = seed_smem + CAP * 384 + threadIdx.x;
     SmemQuery Q; Q.p = myq;
     myq[qw * 128] = 0;
     SeedMachine<SmemList, SmemQuery> m;
@@ -501,12 +518,12 @@ static const int SEED2_STRIDE = 40;       // interval slots per read in the pool
 static bool seed2_enabled() { static int on = getenv("B200_SEED_V1") ? 0 : 1; return on != 0; }
 static bool seed2_usable(const KArgs &A)
 {
-    return seed2_enabled() && !A.order && A.caps.maxlen <= 256 && A.ix.seq_len < (1ull << 36) && A.B.pool.cap[POOL_INTV] >= A.B.n_reads * (i64)SEED2_STRIDE;
+    return seed2_enabled() && !A.order && A.caps.maxlen <= 255 && A.ix.seq_len < (1ull << 36) && A.B.pool.cap[POOL_INTV] >= A.B.n_reads * (i64)SEED2_STRIDE;
 }
 template <int CAP>
 static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
 {
-    size_t smem = (size_t)128 * (CAP * 16 + (qw + 1) * 4);
+    size_t smem = (size_t)128 * (CAP * 12 + (qw + 1) * 4);
     CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     int per = 0;
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP>, 128, smem));
@@ -617,7 +634,7 @@ static void run_stages(Engine &E, KArgs A, int spill, float *ms4)
     int g[4];
     const int tpb = spill >= 2 ? 32 : 128;            // threads per block of the thread-per-read kernels
     if (!spill) { g[0] = stage_grid<0>(E.sms); g[1] = stage_grid<1>(E.sms); g[2] = stage_grid<2>(E.sms); g[3] = stage_grid<3>(E.sms); }
-    else g[0] = g[1] = g[2] = g[3] = std::max<int>(1, (int)std::min<i64>((A.n_work + tpb - 1) / tpb, 8));
+    else g[0] = g[1] = g[2] = g[3] = std::max<int>(1, (int)std::min<i64>((A.n_work + tpb - 1) / tpb, (i64)E.sms * 4));      // bounded by the scratch budget below
     Caps tc = A.caps;
     if (A.B.dp_jobs) tc.z = 64;          // gapped hits go to k_finalize_dp, the thread-per-read stage needs no direction matrix
     size_t stride = max4(seed_scratch_bytes(tc), chain_scratch_bytes(tc), extend_scratch_bytes(tc), finalize_scratch_bytes(tc));

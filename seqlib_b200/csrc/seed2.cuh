@@ -175,7 +175,7 @@ struct SeedMachine {
     HD void push_fwd()
     {
         if (top == 0) { fail(); return; }
-        L.set(--top, pintv_pack(x0, x1, x2, iend));
+        L.put(--top, x0, x1, x2, iend);
         ret = (int)iend;
     }
 
@@ -193,8 +193,8 @@ struct SeedMachine {
                 // bwa/bwt.c:325-345 with c = -1: only the longest survivor can be reported, with start 0
                 if (first || 0 < last_start) {
                     u64 e0, e1, e2; u32 e;
-                    pintv_unpack(L.get(top), e0, e1, e2, e);
-                    if ((int)e >= min_seed_len) { emit(e0, e1, e2, (u64)e); if (ovf) return; }
+                    const bool ok = L.take(top, e0, e1, e2, e);
+                    if ((int)e >= min_seed_len) { if (!ok) { fail(); return; } emit(e0, e1, e2, (u64)e); if (ovf) return; }
                 }
                 mode = M_TASK;
                 if (pass == 1) x = ret;
@@ -253,16 +253,7 @@ struct SeedMachine {
         settle(ix);
     }
 
-    HD void request(u64 &a, u64 &o, u64 &s, int &c)
-    {
-        if (mode == M_BWD) {
-            pintv_unpack(L.get(top + j), p0, p1, p2, pend);
-            have_p = true;
-            a = p0; o = p1; s = p2; c = q[i];
-        } else { a = x1; o = x0; s = x2; c = 3 - q[i]; }
-    }
-
-    // the same, plus the string the extension produces: q[st, st + ln).  tl = ln when a table level holds it, else 0.
+    // The next extension and the string it produces: q[st, st + ln).  tl = ln when a table level holds it, else 0.
     // A backward step that a table answers needs only the END of its list entry (the string is q[i, end)): the entry's
     // interval is fetched lazily, when the entry dies as an SMEM -- lists that keep intervals outside shared memory
     // (k_seed2's HybridList) then touch them in a third of the steps only.
@@ -275,8 +266,8 @@ struct SeedMachine {
             tl = ln <= K ? ln : 0;
             c = q[i];
             if (tl) { have_p = false; a = 1; o = 1; s = 0; key = q.key(i, ln); return; }
-            pintv_unpack(L.get(top + j), p0, p1, p2, pend);
             have_p = true;
+            if (!L.take(top + j, p0, p1, p2, pend)) { p0 = p1 = 1; p2 = 0; fail(); }      // the list did not keep this interval: spill path
             a = p0; o = p1; s = p2; key = 0u;
             return;
         }
@@ -294,13 +285,13 @@ struct SeedMachine {
                 if (ncurr == 0 && (first || i + 1 < last_start)) {
                     first = 0; last_start = i + 1;
                     if ((int)pend - (i + 1) >= min_seed_len) {
-                        if (!have_p) { u32 e_; pintv_unpack(L.get(top + j), p0, p1, p2, e_); have_p = true; }
+                        if (!have_p) { u32 e_; have_p = true; if (!L.take(top + j, p0, p1, p2, e_)) { fail(); return; } }
                         emit(p0, p1, p2, (u64)(i + 1) << 32 | pend);
                         if (ovf) return;
                     }
                 }
             } else if (ncurr == 0 || ns != lastcurr) {
-                L.set(top + ncurr, pintv_pack(na, no, ns, pend));
+                L.put(top + ncurr, na, no, ns, pend);
                 ++ncurr; lastcurr = ns;
             }
             if (++j == nprev) {
@@ -339,8 +330,8 @@ struct SeedMachine {
 // plain-array list / byte query: the host emulation and the debug path
 struct ArrayList {
     PIntv *p;
-    HD PIntv get(int e) const { return p[e]; }
-    HD void set(int e, const PIntv &v) { p[e] = v; }
+    HD void put(int e, u64 x0, u64 x1, u64 x2, u32 end) { p[e] = pintv_pack(x0, x1, x2, end); }
+    HD bool take(int e, u64 &x0, u64 &x1, u64 &x2, u32 &end) const { pintv_unpack(p[e], x0, x1, x2, end); return true; }
     HD u32 end(int e) const { return p[e].w3 >> 16; }
 };
 struct ByteQuery {
