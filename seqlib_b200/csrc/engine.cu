@@ -64,11 +64,12 @@ template <int STAGE>
 __global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
 {
     u8 *scr = A.scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.scratch_stride;
+    const i64 n_work = A.n_work_dev ? (i64)*A.n_work_dev : A.n_work;
     CtrLocal ctr;
     for (;;) {
         i64 w = claim(A.work_ctr);
-        if (w - (threadIdx.x & 31) >= A.n_work) break;
-        if (w < A.n_work) {
+        if (w - (threadIdx.x & 31) >= n_work) break;
+        if (w < n_work) {
             i64 rid = A.order ? A.order[w] : w;
             if (STAGE == 0) stage_seed_t<true>(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
             else if (STAGE == 1) stage_chain(A.ix, A.opt, A.caps, A.B, rid, scr, ctr, A.log_tab, A.n_log);
@@ -341,6 +342,10 @@ __global__ void k_encode(const u8 *__restrict__ in, u8 *__restrict__ out, i64 n)
 __global__ void k_iota32(i32 *a, i64 n) { i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = (i32)i; }
 __global__ void k_clear_u32(u32 *a, i64 n) { i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = 0; }
 __global__ void k_clear_list(u32 *a, const i32 *list, i64 n) { i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[list[i]] = 0; }
+__global__ void k_clear_list_dev(u32 *a, const i32 *list, const unsigned long long *n)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < (i64)*n; i += (i64)gridDim.x * blockDim.x) a[list[i]] = 0;
+}
 
 // list the reads of [0,n) whose ovf bits intersect mask
 __global__ void k_list_ovf(const u32 *__restrict__ ovf, i64 n, u32 mask, i32 *__restrict__ list, unsigned long long *cnt)
@@ -560,7 +565,7 @@ static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
     }
     k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE, keep_level);
 }
-static void launch_seed2(Engine &E, KArgs &A)
+static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
 {
     const i64 n = A.n_work;
     const int qw = (A.caps.maxlen + 15) / 16;
@@ -576,6 +581,20 @@ static void launch_seed2(Engine &E, KArgs &A)
     CU_CHECK(cudaGetLastError());
     k_sort_intv<<<(unsigned)((n + 127) / 128), 128, 0, E.st>>>(A.B.rec, A.B.ovf, n, A.B.pool.intv);
     CU_CHECK(cudaGetLastError());
+    // Reads the machine did not take (an N base, a work list or interval slot that overflowed) go through the reference-shaped
+    // kernel right away, at full width and with the main-pass slots: only what overflows THOSE reaches the few-thread spill pass.
+    // (A batch where 1 % of the reads hold an N would otherwise put 10^4 reads per chunk through the spill pass.)
+    if (grid0 > 0 && A.scratch && E.list.p) {
+        unsigned long long *cnt = A.work_ctr + 4;
+        CU_CHECK(cudaMemsetAsync(cnt, 0, 8, E.st));
+        k_list_ovf<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(A.B.ovf, n, OVF_INTV, E.list.as<i32>(), cnt);
+        k_clear_list_dev<<<64, 256, 0, E.st>>>(A.B.ovf, E.list.as<i32>(), cnt);
+        KArgs A2 = A; A2.order = E.list.as<i32>(); A2.n_work_dev = cnt;
+        CU_CHECK(cudaMemsetAsync(A2.work_ctr, 0, 8, E.st));
+        k_stage<0><<<grid0, 128, 0, E.st>>>(A2);
+        CU_CHECK(cudaGetLastError());
+        E.stats.n_launches += 3;
+    }
     E.stats.n_launches += 3;
 }
 
@@ -651,7 +670,7 @@ static void run_stages(Engine &E, KArgs A, int spill, float *ms4)
     A.scratch = S.as<u8>(); A.scratch_stride = stride;
     cudaEvent_t *ev = E.ev;
     CU_CHECK(cudaEventRecord(ev[0], E.st));
-    if (!spill && seed2_usable(A)) launch_seed2(E, A);
+    if (!spill && seed2_usable(A)) launch_seed2(E, A, g[0]);
     else launch_stage<0>(E, A, g[0], tpb);
     CU_CHECK(cudaEventRecord(ev[1], E.st));
     launch_stage<1>(E, A, g[1], tpb); CU_CHECK(cudaEventRecord(ev[2], E.st));

@@ -278,3 +278,28 @@ def test_tandem_repeat_reads_do_not_fail_the_batch(capi):
     assert parity.compare_results(got, exp) == []
     st = capi.last_stats()
     assert st["n_overflow"] >= 20 and st["n_failed"] == 0
+
+
+def test_reads_with_n_take_the_main_pass(capi):
+    """Reads holding an N are not taken by the seeding machine; they go through the reference-shaped kernel inside the main pass
+    (not the few-thread spill pass) and through the row-synchronous extension kernel.  Hits equal the reference library's."""
+    from oracle import pyref
+    from seqlib_b200 import synth
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    l_pac = 300000
+    pac = synth.reference(l_pac, seed=91)
+    ctg = synth.contigs_for(l_pac, 3, "n")
+    names = [c[0] for c in ctg]
+    seqs = [synth.ascii_of(pac, c[1], c[1] + c[2]) for c in ctg]
+    r, off, _, _ = synth.reads(pac, l_pac, ctg, 6000, 150, 0.02, 1e-3, seed=92)
+    r = r.copy()
+    r[7::211] = ord("N")                         # ~70 % of the reads get at least one N
+    ids = cases.ids_for(6000)
+    ridx = pyref.RefIndex.construct(names, seqs)
+    exp, _ = pyref.align(ridx, (r, off), pyref.default_opt(), ids)
+    idx = capi.Index.construct(names, seqs)
+    got = capi.align(idx, (r, off), capi.default_opt(), ids)
+    assert parity.compare_results(got, exp) == []
+    st = capi.last_stats()
+    assert st["n_overflow"] < 100 and st["ext_fallback"] > 1000 and st["n_failed"] == 0
