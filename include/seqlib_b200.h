@@ -116,7 +116,8 @@ int b200_index_construct(int n, const char *const *names, const char *const *seq
 
 /* Builds an index over a 2-bit forward pac that is already on the host
  * (4 bases/byte, bwa order).  Same engine as b200_index_construct without
- * the ASCII pass; used for the 3 Gb synthetic reference. */
+ * the ASCII pass; used for the 3 Gb synthetic reference.  `pac` holds
+ * ceil(l_pac / 4) bytes; nothing beyond them is read. */
 int b200_index_construct_pac(int64_t l_pac, const uint8_t *pac, int n_seqs,
                              const b200_contig_t *contigs, int flags, b200_index_t **out);
 

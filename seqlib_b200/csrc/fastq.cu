@@ -44,7 +44,7 @@ struct Stream {
     const unsigned char *buf = nullptr;
     std::vector<unsigned char> own;
     long beg = 0, end = 0;
-    bool eof = false, mem = false;
+    bool eof = false, mem = false, io_error = false;
     int last_char = 0;
     bool comment_buf = false, qual_buf = false;      // kseq's comment.s / qual.s have been allocated (FastqReader.cpp:49-56 tests them)
 
@@ -53,6 +53,11 @@ struct Stream {
         if (mem) { eof = true; return false; }
         beg = 0;
         int k = gzread(fp, own.data(), (unsigned)own.size());
+        if (k <= 0) {                                   // corrupt / truncated gzip stream: not a clean end of input (next_batch reports B200_ERR_IO)
+            int zerr = 0;
+            gzerror(fp, &zerr);
+            if (k < 0 || (zerr != Z_OK && zerr != Z_STREAM_END)) io_error = true;
+        }
         end = k > 0 ? k : 0;
         if (end == 0) { eof = true; return false; }
         return true;
@@ -210,6 +215,10 @@ int b200_fastq_next_batch(b200_fastq_t *R, int64_t max_records, b200_fastq_batch
         R->has.push_back((uint8_t)((R->st.comment_buf ? 1 : 0) | (R->st.qual_buf ? 2 : 0)));
     }
     fill_batch(*R, out, status, 0);
+    if (R->st.io_error) {      // gzread failed (corrupt or truncated gzip): the records before the damage are in the batch, the call says so
+        set_error("b200_fastq_next_batch: read error in the compressed stream (truncated or corrupt input)");
+        return B200_ERR_IO;
+    }
     return 0;
 }
 

@@ -419,7 +419,8 @@ int b200_index_construct_pac(int64_t l_pac, const uint8_t *pac, int n_seqs, cons
             idx->contigs.push_back(c);
         }
         idx->l_pac = l_pac;
-        idx->h_pac.assign(pac, pac + l_pac / 4 + 1);
+        idx->h_pac.assign((size_t)l_pac / 4 + 1, 0);                       // bwa's layout keeps l_pac / 4 + 1 bytes; the caller owns ceil(l_pac / 4)
+        memcpy(idx->h_pac.data(), pac, (size_t)(l_pac + 3) / 4);
         idx->h_pac.push_back(0);
         construct_common(idx, flags);
         if (!(flags & 1)) { idx->h_pac.clear(); idx->h_pac.shrink_to_fit(); }

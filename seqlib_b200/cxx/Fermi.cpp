@@ -301,9 +301,18 @@ void BFC::ErrorCorrect()
     std::vector<int32_t> len(m_seqs.size() + 1);
     check(b200_kmer_correct_flat(ch, min_cov, mode, flt_uniq, (int64_t)m_seqs.size(), f.seq.data(), f.has_qual ? f.qual.data() : nullptr,
                                  f.off.data(), len.data()), "BFC::ErrorCorrect");
+    // what worker_ec does with the outcome (fermi-lite/bfc.c:492-509): corrected bases copied back; with flt_uniq set a read is
+    // trimmed to len[i] (seq and qual NUL-terminated there) or, when nothing of it is left, freed and NULLed with l_seq = 0
     for (size_t i = 0; i < m_seqs.size(); ++i) {
-        memcpy(m_seqs[i].seq, f.seq.data() + f.off[i], m_seqs[i].l_seq);
-        if (m_seqs[i].qual) memcpy(m_seqs[i].qual, f.qual.data() + f.off[i], m_seqs[i].l_seq);
+        const int32_t keep = flt_uniq ? len[i] : m_seqs[i].l_seq;
+        if (flt_uniq && keep <= 0) {
+            free(m_seqs[i].seq); free(m_seqs[i].qual);
+            m_seqs[i].seq = m_seqs[i].qual = nullptr; m_seqs[i].l_seq = 0;
+            continue;
+        }
+        memcpy(m_seqs[i].seq, f.seq.data() + f.off[i], keep);
+        if (m_seqs[i].qual) memcpy(m_seqs[i].qual, f.qual.data() + f.off[i], keep);
+        if (keep < m_seqs[i].l_seq) { m_seqs[i].seq[keep] = 0; if (m_seqs[i].qual) m_seqs[i].qual[keep] = 0; m_seqs[i].l_seq = keep; }
     }
 }
 

@@ -141,3 +141,24 @@ def test_cxx_fastq_reader_class(tmp_path):
         if name in ("cr_only_comment",):          # a bare CR inside a field would break the line-based comparison
             continue
         assert lines == exp, name
+
+
+def test_truncated_gzip_is_an_error_not_end_of_input(tmp_path):
+    """A gzip stream cut in the middle: gzread fails; the batch call must report B200_ERR_IO instead of a clean end of input
+    with silently fewer records (kseq itself stops quietly there; the batch API has an error channel, so it uses it)."""
+    import gzip
+    import random
+    from seqlib_b200 import fastq as fq, capi
+    rnd = random.Random(3)
+    text = "".join("@r%d\n%s\n+\n%s\n" % (i, "".join(rnd.choice("ACGT") for _ in range(100)), "I" * 100) for i in range(3000)).encode()
+    p = tmp_path / "cut.fq.gz"
+    blob = gzip.compress(text)
+    p.write_bytes(blob[:len(blob) // 2])
+    r = fq.FastqReader(path=str(p))
+    with pytest.raises(capi.B200Error) as e:
+        while True:
+            b = r.next_batch(1000)
+            if b.status != 0:
+                break
+    assert "b200 error -4" in str(e.value)
+    r.close()
