@@ -1,0 +1,11 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_align.py -x -q 2>&1 | tail -3
+export B200_BENCH_READS=4000000
+timeout 600 python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline > gpurun_out/r02_bench_waveconv.json 2> gpurun_out/r02_bench_waveconv.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r02_bench_waveconv.json"))
+print(d["value"], d["stage_ms_per_step"], d["spill_reads_per_step"])
+PY
+timeout 300 python bench.py --workload ksw --steps 3 --warmup 2 --no-cpu-baseline | cut -c1-160

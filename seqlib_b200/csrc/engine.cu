@@ -144,16 +144,12 @@ __global__ void k_pack_reads(const u8 *__restrict__ seq, const i64 *__restrict__
 }
 
 template <int CAP>
-__global__ void __launch_bounds__(128, 5) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride,
-                                                  int keep_level)
+__global__ void __launch_bounds__(128, 5) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride)
 {
-    // Tried and dropped (round 2): keeping only the entries' ends in shared memory and the 16-byte intervals in an L2-resident
-    // global slot lifts the occupancy from 16 to 24 warps per SM -- and changes nothing (270 vs 264 ms per 10 M reads): the
-    // kernel is bound by the rate at which HBM serves random 128-byte line fills, not by the number of warps waiting for them.
+    // The SMEM passes (bwt_smem1a from every start, re-seeding of long SMEMs).  Tried and dropped (round 2): L2 eviction-policy
+    // hints / a persisting window for the low table levels (no change in hit rate or time, profiles/r02_seed_l2hint_ab.txt);
+    // entry ends in shared memory + intervals in an L2-resident global slot (6 blocks per SM but a global access per step: no gain).
     extern __shared__ u32 seed_smem[];
-    LoadPol pol; pol.keep_level = keep_level;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol.keep));
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol.stream));
     SmemList L; L.p = seed_smem + threadIdx.x;
     u32 *myq = seed_smem + CAP * 384 + threadIdx.x;
     SmemQuery Q; Q.p = myq;
@@ -184,7 +180,7 @@ __global__ void __launch_bounds__(128, 5) k_seed2(const __grid_constant__ KArgs 
                     const u32 *src = packed + rid * qw;
                     for (int k = 0; k < qw; ++k) myq[k * 128] = src[k];
                     IntvSink out; out.a = A.B.pool.intv + rid * stride; out.n = 0; out.cap = stride; out.overflow = false;
-                    m.init(A.opt, len, CAP, L, Q, out, A.tab.K);
+                    m.init(A.opt, len, CAP, L, Q, out, A.tab.K, 2);
                     m.start(A.ix);
                 }
             }
@@ -193,7 +189,60 @@ __global__ void __launch_bounds__(128, 5) k_seed2(const __grid_constant__ KArgs 
         if (m.mode != 0) {
             u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
             m.request(a, o, s, c, tl, key, fwd);
-            extend_or_lookup(A.ix, A.tab, tl, key, fwd, a, o, s, c, na, no, ns, ctr, keep_level >= 0 ? &pol : nullptr);
+            extend_or_lookup(A.ix, A.tab, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
+            m.consume(A.ix, na, no, ns);
+        }
+    }
+    flush_counters(ctr, A.ctrs);
+}
+
+// The third pass (bwt_seed_strategy1 from every start, bwa/bwamem.c:173-184) as its own kernel: every lane is a forward walk, no
+// work list, 48 bytes of shared memory per thread -- occupancy and convergence that the mixed kernel cannot have.
+struct NoList {
+    __device__ __forceinline__ void put(int, u64, u64, u64, u32) {}
+    __device__ __forceinline__ bool take(int, u64 &, u64 &, u64 &, u32 &) const { return false; }
+    __device__ __forceinline__ u32 end(int) const { return 0; }
+};
+__global__ void __launch_bounds__(128, 8) k_seed3(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, int stride)
+{
+    extern __shared__ u32 seed_smem[];
+    u32 *myq = seed_smem + threadIdx.x;
+    SmemQuery Q; Q.p = myq;
+    myq[qw * 128] = 0;
+    SeedMachine<NoList, SmemQuery> m;
+    m.mode = 0; m.ovf = 0;
+    CtrLocal ctr;
+    i64 rid = -1;
+    bool done = false;
+    for (;;) {
+        if (m.mode == 0 && !done) {
+            if (rid >= 0) {
+                ReadRec &R = A.B.rec[rid];
+                if (m.ovf) { A.B.ovf[rid] |= OVF_INTV; R.n_intv = 0; R.intv_off = 0; }
+                else R.n_intv = m.out.n;
+                rid = -1;
+            }
+            i64 w = (i64)atomicAdd(A.work_ctr, 1ull);
+            if (w >= A.n_work) done = true;
+            else {
+                rid = A.order ? A.order[w] : w;
+                if (A.B.ovf[rid]) rid = -1;                      // not taken by k_seed2: the reference-shaped kernel does all three passes
+                else {
+                    const int len = (int)(A.B.seq_off[rid + 1] - A.B.seq_off[rid]);
+                    const u32 *src = packed + rid * qw;
+                    for (int k = 0; k < qw; ++k) myq[k * 128] = src[k];
+                    IntvSink out; out.a = A.B.pool.intv + rid * stride; out.n = 0; out.cap = stride; out.overflow = false;
+                    NoList L;
+                    m.init(A.opt, len, 0, L, Q, out, A.tab.K, 3);
+                    m.start3(A.ix, A.B.rec[rid].n_intv);
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (m.mode != 0) {
+            u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
+            m.request(a, o, s, c, tl, key, fwd);
+            extend_or_lookup(A.ix, A.tab, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
             m.consume(A.ix, na, no, ns);
         }
     }
@@ -534,36 +583,15 @@ static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP>, 128, smem));
     if (per < 1) per = 1;
     { static const int occ = getenv("B200_OCC_SEED") ? atoi(getenv("B200_OCC_SEED")) : 0; if (occ > 0 && occ < per) per = occ; }
-    // levels <= keep_level of the tables are loaded with an evict_last L2 policy, everything else evict_first (-1: no hints)
-    static const int keep_level = getenv("B200_SEED_KEEP") ? atoi(getenv("B200_SEED_KEEP")) : -1;
-    {   // evict_last lines live in the persisting part of L2, which is empty unless a size is set for it
-        static bool once = false;
-        if (!once && keep_level >= 0) {
-            once = true;
-            int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, E.device);
-            size_t want = getenv("B200_L2_PERSIST_MB") ? (size_t)atol(getenv("B200_L2_PERSIST_MB")) << 20 : (size_t)maxp;
-            if (want > (size_t)maxp) want = (size_t)maxp;
-            cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-            if (getenv("B200_TRACE")) fprintf(stderr, "[b200 trace] persisting L2: max %d MB, set %zu MB (%s)\n", maxp >> 20, want >> 20, cudaGetErrorString(e));
-            cudaGetLastError();
-        }
-    }   // measured: no effect on the L2 hit rate or the kernel time (profiles/r02_seed_l2hint_ab.txt)
-    static const int win_level = getenv("B200_SEED_WINDOW") ? atoi(getenv("B200_SEED_WINDOW")) : 0;
-    if (win_level > 0 && A.tab.K > 0) {      // experiment: an access-policy window that makes the low table levels persisting L2 lines
-        int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, E.device);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
-        cudaStreamAttrValue attr; memset(&attr, 0, sizeof(attr));
-        const int lv = std::min(win_level, A.tab.K);
-        attr.accessPolicyWindow.base_ptr = (void *)A.tab.base;
-        attr.accessPolicyWindow.num_bytes = (size_t)seedtab_level_off(lv + 1) * sizeof(PIntv);
-        attr.accessPolicyWindow.hitRatio = 1.0f;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaError_t e = cudaStreamSetAttribute(E.st, cudaStreamAttributeAccessPolicyWindow, &attr);
-        if (getenv("B200_TRACE")) fprintf(stderr, "[b200 trace] access policy window: %zu MB persisting (%s)\n", attr.accessPolicyWindow.num_bytes >> 20, cudaGetErrorString(e));
-        cudaGetLastError();
-    }
-    k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE, keep_level);
+    k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
+    CU_CHECK(cudaGetLastError());
+    // then the third pass
+    size_t smem3 = (size_t)128 * (qw + 1) * 4;
+    int per3 = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, k_seed3, 128, smem3));
+    if (per3 < 1) per3 = 1;
+    CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
+    k_seed3<<<E.sms * per3, 128, smem3, E.st>>>(A, E.packed.as<u32>(), qw, SEED2_STRIDE);
 }
 static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
 {

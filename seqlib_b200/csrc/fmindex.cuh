@@ -27,24 +27,6 @@ HD OccLoad load_block_at(const OccBlock *p)
 }
 HD OccLoad load_block(const DevIndex &ix, u64 blk) { return load_block_at(ix.occ + blk); }
 
-// the same 256-bit load with an L2 eviction policy (createpolicy): the low levels of the seeding tables are kept
-// (evict_last), the Occ blocks and the large levels stream through (evict_first)
-HD OccLoad load_block_hint(const OccBlock *p, u64 policy)
-{
-#if defined(__CUDA_ARCH__)
-    OccLoad r;
-    u32 a0, a1, a2, a3, b0, b1, b2, b3;
-    asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "l"(p), "l"(policy));
-    r.c0 = a0; r.c1 = a1; r.c2 = a2; r.c3 = a3;
-    r.s0 = (u64)b0 | (u64)b1 << 32; r.s1 = (u64)b2 | (u64)b3 << 32;
-    return r;
-#else
-    (void)policy;
-    return load_block_at(p);
-#endif
-}
-
 // counts of A,C,G,T in the first r (1..64) symbols of a loaded block, added to the block base.
 // s0 / s1 are the low / high bit planes of the 64 symbols: three popcounts under one mask give all four counts.
 HD void block_rank4(const OccLoad &b, int r, u64 cnt[4])

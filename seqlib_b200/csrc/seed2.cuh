@@ -102,11 +102,9 @@ HD void extend_lean(const DevIndex &ix, u64 a, u64 o, u64 s, int c, u64 &na, u64
 // through the Occ blocks.  Written so that a warp issues ONE pair of 256-bit loads whatever its lanes need: a table
 // lane loads the 32-byte sector that holds its 16-byte entry (twice -- the second request merges in L1).
 // fwd: the caller extends forward (result coordinates swap roles, see SeedMachine::request).
-struct LoadPol { u64 keep, stream; int keep_level; };      // L2 eviction policies of the seeding kernel (device only)
-
 template <class Ctr>
 HD void extend_or_lookup(const DevIndex &ix, const SeedTab &tab, int tl, u32 key, bool fwd, u64 a, u64 o, u64 s, int c,
-                         u64 &na, u64 &no, u64 &ns, Ctr &ctr, const LoadPol *pol = nullptr)
+                         u64 &na, u64 &no, u64 &ns, Ctr &ctr)
 {
     const u64 k = a - 1, l = k + s;
     const u32 dk = k >= ix.primary, dl = l >= ix.primary;
@@ -120,15 +118,7 @@ HD void extend_or_lookup(const DevIndex &ix, const SeedTab &tab, int tl, u32 key
         p1 = p2 = (const OccBlock *)((uintptr_t)e & ~(uintptr_t)31);
         if (tl <= 10) ctr.tab_lo++; else ctr.tab_hi++;
     } else ctr.occ_blocks += bl != bk ? 2 : 1;
-    OccLoad b1, b2;
-    if (pol) {
-        const u64 py = tl && tl <= pol->keep_level ? pol->keep : pol->stream;
-        b1 = load_block_hint(p1, py);
-        b2 = load_block_hint(p2, py);
-    } else {
-        b1 = load_block_at(p1);
-        b2 = load_block_at(p2);
-    }
+    const OccLoad b1 = load_block_at(p1), b2 = load_block_at(p2);
     extend_blocks(ix, b1, b2, kk, ll, dk, dl, o, c, na, no, ns);
     if (tl) {
         PIntv t;
@@ -145,16 +135,18 @@ template <class List, class Query>
 struct SeedMachine {
     enum { M_DONE = 0, M_FWD, M_BWD, M_P3, M_TASK, M_ENDFWD, M_LASTROW };
     int mode, pass, x, k2, old_n, sx, i, j, nprev, ncurr, top, ret, last_start, first, ovf;
-    int len, cap, min_seed_len, split_len, split_width, max_intv3, min_intv, K;
+    int len, cap, min_seed_len, split_len, split_width, max_intv3, min_intv, K, last_pass;
     u64 x0, x1, x2, lastcurr;     // ik of the forward sweeps / last size pushed in this backward row
     u64 p0, p1, p2;               // the list entry being extended backwards
     u32 iend, pend;
     bool have_p;                  // p0..p2 hold the entry's interval (false: only its end was read)
     List L; Query q; IntvSink out;
 
-    HD void init(const Opt &opt, int len_, int cap_, const List &L_, const Query &q_, const IntvSink &out_, int K_ = 0)
+    // last_pass_ = 2: stop after the SMEM passes (bwt_smem1a calls, re-seeding); start3() then runs the third pass
+    // (bwt_seed_strategy1) on its own -- k_seed2 / k_seed3 split them so that a warp never mixes the two kinds of lanes
+    HD void init(const Opt &opt, int len_, int cap_, const List &L_, const Query &q_, const IntvSink &out_, int K_ = 0, int last_pass_ = 3)
     {
-        len = len_; cap = cap_; L = L_; q = q_; out = out_; K = K_;
+        len = len_; cap = cap_; L = L_; q = q_; out = out_; K = K_; last_pass = last_pass_;
         min_seed_len = opt.min_seed_len;
         split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
         split_width = opt.split_width;
@@ -219,7 +211,7 @@ struct SeedMachine {
                     }
                 }
                 if (pass == 3) {
-                    if (x >= len) { mode = M_DONE; return; }
+                    if (last_pass < 3 || x >= len) { mode = M_DONE; return; }
                     // the first min(K, min_seed_len) - 1 extensions of a bwt_seed_strategy1 start (bwa/bwt.c:355-379) can
                     // neither report nor stop (i - x < min_seed_len): one table lookup of q[x, x + jump) replaces them
                     const int jump = K < min_seed_len ? K : min_seed_len;
@@ -249,6 +241,16 @@ struct SeedMachine {
     HD void start(const DevIndex &ix)
     {
         if (len < min_seed_len) { mode = M_DONE; return; }
+        mode = M_TASK;
+        settle(ix);
+    }
+
+    // the third pass alone, after init(): n0 intervals of the first two passes are already in the sink
+    HD void start3(const DevIndex &ix, int n0)
+    {
+        out.n = n0;
+        pass = 3; x = 0;
+        if (len < min_seed_len || max_intv3 <= 0) { mode = M_DONE; return; }
         mode = M_TASK;
         settle(ix);
     }
@@ -362,18 +364,21 @@ template <class Ctr>
 HD bool collect_intv_v2(const DevIndex &ix, const Opt &opt, int len, const u8 *seq, IntvSink &out, PIntv *list, int cap, Ctr &ctr,
                         const SeedTab *tab = nullptr)
 {
-    SeedMachine<ArrayList, ByteQuery> m;
     ArrayList L; L.p = list;
     ByteQuery q; q.p = seq;
     SeedTab none; none.base = nullptr; none.K = 0;
     const SeedTab &T = tab ? *tab : none;
-    m.init(opt, len, cap, L, q, out, T.K);
-    m.start(ix);
-    while (m.mode != 0) {
-        u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
-        m.request(a, o, s, c, tl, key, fwd);
-        extend_or_lookup(ix, T, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
-        m.consume(ix, na, no, ns);
+    SeedMachine<ArrayList, ByteQuery> m;
+    for (int part = 0; part < 2; ++part) {             // the SMEM passes, then bwt_seed_strategy1: two machines, like k_seed2 + k_seed3
+        if (part == 0) { m.init(opt, len, cap, L, q, out, T.K, 2); m.start(ix); }
+        else { const int n0 = m.out.n; IntvSink o2 = m.out; m.init(opt, len, cap, L, q, o2, T.K, 3); m.start3(ix, n0); }
+        while (m.mode != 0) {
+            u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
+            m.request(a, o, s, c, tl, key, fwd);
+            extend_or_lookup(ix, T, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
+            m.consume(ix, na, no, ns);
+        }
+        if (m.ovf) break;
     }
     out = m.out;
     if (m.ovf) return false;
