@@ -478,7 +478,7 @@ def main():
         line = {
             "metric": "150bp reads/sec (seed+chain+SW end-to-end)", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16x2 (extension) / int32, u64 (seeding, chaining, CIGAR)", "data": "synthetic",
             "config": {"workload": "%d x %dbp synthetic reads per GPU vs %d bp random reference (24 contigs), 1%% substitutions" % (n_per, L, args.ref_len),
                        "reads_per_gpu_per_step": n_per, "read_len": L, "ref_len": args.ref_len,
                        "parallelism": "reads sharded x%d, index replicated (one NCCL broadcast)" % world,
@@ -486,7 +486,7 @@ def main():
             "e2e": {"value": n_per * world * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_stage<0> (SMEM seeding)", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "seeding stage: k_seed2 (SMEM passes) + k_seed3 (bwt_seed_strategy1), one pair of launches per chunk", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                          "frac": achieved / peaks.get("hbm_gbs", 6650.0), "traffic": (tpr * n_per / n_seed_launches if tpr else None), "peak_source": how,
                          "traffic_source": tsrc, "algorithmic_bytes_per_launch": alg_bytes / n_seed_launches,
                          "launches_per_step": n_seed_launches, "kernel_ms_per_launch": 1000.0 * seed_s / n_seed_launches,
@@ -495,7 +495,7 @@ def main():
                          "note": "dependent random gathers; round 1 fetched 1391 Occ blocks per read (44.7 KB), the prefix-interval tables cut the algorithmic bytes to ~17 KB per read "
                                  "and the kernel time by 29 %, so achieved GB/s of ALGORITHMIC bytes falls while the kernel gets faster.  DRAM traffic per read is 3.8x the algorithmic bytes: "
                                  "the L2 fills whole 128-byte lines (profiles/r02_seed_traffic.json); the measured ceiling of random 32-B gathers on this part is 38.4 G/s (scripts/microbench/gather_bw.cu), "
-                                 "the kernel issues 28 G/s at 25 % occupancy (shared-memory work lists) and is latency bound"},
+                                 "the kernel issues ~30 G/s at 31 % occupancy (shared-memory work lists, 5 blocks per SM) and is bound by latency and by lanes of one warp being in different phases of the search"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_s_timed_region": wall_s, "mapped_fraction": mapped, "hits_per_step": n_hits_dev,
             "index_build_s": t_index, "index_bcast_s": t_bcast, "spill_reads_per_step": stats["n_overflow"],
