@@ -153,6 +153,22 @@ def fermi_extra(args, with_cpu):
                                    "sample": "fml_assemble (fermi-lite/misc.c:280-302), n_threads=1, %d reads at the same coverage, %.1f s" % (m, sec)}
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "sample": "unavailable: %s" % e}
+        try:
+            # parity at the config's own size: the reference's fml_assemble on the SAME 1 M reads with all host threads (its unitig SET does
+            # not depend on the thread count), compared as canonical (min of sequence / reverse complement) sorted sequences
+            from oracle import pyref_fml
+            ropt = pyref_fml.default_opt()
+            ropt.n_threads = os.cpu_count() or 1
+            exp, sec = pyref_fml.assemble(ropt, seqs, quals, off)
+            comp = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+
+            def canon(us):
+                return sorted(min(u["seq"], u["seq"].translate(comp)[::-1]) for u in us)
+            a, b = canon(utgs), canon(exp)
+            out["parity"] = {"n_reads": n, "unitigs": len(b), "mismatches": int(a != b) and (len(set(a) ^ set(b)) or 1),
+                             "against": "oracle/_ref fml_assemble (fermi-lite/misc.c:280-302), %d threads, %.1f s" % (ropt.n_threads, sec)}
+        except Exception as e:
+            out["parity"] = {"error": str(e)}
     return out
 
 
