@@ -299,6 +299,7 @@ __device__ __noinline__ bool extend2_wave(const GCtx &g, int qlen, const QSeq &q
         xprev = (int)(((u32)g.bcast((int)L.XC, G - 1) >> 16) & 0xffffu);
         // words beyond the last row's extent that this block did not stream keep an old valid bit: drop it
         for (int j = xprev + 1 + gl; j <= qlen; j += G) E[j] &= ~0x8000u;
+        g.sync();
         // the next block starts at the first non-zero column of the stream the last row left behind
         int cbn = 1 << 20;
         for (int j = cb + gl; j <= qlen; j += G) if ((E[j] & 0x1fff3fffu) != 0) { cbn = j; break; }

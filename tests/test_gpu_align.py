@@ -303,3 +303,31 @@ def test_reads_with_n_take_the_main_pass(capi):
     assert parity.compare_results(got, exp) == []
     st = capi.last_stats()
     assert st["n_overflow"] < 100 and st["ext_fallback"] > 1000 and st["n_failed"] == 0
+
+
+def test_coordinates_beyond_2_32_vs_live_reference(capi):
+    """A 2.2 Gb reference (forward + reverse text = 4.4 * 10^9 symbols > 2^32): interval coordinates need the high nibbles of the
+    packed list entries / table entries (seed2.cuh), the suffix sorter runs its super-bucket paths, contigs straddle 2^32.  The
+    reference library aligns 60 000 of the reads on the SAME index arrays (host view of the GPU-built index); everything must be
+    bit-identical, and the primaries of all reads must sit at their simulated origin."""
+    from oracle import pyref
+    from seqlib_b200 import synth
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    l_pac = 2_200_000_000
+    pac = synth.reference(l_pac, seed=41)
+    ctg = synth.contigs_for(l_pac, 19)
+    idx = capi.Index.construct_pac(pac, l_pac, ctg, keep_host=True)
+    n = 300_000
+    r, off, pos, strand = synth.reads(pac, l_pac, ctg, n, 150, 0.015, 2e-4, seed=42)
+    ids = cases.ids_for(n)
+    opt = capi.default_opt()
+    got = capi.align(idx, (r, off), opt, ids)
+    rec, mapped = parity.truth_recovery(got, pos, strand, ctg, tol=12)
+    assert mapped > 0.999 and rec > 0.995
+    assert int(got.hits["rb"].max()) > (1 << 32)               # the reverse strand lives beyond 2^32
+    m = 60_000
+    ridx = pyref.RefIndex.from_view(idx.view(), keep=idx)
+    exp, _ = pyref.align(ridx, (r[:m * 150], off[:m + 1]), opt, ids[:m], n_threads=os.cpu_count() or 1)
+    bad, msgs = parity.compare_prefix(got, exp, m)
+    assert bad == 0, msgs
