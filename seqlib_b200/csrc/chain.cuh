@@ -193,7 +193,8 @@ HD int build_chains(const DevIndex &ix, const Opt &opt, int len, const Intv *int
         int count = 0;
         for (i64 k = 0; k < (i64)p.x2 && count < opt.max_occ; k += step, ++count) {
             Seed s;
-            s.rbeg = (i64)sa_lookup(ix, p.x0 + k, ctr);
+            // an interval the seeding machine followed through the text carries its position (seed2.cuh), else bwt_sa
+            s.rbeg = (p.x0 >> 63) ? (i64)(p.x0 & ~(1ull << 63)) : (i64)sa_lookup(ix, p.x0 + k, ctr);
             s.qbeg = (i32)(p.info >> 32);
             s.score = s.len = slen;
             s.next = -1;

@@ -102,6 +102,7 @@ struct SmemList {
         q[0] = (u32)x0; q[128] = (u32)x1;
         q[256] = (u32)(x0 >> 32) | (u32)(x1 >> 32) << 4 | (x2 < 0xffffull ? (u32)x2 : 0xffffu) << 8 | end << 24;
     }
+    __device__ __forceinline__ void put_end(int e, u32 end) { p[e * 384 + 256] = 0xffffu << 8 | end << 24; }
     __device__ __forceinline__ bool take(int e, u64 &x0, u64 &x1, u64 &x2, u32 &end) const
     {
         const u32 *q = p + e * 384;
@@ -180,17 +181,19 @@ __global__ void __launch_bounds__(128, 5) k_seed2(const __grid_constant__ KArgs 
                     const u32 *src = packed + rid * qw;
                     for (int k = 0; k < qw; ++k) myq[k * 128] = src[k];
                     IntvSink out; out.a = A.B.pool.intv + rid * stride; out.n = 0; out.cap = stride; out.overflow = false;
-                    m.init(A.opt, len, CAP, L, Q, out, A.tab.K, 2);
+                    m.init(A.opt, len, CAP, L, Q, out, A.tab.K, 2, A.tab.text);
                     m.start(A.ix);
                 }
             }
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (m.mode != 0) {
-            u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
-            m.request(a, o, s, c, tl, key, fwd);
-            extend_or_lookup(A.ix, A.tab, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
-            m.consume(A.ix, na, no, ns);
+            u64 a, o, s, na = 0, no = 0, ns = 0; int c; u32 key; const void *ga, *gb; ChainView cv;
+            const int kind = m.request(A.ix, a, o, s, c, key, ga, gb);
+            if (kind >= 0) {
+                gather(A.ix, A.tab, kind, key, ga, gb, a, o, s, c, na, no, ns, cv, ctr);
+                if (kind == 0) m.consume(A.ix, na, no, ns); else if (kind == 1) m.consume_chain(A.ix, cv); else m.consume_aux(A.ix);
+            }
         }
     }
     flush_counters(ctr, A.ctrs);
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(128, 5) k_seed2(const __grid_constant__ KArgs 
 // work list, 48 bytes of shared memory per thread -- occupancy and convergence that the mixed kernel cannot have.
 struct NoList {
     __device__ __forceinline__ void put(int, u64, u64, u64, u32) {}
+    __device__ __forceinline__ void put_end(int, u32) {}
     __device__ __forceinline__ bool take(int, u64 &, u64 &, u64 &, u32 &) const { return false; }
     __device__ __forceinline__ u32 end(int) const { return 0; }
 };
@@ -233,25 +237,28 @@ __global__ void __launch_bounds__(128, 8) k_seed3(const __grid_constant__ KArgs 
                     for (int k = 0; k < qw; ++k) myq[k * 128] = src[k];
                     IntvSink out; out.a = A.B.pool.intv + rid * stride; out.n = 0; out.cap = stride; out.overflow = false;
                     NoList L;
-                    m.init(A.opt, len, 0, L, Q, out, A.tab.K, 3);
+                    m.init(A.opt, len, 0, L, Q, out, A.tab.K, 3, 0);
                     m.start3(A.ix, A.B.rec[rid].n_intv);
                 }
             }
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (m.mode != 0) {
-            u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
-            m.request(a, o, s, c, tl, key, fwd);
-            extend_or_lookup(A.ix, A.tab, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
-            m.consume(A.ix, na, no, ns);
+            u64 a, o, s, na = 0, no = 0, ns = 0; int c; u32 key; const void *ga, *gb; ChainView cv;
+            const int kind = m.request(A.ix, a, o, s, c, key, ga, gb);
+            if (kind >= 0) {
+                gather(A.ix, A.tab, kind, key, ga, gb, a, o, s, c, na, no, ns, cv, ctr);
+                if (kind == 0) m.consume(A.ix, na, no, ns); else if (kind == 1) m.consume_chain(A.ix, cv); else m.consume_aux(A.ix);
+            }
         }
     }
     flush_counters(ctr, A.ctrs);
 }
 
-// level j of the prefix-interval tables from level j-1: entry[key] = forward extension of entry[key's first j-1 bases]
-// by its last base, computed by the very code the seeding kernel runs (so a lookup returns what the iterated
-// bwt_extend would have, bwa/bwt.c:262-275, including the coordinates of empty intervals).
+// Builder scratch: level j holds the packed interval of every string of j bases (key = the string, base i in bits 2i..);
+// level j from level j-1: entry[key] = forward extension of entry[key's first j-1 bases] by its last base, computed by the
+// very code the seeding kernel runs (so an entry is what the iterated bwt_extend would have produced, bwa/bwt.c:262-275,
+// including the coordinates of empty intervals).
 __global__ void k_seedtab_level(const DevIndex ix, PIntv *__restrict__ base, int j)
 {
     const u64 key = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,6 +276,40 @@ __global__ void k_seedtab_level(const DevIndex ix, PIntv *__restrict__ base, int
     CtrLocal ctr;
     extend_lean(ix, x1, x0, x2, 3 - c, na, no, ns, ctr);
     *out = pintv_pack(no, na, ns, 0);
+}
+// The chain table (seed2.cuh) from levels 1..K-1: the K-mer's own interval is one more extension, the prefix sizes are read
+// from the levels (consecutive keys share their prefixes: coalesced, cache resident for the low levels).
+__global__ void k_chain_build(const DevIndex ix, const PIntv *__restrict__ lev, ChainEnt *__restrict__ out, int K)
+{
+    const u64 key = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= (1ull << (2 * K))) return;
+    u64 sz[18];
+    u64 x0 = 0, x1 = 0, x2 = 0; u32 e;
+    for (int m = 1; m < K; ++m) {
+        pintv_unpack(lev[seedtab_level_off(m) + (key & ((1ull << (2 * m)) - 1))], x0, x1, x2, e);
+        sz[m] = x2;
+    }
+    const int c = (int)(key >> (2 * (K - 1)));
+    u64 na, no, ns;
+    CtrLocal ctr;
+    extend_lean(ix, x1, x0, x2, 3 - c, na, no, ns, ctr);       // x0..x2 = the (K-1)-prefix
+    sz[K] = ns;
+    out[key] = chain_make(K, no, na, ns, sz);
+}
+
+// The text path of the seeding machine (seed2.cuh) compares reads with ix.text: that is only the FM-index's answer when the text
+// IS the text of the BWT.  BWT[k] == text[SA[k] - 1] for every rank k proves it (SA is a permutation of 0..seq_len); an index whose
+// BWT was built over another randomisation of the N bases (SeqLib's ConstructIndex, src/BWAIndex.cpp:102-125) fails and seeds through the
+// Occ blocks only.
+__global__ void k_verify_text(const DevIndex ix, unsigned long long *__restrict__ bad)
+{
+    const u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > ix.seq_len || k == ix.primary) return;
+    const u64 p = k ? ix.sa[k] : ix.seq_len;                               // rank 0 is the empty suffix (bwa keeps -1 there)
+    if (p == 0 || p > ix.seq_len) { atomicAdd(bad, 1ull); return; }       // rank k != primary has a preceding text symbol
+    const u64 x = k - (k > ix.primary);
+    const OccBlock &b = ix.occ[x >> 6];
+    if (occ_sym(b, (int)(x & 63)) != text_base(ix, (i64)(p - 1))) atomicAdd(bad, 1ull);
 }
 
 // order each read's intervals by (start, end) -- the ks_introsort of mem_collect_intv (bwa/bwamem.c:186); equal keys are identical intervals
@@ -626,11 +667,13 @@ static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
     E.stats.n_launches += 3;
 }
 
-// Prefix-interval tables of an index (seed2.cuh): built once, on the first batch that can use them.
-// K = min(B200_SEED_TAB_K (default 15), floor(log4(seq_len)), what a third of the free HBM holds); 23 GB at K = 15.
-static SeedTab seed_tables(Engine &E, const b200_index *idx)
+// Prefix-chain table of an index (seed2.cuh): built once, on the first batch that can use it.
+// K = min(B200_SEED_TAB_K (default 15), floor(log4(seq_len)), what a third of the free HBM holds); 34 GB at K = 15
+// (+ 5.7 GB of builder scratch, freed).  A batch whose options the table cannot serve (min_seed_len <= K, thresholds > 255)
+// runs on the Occ blocks alone.
+static SeedTab seed_tables(Engine &E, const b200_index *idx, const Opt &opt)
 {
-    SeedTab T; T.base = nullptr; T.K = 0;
+    SeedTab T; T.base = nullptr; T.K = 0; T.text = 0;
     std::lock_guard<std::mutex> g(idx->seedtab_mu);
     if (idx->seedtab_K < 0) {
         static const int want = getenv("B200_SEED_TAB_K") ? atoi(getenv("B200_SEED_TAB_K")) : 15;
@@ -638,25 +681,41 @@ static SeedTab seed_tables(Engine &E, const b200_index *idx)
         while (K > 0 && (1ull << (2 * K)) > idx->seq_len) --K;
         size_t free_b = 0, total_b = 0;
         CU_CHECK(cudaMemGetInfo(&free_b, &total_b));
-        while (K > 0 && seedtab_entries(K) * sizeof(PIntv) > (free_b + dev_pool().pooled) / 3) --K;
-        if (idx->seq_len >= (1ull << 36)) K = 0;
+        while (K > 0 && ((1ull << (2 * K)) * sizeof(ChainEnt) + seedtab_entries(K - 1) * sizeof(PIntv)) > (free_b + dev_pool().pooled) / 3) --K;
+        if (idx->seq_len >= (1ull << 36) || K < 4) K = 0;
         if (K > 0) {
-            void *p = nullptr;
-            if (cudaMalloc(&p, seedtab_entries(K) * sizeof(PIntv)) != cudaSuccess) {
+            void *p = nullptr, *lev = nullptr;
+            const size_t bytes = (1ull << (2 * K)) * sizeof(ChainEnt), lev_bytes = seedtab_entries(K - 1) * sizeof(PIntv);
+            if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMalloc(&lev, lev_bytes) != cudaSuccess) {
                 cudaGetLastError(); dev_pool().trim(0);
-                CU_CHECK(cudaMalloc(&p, seedtab_entries(K) * sizeof(PIntv)));
+                if (!p) CU_CHECK(cudaMalloc(&p, bytes));
+                CU_CHECK(cudaMalloc(&lev, lev_bytes));
             }
-            for (int j = 1; j <= K; ++j) {
+            for (int j = 1; j < K; ++j) {
                 const u64 n = 1ull << (2 * j);
-                k_seedtab_level<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(idx->dev, (PIntv *)p, j);
+                k_seedtab_level<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(idx->dev, (PIntv *)lev, j);
             }
+            k_chain_build<<<(unsigned)(((1ull << (2 * K)) + 255) / 256), 256, 0, E.st>>>(idx->dev, (const PIntv *)lev, (ChainEnt *)p, K);
             CU_CHECK(cudaGetLastError());
             CU_CHECK(cudaStreamSynchronize(E.st));
+            CU_CHECK(cudaFree(lev));
             idx->d_seedtab = p;
         }
         idx->seedtab_K = K;
+        // may the machine follow size-one intervals through the text?  (full suffix array + text == the BWT's text)
+        idx->seed_text_ok = 0;
+        static const int text_on = getenv("B200_SEED_NO_TEXT") ? 0 : 1;
+        if (text_on && idx->dev.sa_shift == 0 && idx->dev.n_sa > idx->seq_len) {
+            unsigned long long *bad = E.small.as<unsigned long long>() + 500, h_bad = 1;
+            CU_CHECK(cudaMemsetAsync(bad, 0, 8, E.st));
+            k_verify_text<<<(unsigned)((idx->seq_len + 256) / 256), 256, 0, E.st>>>(idx->dev, bad);
+            CU_CHECK(cudaMemcpyAsync(&h_bad, bad, 8, cudaMemcpyDeviceToHost, E.st));
+            CU_CHECK(cudaStreamSynchronize(E.st));
+            idx->seed_text_ok = h_bad == 0;
+        }
     }
-    T.base = (const PIntv *)idx->d_seedtab; T.K = idx->seedtab_K;
+    if (seedtab_opt_ok(idx->seedtab_K, opt.min_seed_len, opt.split_width, opt.max_mem_intv)) { T.base = (const ChainEnt *)idx->d_seedtab; T.K = idx->seedtab_K; }
+    T.text = idx->seed_text_ok;
     return T;
 }
 
@@ -817,7 +876,7 @@ static ChunkOut process_chunk(Engine &E, const b200_index *idx, const Opt &opt, 
         k_clear_u32<<<(unsigned)((n + 255) / 256), 256, 0, E.st>>>(E.ovf.as<u32>(), n);
         KArgs A; memset(&A, 0, sizeof(A));
         A.ix = idx->dev; A.opt = opt; A.caps = caps;
-        A.tab = seed_tables(E, idx);
+        A.tab = seed_tables(E, idx, opt);
         A.B.n_reads = n; A.B.seq = d_seq; A.B.seq_off = d_off; A.B.hash_id = d_ids; A.B.ovf = E.ovf.as<u32>(); A.B.rec = E.rec.as<ReadRec>();
         Pools &P = A.B.pool;
         P.intv = E.p_intv.as<Intv>(); P.chains = E.p_chain.as<Chain>(); P.seeds = E.p_seed.as<Seed>(); P.regs = E.p_reg.as<Reg>();
@@ -1206,7 +1265,8 @@ int b200_debug_collect_intv(const b200_index_t *idx, const b200_mem_opt_t *opt, 
         KArgs A; memset(&A, 0, sizeof(A));
         unsigned long long *d_small = E.small.as<unsigned long long>();
         A.ix = idx->dev; A.opt = b->opt; A.caps = big;
-        A.tab = seed_tables(E, idx);
+        A.tab = seed_tables(E, idx, b->opt);
+        A.tab.text = 0;                                    // the reference's coordinates (x0, x1) for every interval
         A.B.n_reads = n; A.B.seq = b->d_seq.as<u8>(); A.B.seq_off = b->d_off.as<i64>(); A.B.hash_id = b->d_ids.as<i64>();
         A.B.ovf = E.ovf.as<u32>(); A.B.rec = E.rec.as<ReadRec>();
         A.B.pool.intv = E.p_intv.as<Intv>(); A.B.pool.cap[POOL_INTV] = cap; A.B.pool.used = d_small + 8;

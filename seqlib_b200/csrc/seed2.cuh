@@ -20,14 +20,33 @@
 // Restrictions (the caller routes everything else to seed.cuh): no base > 3 in the read, len < 65536,
 // seq_len < 2^36, and the list capacity.
 //
-// Prefix-interval tables (SeedTab).  The bi-interval of a string is a pure function of the index, so for every
-// string of length j <= K the result of "extend to that string" is tabulated once per index: level j holds 4^j packed
-// 16-byte intervals, keyed by the string itself (base i in bits 2i..).  Every extension whose RESULT is a string of
-// length <= K -- the first K steps of each forward sweep, the short entries of every backward row, the first K steps
-// of every bwt_seed_strategy1 start -- becomes one 16-byte gather (L2-resident for the low levels) instead of two
-// dependent-free 32-byte Occ gathers.  The tables are produced by the same extend_lean code, level j from level
-// j-1 (k_seedtab_level, engine.cu), so they hold exactly what the iterated bwt_extend (bwa/bwt.c:262-275) computes,
-// and interval lists stay identical to the reference's.  With 180 GB of HBM, K = 15 (23 GB) fits next to a 3 Gb index.
+// Prefix-chain table (SeedTab).  The bi-interval of a string is a pure function of the index, and so is the size of the
+// interval of each of its prefixes.  For every K-mer W the table holds ONE 32-byte entry: the packed bi-interval of W,
+// min(size, 255) of the interval of every proper prefix W[0, m), m = 1..K-1, and a mask whose bit m says "the size of
+// the (m+1)-prefix differs from the size of the m-prefix".  That is everything bwt_smem1a (bwa/bwt.c:289-351) asks of
+// strings of at most K bases: it compares sizes of nested strings for equality (the mask), compares sizes with small
+// thresholds (min_intv <= split_width + 1, max_mem_intv; saturation at 255 is exact for thresholds <= 255), and it
+// needs coordinates only of what it reports (>= min_seed_len > K bases) or extends beyond K bases (the K-mer itself).
+// So ONE gather of the entry of q[sx, sx+K) replaces the first K - 1 extensions of a forward sweep, and ONE gather of
+// the entry of q[i, i+K) answers row i of the backward sweep for every list entry that ends within K bases of i --
+// the triangle of ~K^2/2 short extensions per bwt_smem1a call becomes ~K gathers.  List entries shorter than K bases
+// carry only their end.  The entries are produced from the same extend_lean code (k_chain_build, engine.cu), so
+// every number is exactly what the iterated bwt_extend (bwa/bwt.c:262-275) computes and interval lists stay
+// identical to the reference's.  K = 15: 4^15 x 32 B = 34 GB next to the 52 GB image of a 3 Gb index.
+// The caller switches the table off (K = 0, Occ blocks only) when min_seed_len <= K or a threshold exceeds 255.
+//
+// Text path.  Once a forward sweep of the first pass (min_intv == 1) holds an interval of size ONE, every further
+// extension succeeds iff the next read base equals the text base behind that single occurrence (the FM-index is the index
+// of the forward + reverse-complement text, ix.text).  So the machine reads the occurrence's position from the suffix
+// array (one gather), compares the read with the text word by word (one or two sectors) and gets the end of the sweep --
+// instead of one dependent Occ gather per base.  The same holds for the backward sweep: the size-one entry is the longest
+// of the list, it stays size one until the text before the occurrence differs from the read, so the number of rows it
+// survives is one more comparison; the rows themselves then need no gather for it.  Such an interval is reported with
+// x0 = INTV_TEXT_FLAG | position: the chain stage, the only consumer of x0 (bwt_sa of it, bwa/bwamem.c:279), takes the
+// position as it is.  x1 of a tracked interval is not maintained (nothing reads it); b200_debug_collect_intv runs
+// with the text path off and returns the reference's coordinates.  Needs the full suffix array (sa_shift == 0) and a text
+// that IS the text of the BWT (SeqLib's ConstructIndex builds the BWT over a second randomisation of N bases: the
+// engine verifies BWT[k] == text[SA[k] - 1] for all k before it sets SeedTab::text).
 #pragma once
 #include "common.cuh"
 #include "fmindex.cuh"
@@ -52,9 +71,45 @@ HD void pintv_unpack(const PIntv &p, u64 &x0, u64 &x1, u64 &x2, u32 &end)
     end = p.w3 >> 16;
 }
 
-struct SeedTab { const PIntv *base; int K; };    // K == 0: no tables
-HD u64 seedtab_level_off(int j) { return ((1ull << (2 * j)) - 4) / 3; }      // entries of levels 1..j-1 (a multiple of 4)
+struct alignas(32) ChainEnt { u32 w0, w1, w2, w3; u8 sz[16]; };   // w0..w3 as PIntv with w3 >> 16 = change mask; sz[m] = min(size of the m-prefix, 255)
+struct SeedTab { const ChainEnt *base; int K; int text; };     // K == 0: no table; text != 0: the text path may be used (see SeedMachine)
+HD u64 seedtab_level_off(int j) { return ((1ull << (2 * j)) - 4) / 3; }      // entries of levels 1..j-1 of the builder's scratch (a multiple of 4)
 HD u64 seedtab_entries(int K) { return K > 0 ? seedtab_level_off(K + 1) : 0; }
+HD bool seedtab_opt_ok(int K, int min_seed_len, int split_width, i64 max_mem_intv)
+{
+    return K >= 4 && K <= 16 && min_seed_len > K && split_width >= 0 && split_width < 254 && max_mem_intv <= 255;
+}
+
+// a loaded chain entry
+struct ChainView {
+    u64 x0, x1, x2, szlo, szhi; u32 mask;
+    HD u32 size_sat(int m, int K) const       // min(size of the m-prefix, 255), 1 <= m <= K
+    {
+        if (m >= K) return x2 < 255 ? (u32)x2 : 255u;
+        return (u32)(((m < 8 ? szlo : szhi) >> (8 * (m & 7))) & 255u);
+    }
+    HD bool same(int a, int b) const { return ((mask >> a) & ((1u << (b - a)) - 1u)) == 0; }   // sizes of the a- and b-prefix equal (a < b <= K)
+};
+HD ChainView chain_view(const OccLoad &b)
+{
+    ChainView v; PIntv t; t.w0 = b.c0; t.w1 = b.c1; t.w2 = b.c2; t.w3 = b.c3;
+    u32 e_; pintv_unpack(t, v.x0, v.x1, v.x2, e_);
+    v.mask = e_; v.szlo = b.s0; v.szhi = b.s1;
+    return v;
+}
+// entry of a K-mer from the sizes of its prefixes (s[1..K]) and its interval
+HD ChainEnt chain_make(int K, u64 x0, u64 x1, u64 x2, const u64 *s)
+{
+    ChainEnt e; u32 mask = 0;
+    for (int m = 0; m < 16; ++m) e.sz[m] = 0;
+    for (int m = 1; m < K; ++m) {
+        e.sz[m] = (u8)(s[m] < 255 ? s[m] : 255);
+        if (s[m + 1] != s[m]) mask |= 1u << m;
+    }
+    PIntv p = pintv_pack(x0, x1, x2, mask);
+    e.w0 = p.w0; e.w1 = p.w1; e.w2 = p.w2; e.w3 = p.w3;
+    return e;
+}
 
 // bwt_extend (bwa/bwt.c:262-275) for the one child the callers use, on raw coordinates:
 //   a = the coordinate the Occ ranks are taken on (x[!is_back]), o = the other one, s = interval size.
@@ -98,55 +153,80 @@ HD void extend_lean(const DevIndex &ix, u64 a, u64 o, u64 s, int c, u64 &na, u64
     extend_blocks(ix, b1, b2, kk, ll, dk, dl, o, c, na, no, ns);
 }
 
-// One extension through the tables when the result string is short enough (tl = its length, key = the string), else
-// through the Occ blocks.  Written so that a warp issues ONE pair of 256-bit loads whatever its lanes need: a table
-// lane loads the 32-byte sector that holds its 16-byte entry (twice -- the second request merges in L1).
-// fwd: the caller extends forward (result coordinates swap roles, see SeedMachine::request).
+// The one gather site: the two Occ blocks of an extension (kind 0), the 32-byte chain entry of a K-mer (kind 1; loaded twice,
+// the second request merges in L1), or two sectors the machine will read next (kind 2: a suffix-array entry, text around a
+// position -- the loads pull them into L1, the values are picked up by consume_aux), so that a warp issues ONE pair of
+// 256-bit loads whatever its lanes need.
 template <class Ctr>
-HD void extend_or_lookup(const DevIndex &ix, const SeedTab &tab, int tl, u32 key, bool fwd, u64 a, u64 o, u64 s, int c,
-                         u64 &na, u64 &no, u64 &ns, Ctr &ctr)
+HD void gather(const DevIndex &ix, const SeedTab &tab, int kind, u32 key, const void *ga, const void *gb, u64 a, u64 o, u64 s, int c,
+               u64 &na, u64 &no, u64 &ns, ChainView &cv, Ctr &ctr)
 {
     const u64 k = a - 1, l = k + s;
     const u32 dk = k >= ix.primary, dl = l >= ix.primary;
     const u64 kk = k - dk, ll = l - dl;
     u64 bk = kk >> 6, bl = ll >> 6;
     const OccBlock *p1 = ix.occ + bk, *p2 = ix.occ + bl;
-    u32 half = 0;
-    if (tl) {
-        const PIntv *e = tab.base + seedtab_level_off(tl) + key;
-        half = (u32)(((uintptr_t)e >> 4) & 1);
-        p1 = p2 = (const OccBlock *)((uintptr_t)e & ~(uintptr_t)31);
-        if (tl <= 10) ctr.tab_lo++; else ctr.tab_hi++;
-    } else ctr.occ_blocks += bl != bk ? 2 : 1;
+    if (kind == 1) { p1 = p2 = (const OccBlock *)(tab.base + key); ctr.tab_hi++; }
+    else if (kind == 2) { p1 = (const OccBlock *)ga; p2 = (const OccBlock *)gb; ctr.tab_lo++; }
+    else ctr.occ_blocks += bl != bk ? 2 : 1;
     const OccLoad b1 = load_block_at(p1), b2 = load_block_at(p2);
-    extend_blocks(ix, b1, b2, kk, ll, dk, dl, o, c, na, no, ns);
-    if (tl) {
-        PIntv t;
-        if (half) { t.w0 = (u32)b1.s0; t.w1 = (u32)(b1.s0 >> 32); t.w2 = (u32)b1.s1; t.w3 = (u32)(b1.s1 >> 32); }
-        else { t.w0 = b1.c0; t.w1 = b1.c1; t.w2 = b1.c2; t.w3 = b1.c3; }
-        u64 t0, t1, t2; u32 e_;
-        pintv_unpack(t, t0, t1, t2, e_);
-        na = fwd ? t1 : t0; no = fwd ? t0 : t1; ns = t2;
-    }
+    if (kind == 1) cv = chain_view(b1);
+    else if (kind == 0) extend_blocks(ix, b1, b2, kk, ll, dk, dl, o, c, na, no, ns);
+#if defined(__CUDA_ARCH__)
+    else asm volatile("" :: "r"(b1.c0), "r"(b2.c0));      // keep the prefetching loads
+#endif
 }
+
+HD u64 ld_u64(const u64 *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// 16 bases of the text from position P on, base t in bits 2t.. (reads the word after P's as well: the text has a padding word)
+HD u32 text_bits32(const DevIndex &ix, u64 P)
+{
+    const u64 w = ld_u64(ix.text + (P >> 5)), w2 = ld_u64(ix.text + (P >> 5) + 1);
+    const int sh = (int)(P & 31) * 2;
+    return (u32)(sh ? (w >> sh) | (w2 << (64 - sh)) : w);
+}
+HD int ctz32(u32 x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+HD int clz32(u32 x)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return __builtin_clz(x);
+#endif
+}
+static const u64 INTV_TEXT_FLAG = 1ull << 63;      // Intv::x0 with this bit: the low bits are the text position of the (single) occurrence
 
 // One read's seeding as a resumable machine.  List: get(e) / set(e, PIntv) over `cap` entries; Query: operator[](i) in 0..3.
 template <class List, class Query>
 struct SeedMachine {
-    enum { M_DONE = 0, M_FWD, M_BWD, M_P3, M_TASK, M_ENDFWD, M_LASTROW };
-    int mode, pass, x, k2, old_n, sx, i, j, nprev, ncurr, top, ret, last_start, first, ovf;
+    enum { M_DONE = 0, M_FWD, M_BWD, M_P3, M_FWDC, M_FSA, M_FTX, M_BTX, M_TASK, M_ENDFWD, M_LASTROW };
+    int mode, pass, x, k2, old_n, sx, i, j, nprev, ncurr, top, ret, last_start, first, ovf, lastlen;
     int len, cap, min_seed_len, split_len, split_width, max_intv3, min_intv, K, last_pass;
     u64 x0, x1, x2, lastcurr;     // ik of the forward sweeps / last size pushed in this backward row
     u64 p0, p1, p2;               // the list entry being extended backwards
     u32 iend, pend;
-    bool have_p;                  // p0..p2 hold the entry's interval (false: only its end was read)
+    u64 tpos; int tleft, textok; bool tracked;      // text path: position of q[sx] of the tracked (size-one, longest) entry, rows it survives
     List L; Query q; IntvSink out;
 
     // last_pass_ = 2: stop after the SMEM passes (bwt_smem1a calls, re-seeding); start3() then runs the third pass
     // (bwt_seed_strategy1) on its own -- k_seed2 / k_seed3 split them so that a warp never mixes the two kinds of lanes
-    HD void init(const Opt &opt, int len_, int cap_, const List &L_, const Query &q_, const IntvSink &out_, int K_ = 0, int last_pass_ = 3)
+    HD void init(const Opt &opt, int len_, int cap_, const List &L_, const Query &q_, const IntvSink &out_, int K_ = 0, int last_pass_ = 3, int textok_ = 0)
     {
-        len = len_; cap = cap_; L = L_; q = q_; out = out_; K = K_; last_pass = last_pass_;
+        len = len_; cap = cap_; L = L_; q = q_; out = out_; K = K_; last_pass = last_pass_; textok = textok_; tracked = false; tleft = 0; tpos = 0;
         min_seed_len = opt.min_seed_len;
         split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
         split_width = opt.split_width;
@@ -170,6 +250,12 @@ struct SeedMachine {
         L.put(--top, x0, x1, x2, iend);
         ret = (int)iend;
     }
+    HD void push_fwd_end(u32 end)          // a string shorter than K bases: only its end is kept
+    {
+        if (top == 0) { fail(); return; }
+        L.put_end(--top, end);
+        ret = (int)end;
+    }
 
     // Everything between two extensions that is not the per-extension bookkeeping: ending a forward sweep, the row
     // i == -1 of a backward sweep, picking the next bwt_smem1 / bwt_seed_strategy1 call (bwa/bwamem.c:150-184).
@@ -180,14 +266,20 @@ struct SeedMachine {
             if (mode == M_ENDFWD) {
                 nprev = cap - top; ncurr = 0; j = 0; first = 1; last_start = 0;
                 i = sx - 1;
-                mode = i < 0 ? M_LASTROW : M_BWD;
+                mode = i < 0 ? M_LASTROW : tracked ? M_BTX : M_BWD;
             } else if (mode == M_LASTROW) {
                 // bwa/bwt.c:325-345 with c = -1: only the longest survivor can be reported, with start 0
                 if (first || 0 < last_start) {
                     u64 e0, e1, e2; u32 e;
-                    const bool ok = L.take(top, e0, e1, e2, e);
-                    if ((int)e >= min_seed_len) { if (!ok) { fail(); return; } emit(e0, e1, e2, (u64)e); if (ovf) return; }
+                    if (tracked) {
+                        e = L.end(top);
+                        if ((int)e >= min_seed_len) { emit(INTV_TEXT_FLAG | (tpos - (u64)sx), 0, 1, (u64)e); if (ovf) return; }
+                    } else {
+                        const bool ok = L.take(top, e0, e1, e2, e);
+                        if ((int)e >= min_seed_len) { if (!ok) { fail(); return; } emit(e0, e1, e2, (u64)e); if (ovf) return; }
+                    }
                 }
+                tracked = false;
                 mode = M_TASK;
                 if (pass == 1) x = ret;
             } else if (mode == M_TASK) {
@@ -212,12 +304,13 @@ struct SeedMachine {
                 }
                 if (pass == 3) {
                     if (last_pass < 3 || x >= len) { mode = M_DONE; return; }
-                    // the first min(K, min_seed_len) - 1 extensions of a bwt_seed_strategy1 start (bwa/bwt.c:355-379) can
-                    // neither report nor stop (i - x < min_seed_len): one table lookup of q[x, x + jump) replaces them
-                    const int jump = K < min_seed_len ? K : min_seed_len;
-                    if (jump >= 2 && x + jump <= len) {
+                    // the first K - 1 extensions of a bwt_seed_strategy1 start (bwa/bwt.c:355-379) can neither report nor
+                    // stop (i - x < min_seed_len): the interval of q[x, x + K) in the chain entry replaces them
+                    // (K < min_seed_len: with fewer than K bases left nothing can be reported any more)
+                    if (K > 0) {
+                        if (x + K > len) { mode = M_DONE; return; }
                         x0 = x1 = 1; x2 = 0;             // placeholders: the lookup result overwrites them
-                        i = x + jump - 1;
+                        i = x + K - 1;
                         mode = M_P3;
                         return;
                     }
@@ -228,6 +321,8 @@ struct SeedMachine {
                     return;
                 }
                 // begin the forward sweep of bwt_smem1a at sx
+                tracked = false;
+                if (K > 0) { top = cap; mode = M_FWDC; return; }       // through the chain entry of q[sx, sx + K)
                 Intv t; set_intv(ix, q[sx], t);
                 x0 = t.x0; x1 = t.x1; x2 = t.x2; iend = (u32)(sx + 1);
                 top = cap;
@@ -255,29 +350,165 @@ struct SeedMachine {
         settle(ix);
     }
 
-    // The next extension and the string it produces: q[st, st + ln).  tl = ln when a table level holds it, else 0.
-    // A backward step that a table answers needs only the END of its list entry (the string is q[i, end)): the entry's
-    // interval is fetched lazily, when the entry dies as an SMEM -- lists that keep intervals outside shared memory
-    // (k_seed2's HybridList) then touch them in a third of the steps only.
-    HD void request(u64 &a, u64 &o, u64 &s, int &c, int &tl, u32 &key, bool &fwd)
+    // Row i of a backward sweep starts with the tracked entry: no gather, the text comparison already said how long it lives.
+    HD void tracked_top()
     {
-        fwd = mode != M_BWD;
+        if (tleft > 0) {
+            if (nprev == 1) {          // alone: all the rows until it dies or reaches the read's start
+                const int d = tleft < i + 1 ? tleft : i + 1;
+                tleft -= d; i -= d;
+                if (i < 0) mode = M_LASTROW;
+            } else { --tleft; ncurr = 1; lastcurr = 1; lastlen = K + 1; j = 1; }      // kept in slot top + 0, where it is
+            return;
+        }
+        tracked = false;
+        const u32 e = L.end(top);
+        if (first || i + 1 < last_start) {
+            first = 0; last_start = i + 1;
+            if ((int)e - (i + 1) >= min_seed_len) {
+                emit(INTV_TEXT_FLAG | (tpos - (u64)(sx - (i + 1))), 0, 1, (u64)(i + 1) << 32 | e);
+                if (ovf) return;
+            }
+        }
+        j = 1;
+        if (j == nprev) { mode = M_TASK; if (pass == 1) x = ret; }
+    }
+
+    // The next gather.  Returns its kind: 0 = an extension through the Occ blocks (coordinate a, other coordinate o, size s,
+    // base c); 1 = the chain entry of the K-mer `key` -- the start of a forward sweep, the jump of a third-pass start, or a
+    // backward row whose remaining entries all end within K bases of i (they are sorted longest first); 2 = the sectors at
+    // ga / gb (text path); -1 = the read finished meanwhile, nothing to fetch.
+    HD int request(const DevIndex &ix, u64 &a, u64 &o, u64 &s, int &c, u32 &key, const void *&ga, const void *&gb)
+    {
+        while (mode == M_BWD && j == 0 && tracked) {
+            tracked_top();
+            if (mode > M_BTX) settle(ix);
+        }
+        if (mode == M_DONE) return -1;
+        key = 0u; a = 1; o = 1; s = 0; c = 0; ga = gb = ix.occ;
         if (mode == M_BWD) {
             pend = L.end(top + j);
             const int ln = (int)pend - i;
-            tl = ln <= K ? ln : 0;
             c = q[i];
-            if (tl) { have_p = false; a = 1; o = 1; s = 0; key = q.key(i, ln); return; }
-            have_p = true;
+            if (ln <= K) { key = q.key(i, K); return 1; }
             if (!L.take(top + j, p0, p1, p2, pend)) { p0 = p1 = 1; p2 = 0; fail(); }      // the list did not keep this interval: spill path
-            a = p0; o = p1; s = p2; key = 0u;
-            return;
+            a = p0; o = p1; s = p2;
+            return 0;
+        }
+        if (mode == M_FWDC) { key = q.key(sx, K); return 1; }
+        if (mode >= M_FSA) {        // M_FSA, M_FTX, M_BTX
+            const u8 *t0 = (const u8 *)ix.text;
+            if (mode == M_FSA) ga = gb = (const u8 *)ix.sa + ((x0 * 8) & ~31ull);
+            else if (mode == M_FTX) {
+                const u64 sec = (tpos + (u64)(i - sx)) >> 7, last = (ix.seq_len + 31) >> 7;     // the text has (seq_len + 31) / 32 + 1 words
+                ga = t0 + (sec << 5); gb = t0 + ((sec < last ? sec + 1 : sec) << 5);
+            } else {
+                const u64 sec = (tpos ? tpos - 1 : 0) >> 7;
+                ga = t0 + (sec << 5); gb = t0 + ((sec ? sec - 1 : 0) << 5);
+            }
+            return 2;
         }
         a = x1; o = x0; s = x2; c = 3 - q[i];
-        const int st = mode == M_FWD ? sx : x;
-        const int ln = i + 1 - st;
-        tl = ln <= K ? ln : 0;
-        key = tl ? q.key(st, ln) : 0u;
+        if (mode == M_P3 && K > 0 && i + 1 - x == K) { key = q.key(x, K); return 1; }
+        return 0;
+    }
+
+    // text path: the prefetched sectors are in L1, the machine reads what it needs from them
+    HD void consume_aux(const DevIndex &ix)
+    {
+        if (mode == M_FSA) { tpos = ld_u64(ix.sa + x0); tracked = true; mode = M_FTX; return; }
+        if (mode == M_FTX) {
+            // the interval of q[sx, i) has size one and its occurrence starts at tpos: q[i, len) against the text behind it
+            // (bwa/bwt.c:303-320 with ok[c].x[2] in {0, 1}: the sweep ends at the first difference, the text's or the read's end)
+            const u64 P = tpos + (u64)(i - sx);
+            int n = len - i;
+            if ((u64)n > ix.seq_len - P) n = (int)(ix.seq_len - P);
+            int t = 0;
+            while (t < n) {
+                const int cnt = n - t < 16 ? n - t : 16;
+                u32 d = text_bits32(ix, P + (u64)t) ^ q.key(i + t, 16);
+                if (cnt < 16) d &= (1u << (2 * cnt)) - 1u;
+                if (d) { t += ctz32(d) >> 1; break; }
+                t += cnt;
+            }
+            i += t; iend = (u32)i; x2 = 1;
+            push_fwd();
+            if (ovf) return;
+            mode = M_ENDFWD;
+            settle(ix);
+            return;
+        }
+        // M_BTX: q[sx-1], q[sx-2], ... against the text before the occurrence = the number of rows the tracked entry survives
+        int n = sx;
+        if ((u64)n > tpos) n = (int)tpos;
+        int t = 0;
+        while (t < n) {
+            const int cnt = n - t < 16 ? n - t : 16;
+            u32 d = text_bits32(ix, tpos - (u64)(t + cnt)) ^ q.key(sx - t - cnt, 16);
+            d <<= 32 - 2 * cnt;                 // base cnt-1 of the chunk (the one next to what matched so far) on top
+            if (d) { t += clz32(d) >> 1; break; }
+            t += cnt;
+        }
+        tleft = t;
+        mode = M_BWD;
+    }
+
+    // A chain entry arrives: the whole forward prefix (M_FWDC), the rest of a backward row (M_BWD), or a third-pass jump.
+    HD void consume_chain(const DevIndex &ix, const ChainView &E)
+    {
+        if (mode == M_P3) { consume(ix, E.x1, E.x0, E.x2); return; }
+        if (mode == M_FWDC) {
+            // bwa/bwt.c:303-320 for the strings q[sx, sx + m), m = 1 .. avail
+            const int avail = len - sx < K ? len - sx : K;
+            int m = 1; bool stop = false;
+            while (m < avail) {
+                if ((E.mask >> m) & 1u) {                      // the (m+1)-prefix has another size: the m-prefix is listed
+                    push_fwd_end((u32)(sx + m));
+                    if (ovf) return;
+                    if (E.size_sat(m + 1, K) < (u32)min_intv) { stop = true; break; }
+                }
+                ++m;
+            }
+            if (!stop) {
+                if (sx + m == len) {                           // ran into the read's end: the last string is listed
+                    if (m == K) { x0 = E.x0; x1 = E.x1; x2 = E.x2; iend = (u32)len; push_fwd(); }
+                    else push_fwd_end((u32)len);
+                    if (ovf) return;
+                    stop = true;
+                } else {                                       // m == K: on with the Occ blocks
+                    x0 = E.x0; x1 = E.x1; x2 = E.x2; iend = (u32)(sx + K);
+                    i = sx + K;
+                    mode = textok && x2 == 1 && min_intv == 1 ? M_FSA : M_FWD;
+                }
+            }
+            if (stop) { mode = M_ENDFWD; settle(ix); }
+            return;
+        }
+        // M_BWD, row i: entries j .. nprev-1 produce q[i, end) of at most K bases (bwa/bwt.c:325-345)
+        for (; j < nprev; ++j) {
+            const u32 e = L.end(top + j);
+            const int ln = (int)e - i;
+            if (E.size_sat(ln, K) < (u32)min_intv) {
+                if (ncurr == 0 && (first || i + 1 < last_start)) {
+                    first = 0; last_start = i + 1;
+                    if ((int)e - (i + 1) >= min_seed_len) { fail(); return; }     // cannot happen: min_seed_len > K
+                }
+            } else {
+                bool same = false;
+                if (ncurr > 0) same = lastlen > K ? (lastcurr == E.x2 && E.same(ln, K)) : E.same(ln, lastlen);
+                if (!same) {
+                    if (ln == K) { L.put(top + ncurr, E.x0, E.x1, E.x2, e); lastcurr = E.x2; }
+                    else L.put_end(top + ncurr, e);
+                    ++ncurr; lastlen = ln;
+                }
+            }
+        }
+        if (ncurr == 0) { mode = M_TASK; if (pass == 1) x = ret; }
+        else {
+            nprev = ncurr; ncurr = 0; j = 0;
+            if (--i < 0) mode = M_LASTROW;
+        }
+        if (mode > M_BTX) settle(ix);
     }
 
     HD void consume(const DevIndex &ix, u64 na, u64 no, u64 ns)
@@ -287,14 +518,13 @@ struct SeedMachine {
                 if (ncurr == 0 && (first || i + 1 < last_start)) {
                     first = 0; last_start = i + 1;
                     if ((int)pend - (i + 1) >= min_seed_len) {
-                        if (!have_p) { u32 e_; have_p = true; if (!L.take(top + j, p0, p1, p2, e_)) { fail(); return; } }
                         emit(p0, p1, p2, (u64)(i + 1) << 32 | pend);
                         if (ovf) return;
                     }
                 }
             } else if (ncurr == 0 || ns != lastcurr) {
                 L.put(top + ncurr, na, no, ns, pend);
-                ++ncurr; lastcurr = ns;
+                ++ncurr; lastcurr = ns; lastlen = K + 1;
             }
             if (++j == nprev) {
                 if (ncurr == 0) { mode = M_TASK; if (pass == 1) x = ret; }
@@ -313,6 +543,7 @@ struct SeedMachine {
             if (!stop) {
                 x1 = na; x0 = no; x2 = ns; iend = (u32)(i + 1);
                 if (++i == len) { push_fwd(); if (ovf) return; stop = true; }
+                else if (textok && ns == 1 && min_intv == 1) mode = M_FSA;
             }
             if (stop) mode = M_ENDFWD;
         } else {        // M_P3
@@ -325,7 +556,7 @@ struct SeedMachine {
                 if (++i >= len) mode = M_DONE;
             }
         }
-        if (mode > M_P3) settle(ix);
+        if (mode > M_BTX) settle(ix);
     }
 };
 
@@ -333,13 +564,15 @@ struct SeedMachine {
 struct ArrayList {
     PIntv *p;
     HD void put(int e, u64 x0, u64 x1, u64 x2, u32 end) { p[e] = pintv_pack(x0, x1, x2, end); }
-    HD bool take(int e, u64 &x0, u64 &x1, u64 &x2, u32 &end) const { pintv_unpack(p[e], x0, x1, x2, end); return true; }
+    HD void put_end(int e, u32 end) { p[e] = pintv_pack(0, 0, 0, end); }          // x0 == 0: no interval (every interval starts at >= 1)
+    HD bool take(int e, u64 &x0, u64 &x1, u64 &x2, u32 &end) const { pintv_unpack(p[e], x0, x1, x2, end); return x0 != 0; }
     HD u32 end(int e) const { return p[e].w3 >> 16; }
 };
 struct ByteQuery {
-    const u8 *p;
+    const u8 *p; int n;
     HD int operator[](int i) const { return p[i]; }
-    HD u32 key(int st, int ln) const { u32 k = 0; for (int t = 0; t < ln; ++t) k |= (u32)p[st + t] << (2 * t); return k; }
+    // bases [st, st + ln), base t in bits 2t..; positions beyond the read count as base 0
+    HD u32 key(int st, int ln) const { u32 k = 0; for (int t = 0; t < ln && st + t < n; ++t) k |= (u32)p[st + t] << (2 * t); return k; }
 };
 
 HD bool seed2_eligible(const DevIndex &ix, int len, const u8 *seq)
@@ -365,18 +598,20 @@ HD bool collect_intv_v2(const DevIndex &ix, const Opt &opt, int len, const u8 *s
                         const SeedTab *tab = nullptr)
 {
     ArrayList L; L.p = list;
-    ByteQuery q; q.p = seq;
+    ByteQuery q; q.p = seq; q.n = len;
     SeedTab none; none.base = nullptr; none.K = 0;
-    const SeedTab &T = tab ? *tab : none;
+    const SeedTab &T = tab && seedtab_opt_ok(tab->K, opt.min_seed_len, opt.split_width, opt.max_mem_intv) ? *tab : none;
     SeedMachine<ArrayList, ByteQuery> m;
     for (int part = 0; part < 2; ++part) {             // the SMEM passes, then bwt_seed_strategy1: two machines, like k_seed2 + k_seed3
-        if (part == 0) { m.init(opt, len, cap, L, q, out, T.K, 2); m.start(ix); }
-        else { const int n0 = m.out.n; IntvSink o2 = m.out; m.init(opt, len, cap, L, q, o2, T.K, 3); m.start3(ix, n0); }
+        const int textok = tab && tab->text && ix.sa_shift == 0;
+        if (part == 0) { m.init(opt, len, cap, L, q, out, T.K, 2, textok); m.start(ix); }
+        else { const int n0 = m.out.n; IntvSink o2 = m.out; m.init(opt, len, cap, L, q, o2, T.K, 3, textok); m.start3(ix, n0); }
         while (m.mode != 0) {
-            u64 a, o, s, na, no, ns; int c, tl; u32 key; bool fwd;
-            m.request(a, o, s, c, tl, key, fwd);
-            extend_or_lookup(ix, T, tl, key, fwd, a, o, s, c, na, no, ns, ctr);
-            m.consume(ix, na, no, ns);
+            u64 a, o, s, na = 0, no = 0, ns = 0; int c; u32 key; const void *ga, *gb; ChainView cv;
+            const int kind = m.request(ix, a, o, s, c, key, ga, gb);
+            if (kind < 0) break;
+            gather(ix, T, kind, key, ga, gb, a, o, s, c, na, no, ns, cv, ctr);
+            if (kind == 0) m.consume(ix, na, no, ns); else if (kind == 1) m.consume_chain(ix, cv); else m.consume_aux(ix);
         }
         if (m.ovf) break;
     }

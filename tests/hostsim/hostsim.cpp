@@ -73,9 +73,14 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
     bool dbg = getenv("HOSTSIM_DEBUG") != 0;
     int seed_v2 = getenv("HOSTSIM_SEED_V2") ? atoi(getenv("HOSTSIM_SEED_V2")) : 0;   // list capacity of the seed2.cuh machine, 0 = seed_fsm
     int tab_K = getenv("HOSTSIM_SEED_TAB_K") ? atoi(getenv("HOSTSIM_SEED_TAB_K")) : 0;   // prefix-interval tables for the seed2 machine
-    if (seed_v2 && tab_K > 0 && hi->tab.K != tab_K) hi->build_tab(tab_K);
-    const SeedTab *tabp = seed_v2 && tab_K > 0 ? &hi->tab : nullptr;
+    if (seed_v2 && tab_K > 0) { if (hi->tab.K != tab_K) hi->build_tab(tab_K); }
+    else { hi->tab.base = nullptr; hi->tab.K = 0; }
+    const int seed_text = getenv("HOSTSIM_SEED_TEXT") ? atoi(getenv("HOSTSIM_SEED_TEXT")) : 0;      // the machine's text path (needs the full suffix array)
+    if (seed_v2 && seed_text) { hi->densify_sa(); hi->tab.text = hi->verify_text() ? 1 : 0; if (!hi->tab.text) fprintf(stderr, "hostsim: text != text of the BWT\n"); }
+    else hi->tab.text = 0;
+    const SeedTab *tabp = seed_v2 && (tab_K > 0 || seed_text) ? &hi->tab : nullptr;
     std::vector<std::vector<Reg> > raws(n);
+    unsigned long long tot_occ = 0, tot_tab = 0;
     for (int64_t r = 0; r < n; ++r) {
         for (int pass = 0; pass < 2; ++pass) {
             const Caps &c = caps[pass];
@@ -85,6 +90,7 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
             if (dbg) fprintf(stderr, "read %ld pass %d\n", (long)r, pass);
             if (seed_v2) stage_seed_v2(ix, opt, c, B, r, s1.data(), ctr, seed_v2, tabp);
             else stage_seed(ix, opt, c, B, r, s1.data(), ctr);
+            tot_occ += ctr.occ_blocks; tot_tab += ctr.tab_hi;
             stage_chain(ix, opt, c, B, r, s2.data(), ctr, logtab.data(), (int)logtab.size());
             stage_extend(ix, opt, c, B, r, s3.data(), ctr);
             raws[r].assign(B.pool.regs + rec[r].reg_off, B.pool.regs + rec[r].reg_off + rec[r].n_regs);
@@ -126,6 +132,7 @@ void *hostsim_align(void *hidx, const b200_mem_opt_t *o, int64_t n, const char *
         R->chn_off[r + 1] = (int64_t)R->chn.size() / 6;
         R->reg_off[r + 1] = (int64_t)R->regs.size();
     }
+    if (getenv("HOSTSIM_STATS")) fprintf(stderr, "hostsim: seeding of %ld reads: %.1f Occ blocks, %.1f chain entries per read\n", (long)n, (double)tot_occ / (n ? n : 1), (double)tot_tab / (n ? n : 1));
     return R;
 }
 

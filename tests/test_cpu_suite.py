@@ -47,27 +47,31 @@ def _sim_index_for_tiny():
     return simlib.SimIndex(tidx.view(), keep=tidx), tidx
 
 
-@pytest.mark.parametrize("name,small,seed_v2,tab_k", [("sim1_5k", False, 0, 0), ("bcr_2k", False, 0, 0), ("bcr_2k", True, 0, 0),
-                                                      ("sim1_5k", False, 24, 0), ("bcr_2k", False, 24, 0), ("bcr_2k", False, 7, 0),
-                                                      ("sim1_5k", False, 24, 8), ("bcr_2k", False, 24, 8), ("bcr_2k", False, 24, 3),
-                                                      ("bcr_2k", False, 7, 6)])
-def test_stage_functions_on_cpu_vs_golden(name, small, seed_v2, tab_k, monkeypatch):
+@pytest.mark.parametrize("name,small,seed_v2,tab_k,text", [("sim1_5k", False, 0, 0, 0), ("bcr_2k", False, 0, 0, 0), ("bcr_2k", True, 0, 0, 0),
+                                                           ("sim1_5k", False, 24, 0, 0), ("bcr_2k", False, 24, 0, 0), ("bcr_2k", False, 7, 0, 0),
+                                                           ("sim1_5k", False, 24, 8, 0), ("bcr_2k", False, 24, 8, 0), ("bcr_2k", False, 24, 4, 0),
+                                                           ("sim1_5k", False, 24, 5, 0), ("bcr_2k", False, 7, 6, 0),
+                                                           ("sim1_5k", False, 24, 8, 1), ("bcr_2k", False, 24, 9, 1), ("sim1_5k", False, 24, 0, 1),
+                                                           ("bcr_2k", False, 9, 6, 1)])
+def test_stage_functions_on_cpu_vs_golden(name, small, seed_v2, tab_k, text, monkeypatch):
     """The per-read device functions, compiled for the host (tests/hostsim), reproduce the golden vectors;
     `small` forces every read through the spill path; seed_v2 = work-list capacity of the single-extension-site
     seeding machine (seed2.cuh) the GPU kernel runs (0: the reference-shaped loops; 7: most reads overflow the list
-    and fall back, as in the kernel's spill pass); tab_k = levels of the prefix-interval tables that replace the
-    extensions to strings of at most tab_k bases (interval lists must stay identical)."""
+    and fall back, as in the kernel's spill pass); tab_k = depth of the prefix-chain table that answers everything
+    bwt_smem1a asks about strings of at most tab_k bases (interval lists must stay identical); text = the machine
+    follows size-one intervals through the text (same hits; such an interval carries its text position instead of x0)."""
     if seed_v2:
         monkeypatch.setenv("HOSTSIM_SEED_V2", str(seed_v2))
     else:
         monkeypatch.delenv("HOSTSIM_SEED_V2", raising=False)
     monkeypatch.setenv("HOSTSIM_SEED_TAB_K", str(tab_k))
+    monkeypatch.setenv("HOSTSIM_SEED_TEXT", str(text))
     from oracle import pyref
     if not pyref.have_ref():
         pytest.skip("needs oracle/_ref to parse the bwa index for the host harness")
     import simlib
     gold, z = goldenlib.load(name)
-    sidx, _keep = _sim_index_for_tiny()
+    sidx, tidx = _sim_index_for_tiny()
     reads = cases.read_lines(goldenlib.path(name + ".txt"))
     if small:
         reads = reads[:600]
@@ -80,7 +84,31 @@ def test_stage_functions_on_cpu_vs_golden(name, small, seed_v2, tab_k, monkeypat
             assert np.array_equal(got.hits[f], gold.hits[f][:k]), f
     else:
         assert parity.compare_results(got, gold) == []
-        assert np.array_equal(got.intv_off, z["intv_off"]) and np.array_equal(got.intv, z["intv"])
+        assert np.array_equal(got.intv_off, z["intv_off"])
+        gi, zi = got.intv, z["intv"]
+        assert np.array_equal(gi["x2"], zi["x2"]) and np.array_equal(gi["info"], zi["info"])
+        flagged = (gi["x0"] >> np.uint64(63)) != 0
+        assert np.array_equal(gi["x0"][~flagged], zi["x0"][~flagged])
+        if not text:
+            assert not flagged.any() and np.array_equal(gi["x1"], zi["x1"])
+        else:
+            # a flagged interval: size one, and the text at its position spells the read's substring
+            assert (flagged.mean() > 0.1 or seed_v2 < 24) and (gi["x2"][flagged] == 1).all()
+            a = tidx.arrays()
+            l_pac = int(a["l_pac"])
+            fwd = np.unpackbits(np.frombuffer(a["pac"], dtype=np.uint8)[: (l_pac + 3) // 4]).reshape(-1, 2)
+            fwd = (fwd[:, 0] * 2 + fwd[:, 1])[:l_pac].astype(np.uint8)
+            txt = np.concatenate([fwd, 3 - fwd[::-1]])
+            code = np.full(256, 4, np.uint8)
+            for i, ch in enumerate("ACGT"):
+                code[ord(ch)] = i; code[ord(ch.lower())] = i
+            rid = np.searchsorted(z["intv_off"], np.arange(len(gi)), side="right") - 1
+            idxs = np.nonzero(flagged)[0]
+            for t in idxs[:: max(1, len(idxs) // 3000)]:
+                pos = int(gi["x0"][t] & np.uint64((1 << 63) - 1))
+                st, en = int(gi["info"][t] >> np.uint64(32)), int(gi["info"][t] & np.uint64(0xffffffff))
+                q = code[np.frombuffer(reads[rid[t]].encode(), dtype=np.uint8)][st:en]
+                assert np.array_equal(txt[pos:pos + en - st], q), (t, pos, st, en)
 
 
 def test_long_reads_seed_sw_filter_on_cpu_vs_reference(monkeypatch):
