@@ -144,8 +144,8 @@ __global__ void k_pack_reads(const u8 *__restrict__ seq, const i64 *__restrict__
     if (n_base || (w == 0 && len > (i64)qw * 16)) atomicOr(bad + r, 1u);
 }
 
-template <int CAP>
-__global__ void __launch_bounds__(128, 5) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride)
+template <int CAP, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride)
 {
     // The SMEM passes (bwt_smem1a from every start, re-seeding of long SMEMs).  Tried and dropped (round 2): L2 eviction-policy
     // hints / a persisting window for the low table levels (no change in hit rate or time, profiles/r02_seed_l2hint_ab.txt);
@@ -608,23 +608,23 @@ static void launch_stage(Engine &E, KArgs &A, int grid, int tpb = 128)
 }
 
 // Main-pass seeding with k_seed2: usable for batches of short reads on indexes below 2^36 symbols.
-static const int SEED2_CAP = 24;          // work-list entries per read in shared memory
+static const int SEED2_CAP = 16;          // long work-list entries per read in shared memory (a power of two: ring)
 static const int SEED2_STRIDE = 40;       // interval slots per read in the pool
 static bool seed2_enabled() { static int on = getenv("B200_SEED_V1") ? 0 : 1; return on != 0; }
 static bool seed2_usable(const KArgs &A)
 {
     return seed2_enabled() && !A.order && A.caps.maxlen <= 255 && A.ix.seq_len < (1ull << 36) && A.B.pool.cap[POOL_INTV] >= A.B.n_reads * (i64)SEED2_STRIDE;
 }
-template <int CAP>
+template <int CAP, int MINB>
 static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
 {
     size_t smem = (size_t)128 * (CAP * 12 + (qw + 1) * 4);
-    CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     int per = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP>, 128, smem));
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP, MINB>, 128, smem));
     if (per < 1) per = 1;
     { static const int occ = getenv("B200_OCC_SEED") ? atoi(getenv("B200_OCC_SEED")) : 0; if (occ > 0 && occ < per) per = occ; }
-    k_seed2<CAP><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
+    k_seed2<CAP, MINB><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
     CU_CHECK(cudaGetLastError());
     // then the third pass
     size_t smem3 = (size_t)128 * (qw + 1) * 4;
@@ -644,9 +644,11 @@ static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
     k_set_u64<<<1, 1, 0, E.st>>>(A.B.pool.used + POOL_INTV, (unsigned long long)(n * SEED2_STRIDE));   // spill-pass allocations start after the fixed slots
     static int cap_sel = getenv("B200_SEED_CAP") ? atoi(getenv("B200_SEED_CAP")) : SEED2_CAP;
     CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
-    if (cap_sel == 16) launch_seed2_cap<16>(E, A, qw);
-    else if (cap_sel == 32) launch_seed2_cap<32>(E, A, qw);
-    else launch_seed2_cap<SEED2_CAP>(E, A, qw);
+    static int minb = getenv("B200_SEED_MINB") ? atoi(getenv("B200_SEED_MINB")) : 6;
+    if (cap_sel == 8) launch_seed2_cap<8, 6>(E, A, qw);
+    else if (cap_sel == 32) launch_seed2_cap<32, 5>(E, A, qw);
+    else if (minb == 6) launch_seed2_cap<SEED2_CAP, 6>(E, A, qw);
+    else launch_seed2_cap<SEED2_CAP, 5>(E, A, qw);
     CU_CHECK(cudaGetLastError());
     k_sort_intv<<<(unsigned)((n + 127) / 128), 128, 0, E.st>>>(A.B.rec, A.B.ovf, n, A.B.pool.intv);
     CU_CHECK(cudaGetLastError());

@@ -127,7 +127,7 @@ HD void stage_seed_v2(const DevIndex &ix, const Opt &opt, const Caps &caps, cons
     if (B.ovf[rid]) return;
     Intv *prev = (Intv *)scratch, *curr = prev + (caps.maxlen + 1);
     IntvSink out; out.a = curr + (caps.maxlen + 1); out.n = 0; out.cap = caps.intv; out.overflow = false;
-    if (list_cap > caps.maxlen + 1) list_cap = caps.maxlen + 1;
+    while (list_cap > 2 * (caps.maxlen + 1) || (list_cap & (list_cap - 1))) list_cap &= list_cap - 1;      // a power of two that fits `prev` (16-byte entries)
     bool ok = seed2_eligible(ix, len, seq) && collect_intv_v2(ix, opt, len, seq, out, (PIntv *)prev, list_cap, ctr, tab);
     if (!ok && !out.overflow) { out.n = 0; if (len >= opt.min_seed_len) collect_intv(ix, opt, len, seq, out, prev, curr, ctr); }
     if (out.overflow) { B.ovf[rid] |= OVF_INTV; return; }

@@ -88,7 +88,20 @@ struct ChainView {
         if (m >= K) return x2 < 255 ? (u32)x2 : 255u;
         return (u32)(((m < 8 ? szlo : szhi) >> (8 * (m & 7))) & 255u);
     }
-    HD bool same(int a, int b) const { return ((mask >> a) & ((1u << (b - a)) - 1u)) == 0; }   // sizes of the a- and b-prefix equal (a < b <= K)
+    HD bool same(int a, int b) const { return ((mask >> a) & ((1u << (b - a)) - 1u)) == 0; }   // sizes of the a- and b-prefix equal (a <= b <= K)
+    // number of prefix lengths 1..K whose size is >= t (1 <= t <= 255; sizes never grow with the length, byte 0 and bytes >= K are 0)
+    HD int lmax(u32 t, int K) const
+    {
+        int n = x2 >= (u64)t ? 1 : 0;
+#if defined(__CUDA_ARCH__)
+        const u32 tt = t * 0x01010101u;       // __vcmpgeu4: 0xff in every byte lane where a >= b
+        n += (__popc(__vcmpgeu4((u32)szlo, tt)) + __popc(__vcmpgeu4((u32)(szlo >> 32), tt)) +
+              __popc(__vcmpgeu4((u32)szhi, tt)) + __popc(__vcmpgeu4((u32)(szhi >> 32), tt))) >> 3;
+#else
+        for (int m = 1; m < K; ++m) n += size_sat(m, K) >= t;
+#endif
+        return n;
+    }
 };
 HD ChainView chain_view(const OccLoad &b)
 {
@@ -210,13 +223,23 @@ HD int clz32(u32 x)
 }
 static const u64 INTV_TEXT_FLAG = 1ull << 63;      // Intv::x0 with this bit: the low bits are the text position of the (single) occurrence
 
-// One read's seeding as a resumable machine.  List: get(e) / set(e, PIntv) over `cap` entries; Query: operator[](i) in 0..3.
+// One read's seeding as a resumable machine.  Query: operator[](i) in 0..3, key(st, ln).
+// Work list of a bwt_smem1a call (the reference's prev / curr arrays, bwa/bwt.c:303-349), in two parts:
+//   * "long" entries -- strings of at least K bases, the only ones whose interval is ever needed -- in the caller's List
+//     (get / put of packed intervals; `cap` slots, a power of two, used as a ring: the forward sweep fills it downwards, so
+//     the list is born longest-first as the reference wants it after its in-place reversal; a backward row compacts it in
+//     place and may append one entry, the string that just reached K bases);
+//   * "short" entries -- strings of fewer than K bases that start at sx: only their ends matter, and those are a bit mask
+//     (bit m: the entry that ends at sx + m).  A backward row turns that mask into the next one with a dozen bit operations
+//     on the row's chain entry (sizes are monotone in the length, so "alive" is a prefix of the mask and "size differs from
+//     the last kept entry" is "a change bit lies between this entry and the next longer one").
 template <class List, class Query>
 struct SeedMachine {
     enum { M_DONE = 0, M_FWD, M_BWD, M_P3, M_FWDC, M_FSA, M_FTX, M_BTX, M_TASK, M_ENDFWD, M_LASTROW };
-    int mode, pass, x, k2, old_n, sx, i, j, nprev, ncurr, top, ret, last_start, first, ovf, lastlen;
+    int mode, pass, x, k2, old_n, sx, i, j, nlong, ncurr, ret, last_start, first, ovf;
     int len, cap, min_seed_len, split_len, split_width, max_intv3, min_intv, K, last_pass;
-    u64 x0, x1, x2, lastcurr;     // ik of the forward sweeps / last size pushed in this backward row
+    u32 top, smask;               // ring position of the longest long entry; short entries
+    u64 x0, x1, x2, lastcurr;     // ik of the forward sweeps / last size kept in this backward row
     u64 p0, p1, p2;               // the list entry being extended backwards
     u32 iend, pend;
     u64 tpos; int tleft, textok; bool tracked;      // text path: position of q[sx] of the tracked (size-one, longest) entry, rows it survives
@@ -231,10 +254,11 @@ struct SeedMachine {
         split_len = (int)(opt.min_seed_len * opt.split_factor + .499);
         split_width = opt.split_width;
         max_intv3 = (int)opt.max_mem_intv;
-        pass = 1; x = 0; k2 = 0; old_n = 0; ovf = 0; mode = M_DONE;
+        pass = 1; x = 0; k2 = 0; old_n = 0; ovf = 0; mode = M_DONE; nlong = 0; smask = 0; top = 1u << 20;
         out.n = 0; out.overflow = false;
     }
 
+    HD int slot(u32 e) const { return (int)(e & (u32)(cap - 1)); }
     HD void fail() { ovf = 1; mode = M_DONE; }
 
     HD void emit(u64 e0, u64 e1, u64 e2, u64 info)
@@ -244,38 +268,44 @@ struct SeedMachine {
         if (out.overflow) fail();
     }
 
-    HD void push_fwd()
+    HD void push_fwd()             // the forward sweep lists ik (a long entry)
     {
-        if (top == 0) { fail(); return; }
-        L.put(--top, x0, x1, x2, iend);
+        if (nlong == cap) { fail(); return; }
+        L.put(slot(--top), x0, x1, x2, iend);
+        ++nlong;
         ret = (int)iend;
     }
-    HD void push_fwd_end(u32 end)          // a string shorter than K bases: only its end is kept
+
+    // the end of a backward row (bwa/bwt.c:346-348)
+    HD void row_end()
     {
-        if (top == 0) { fail(); return; }
-        L.put_end(--top, end);
-        ret = (int)end;
+        if (ncurr == 0 && smask == 0) { mode = M_TASK; if (pass == 1) x = ret; }
+        else {
+            nlong = ncurr; ncurr = 0; j = 0;
+            if (--i < 0) mode = M_LASTROW;
+        }
     }
 
-    // Everything between two extensions that is not the per-extension bookkeeping: ending a forward sweep, the row
+    // Everything between two gathers that is not the per-extension bookkeeping: ending a forward sweep, the row
     // i == -1 of a backward sweep, picking the next bwt_smem1 / bwt_seed_strategy1 call (bwa/bwamem.c:150-184).
     // A loop over transient modes instead of mutually recursive helpers, so that it inlines and the state stays in registers.
     HD void settle(const DevIndex &ix)
     {
         for (;;) {
             if (mode == M_ENDFWD) {
-                nprev = cap - top; ncurr = 0; j = 0; first = 1; last_start = 0;
+                ncurr = 0; j = 0; first = 1; last_start = 0;
                 i = sx - 1;
                 mode = i < 0 ? M_LASTROW : tracked ? M_BTX : M_BWD;
             } else if (mode == M_LASTROW) {
-                // bwa/bwt.c:325-345 with c = -1: only the longest survivor can be reported, with start 0
-                if (first || 0 < last_start) {
+                // bwa/bwt.c:325-345 with c = -1: only the longest survivor can be reported, with start 0 (a short entry never:
+                // it has fewer than K < min_seed_len bases)
+                if (nlong > 0 && (first || 0 < last_start)) {
                     u64 e0, e1, e2; u32 e;
                     if (tracked) {
-                        e = L.end(top);
+                        e = L.end(slot(top));
                         if ((int)e >= min_seed_len) { emit(INTV_TEXT_FLAG | (tpos - (u64)sx), 0, 1, (u64)e); if (ovf) return; }
                     } else {
-                        const bool ok = L.take(top, e0, e1, e2, e);
+                        const bool ok = L.take(slot(top), e0, e1, e2, e);
                         if ((int)e >= min_seed_len) { if (!ok) { fail(); return; } emit(e0, e1, e2, (u64)e); if (ovf) return; }
                     }
                 }
@@ -321,11 +351,10 @@ struct SeedMachine {
                     return;
                 }
                 // begin the forward sweep of bwt_smem1a at sx
-                tracked = false;
-                if (K > 0) { top = cap; mode = M_FWDC; return; }       // through the chain entry of q[sx, sx + K)
+                tracked = false; nlong = 0; smask = 0;
+                if (K > 0) { mode = M_FWDC; return; }       // through the chain entry of q[sx, sx + K)
                 Intv t; set_intv(ix, q[sx], t);
                 x0 = t.x0; x1 = t.x1; x2 = t.x2; iend = (u32)(sx + 1);
-                top = cap;
                 i = sx + 1;
                 mode = M_FWD;
                 if (i >= len) { push_fwd(); if (ovf) return; mode = M_ENDFWD; }
@@ -354,30 +383,31 @@ struct SeedMachine {
     HD void tracked_top()
     {
         if (tleft > 0) {
-            if (nprev == 1) {          // alone: all the rows until it dies or reaches the read's start
+            if (nlong == 1 && smask == 0) {          // alone: all the rows until it dies or reaches the read's start
                 const int d = tleft < i + 1 ? tleft : i + 1;
                 tleft -= d; i -= d;
                 if (i < 0) mode = M_LASTROW;
-            } else { --tleft; ncurr = 1; lastcurr = 1; lastlen = K + 1; j = 1; }      // kept in slot top + 0, where it is
-            return;
-        }
-        tracked = false;
-        const u32 e = L.end(top);
-        if (first || i + 1 < last_start) {
-            first = 0; last_start = i + 1;
-            if ((int)e - (i + 1) >= min_seed_len) {
-                emit(INTV_TEXT_FLAG | (tpos - (u64)(sx - (i + 1))), 0, 1, (u64)(i + 1) << 32 | e);
-                if (ovf) return;
+                return;
             }
+            --tleft; ncurr = 1; lastcurr = 1; j = 1;      // kept in the first slot, where it is
+        } else {
+            tracked = false;
+            const u32 e = L.end(slot(top));
+            if (first || i + 1 < last_start) {
+                first = 0; last_start = i + 1;
+                if ((int)e - (i + 1) >= min_seed_len) {
+                    emit(INTV_TEXT_FLAG | (tpos - (u64)(sx - (i + 1))), 0, 1, (u64)(i + 1) << 32 | e);
+                    if (ovf) return;
+                }
+            }
+            j = 1;
         }
-        j = 1;
-        if (j == nprev) { mode = M_TASK; if (pass == 1) x = ret; }
+        if (j == nlong && smask == 0) row_end();
     }
 
     // The next gather.  Returns its kind: 0 = an extension through the Occ blocks (coordinate a, other coordinate o, size s,
-    // base c); 1 = the chain entry of the K-mer `key` -- the start of a forward sweep, the jump of a third-pass start, or a
-    // backward row whose remaining entries all end within K bases of i (they are sorted longest first); 2 = the sectors at
-    // ga / gb (text path); -1 = the read finished meanwhile, nothing to fetch.
+    // base c); 1 = the chain entry of the K-mer `key` -- the start of a forward sweep, the jump of a third-pass start, or the
+    // short entries of a backward row; 2 = the sectors at ga / gb (text path); -1 = the read finished meanwhile.
     HD int request(const DevIndex &ix, u64 &a, u64 &o, u64 &s, int &c, u32 &key, const void *&ga, const void *&gb)
     {
         while (mode == M_BWD && j == 0 && tracked) {
@@ -387,11 +417,9 @@ struct SeedMachine {
         if (mode == M_DONE) return -1;
         key = 0u; a = 1; o = 1; s = 0; c = 0; ga = gb = ix.occ;
         if (mode == M_BWD) {
-            pend = L.end(top + j);
-            const int ln = (int)pend - i;
+            if (j == nlong) { key = q.key(i, K); return 1; }          // the short entries: q[i, end) of at most K bases
             c = q[i];
-            if (ln <= K) { key = q.key(i, K); return 1; }
-            if (!L.take(top + j, p0, p1, p2, pend)) { p0 = p1 = 1; p2 = 0; fail(); }      // the list did not keep this interval: spill path
+            if (!L.take(slot(top + (u32)j), p0, p1, p2, pend)) { p0 = p1 = 1; p2 = 0; fail(); }      // the list did not keep this interval: spill path
             a = p0; o = p1; s = p2;
             return 0;
         }
@@ -453,61 +481,66 @@ struct SeedMachine {
         mode = M_BWD;
     }
 
-    // A chain entry arrives: the whole forward prefix (M_FWDC), the rest of a backward row (M_BWD), or a third-pass jump.
+    // A chain entry arrives: the whole forward prefix (M_FWDC), the short entries of a backward row (M_BWD), or a third-pass jump.
     HD void consume_chain(const DevIndex &ix, const ChainView &E)
     {
         if (mode == M_P3) { consume(ix, E.x1, E.x0, E.x2); return; }
+        const int lmax = E.lmax((u32)min_intv, K);               // prefixes of up to lmax bases have >= min_intv occurrences
         if (mode == M_FWDC) {
-            // bwa/bwt.c:303-320 for the strings q[sx, sx + m), m = 1 .. avail
+            // bwa/bwt.c:303-320 for the strings q[sx, sx + m), m = 1 .. avail: the m-prefix is listed when the (m+1)-prefix has
+            // another size (change bit m), and the sweep stops there when that size is below min_intv, i.e. m >= lmax
             const int avail = len - sx < K ? len - sx : K;
-            int m = 1; bool stop = false;
-            while (m < avail) {
-                if ((E.mask >> m) & 1u) {                      // the (m+1)-prefix has another size: the m-prefix is listed
-                    push_fwd_end((u32)(sx + m));
-                    if (ovf) return;
-                    if (E.size_sat(m + 1, K) < (u32)min_intv) { stop = true; break; }
-                }
-                ++m;
-            }
-            if (!stop) {
-                if (sx + m == len) {                           // ran into the read's end: the last string is listed
-                    if (m == K) { x0 = E.x0; x1 = E.x1; x2 = E.x2; iend = (u32)len; push_fwd(); }
-                    else push_fwd_end((u32)len);
-                    if (ovf) return;
-                    stop = true;
-                } else {                                       // m == K: on with the Occ blocks
+            const u32 cm = E.mask & ((1u << avail) - 2u);        // change bits m = 1 .. avail-1
+            const u32 st = cm & ~((1u << (lmax > 1 ? lmax : 1)) - 1u);      // change bits m >= max(lmax, 1): the first one stops the sweep
+            if (st) {
+                const int ms = ctz32(st);
+                smask = cm & ((2u << ms) - 1u);
+                ret = sx + ms;
+                mode = M_ENDFWD;
+            } else {
+                smask = cm;
+                if (sx + avail == len) {                       // ran into the read's end: the last string is listed
+                    if (avail == K) { x0 = E.x0; x1 = E.x1; x2 = E.x2; iend = (u32)len; push_fwd(); if (ovf) return; }
+                    else { smask |= 1u << avail; ret = len; }
+                    mode = M_ENDFWD;
+                } else {                                       // avail == K: on with the Occ blocks
                     x0 = E.x0; x1 = E.x1; x2 = E.x2; iend = (u32)(sx + K);
                     i = sx + K;
+                    if (cm) ret = sx + 31 - clz32(cm);
                     mode = textok && x2 == 1 && min_intv == 1 ? M_FSA : M_FWD;
                 }
             }
-            if (stop) { mode = M_ENDFWD; settle(ix); }
+            if (mode == M_ENDFWD) settle(ix);
             return;
         }
-        // M_BWD, row i: entries j .. nprev-1 produce q[i, end) of at most K bases (bwa/bwt.c:325-345)
-        for (; j < nprev; ++j) {
-            const u32 e = L.end(top + j);
-            const int ln = (int)e - i;
-            if (E.size_sat(ln, K) < (u32)min_intv) {
-                if (ncurr == 0 && (first || i + 1 < last_start)) {
-                    first = 0; last_start = i + 1;
-                    if ((int)e - (i + 1) >= min_seed_len) { fail(); return; }     // cannot happen: min_seed_len > K
-                }
-            } else {
-                bool same = false;
-                if (ncurr > 0) same = lastlen > K ? (lastcurr == E.x2 && E.same(ln, K)) : E.same(ln, lastlen);
-                if (!same) {
-                    if (ln == K) { L.put(top + ncurr, E.x0, E.x1, E.x2, e); lastcurr = E.x2; }
-                    else L.put_end(top + ncurr, e);
-                    ++ncurr; lastlen = ln;
-                }
+        // M_BWD, row i: the short entry that ends at sx + m becomes q[i, sx + m) of m + d bases, d = sx - i (bwa/bwt.c:325-345).
+        // Longest first: dead ones (more than lmax bases) come before alive ones.
+        const int d = sx - i;
+        const u32 A = lmax > d ? smask & ((2u << (lmax - d)) - 1u) : 0u;
+        if ((smask & ~A) && ncurr == 0 && (first || i + 1 < last_start)) { first = 0; last_start = i + 1; }     // (too short to be reported)
+        u32 kept = 0;
+        if (A) {
+            const int tm = 31 - clz32(A);                       // the longest alive short entry: compared with the last long entry kept
+            const bool keep_top = ncurr == 0 || !(lastcurr == E.x2 && E.same(tm + d, K));
+            // another one is kept iff its size differs from the next longer alive entry's: a change bit in between.  Every change
+            // bit below the top entry marks the highest alive entry at or below it (occluded fill downwards, alive entries block).
+            const u32 X = (E.mask >> d) & ((1u << tm) - 1u);
+            u32 gen = X & ~A, pro = ~A;
+            gen |= pro & (gen >> 1); pro &= pro >> 1;
+            gen |= pro & (gen >> 2); pro &= pro >> 2;
+            gen |= pro & (gen >> 4); pro &= pro >> 4;
+            gen |= pro & (gen >> 8);
+            kept = (A & (X | (gen >> 1))) & ~(1u << tm);
+            if (keep_top) {
+                if (tm + d == K) {                              // it reached K bases: a long entry from now on
+                    if (ncurr == cap) { fail(); return; }
+                    L.put(slot(top + (u32)ncurr), E.x0, E.x1, E.x2, (u32)(sx + tm));
+                    ++ncurr;
+                } else kept |= 1u << tm;
             }
         }
-        if (ncurr == 0) { mode = M_TASK; if (pass == 1) x = ret; }
-        else {
-            nprev = ncurr; ncurr = 0; j = 0;
-            if (--i < 0) mode = M_LASTROW;
-        }
+        smask = kept;
+        row_end();
         if (mode > M_BTX) settle(ix);
     }
 
@@ -523,16 +556,10 @@ struct SeedMachine {
                     }
                 }
             } else if (ncurr == 0 || ns != lastcurr) {
-                L.put(top + ncurr, na, no, ns, pend);
-                ++ncurr; lastcurr = ns; lastlen = K + 1;
+                L.put(slot(top + (u32)ncurr), na, no, ns, pend);
+                ++ncurr; lastcurr = ns;
             }
-            if (++j == nprev) {
-                if (ncurr == 0) { mode = M_TASK; if (pass == 1) x = ret; }
-                else {
-                    nprev = ncurr; ncurr = 0; j = 0;
-                    if (--i < 0) mode = M_LASTROW;
-                }
-            }
+            if (++j == nlong && smask == 0) row_end();
         } else if (mode == M_FWD) {
             bool stop = false;
             if (ns != x2) {
