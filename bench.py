@@ -481,16 +481,23 @@ def main():
         peaks, how = measured_peaks()
         total_reads = n_per * world * args.steps
         value = total_reads / dev_s
-        # roofline of the dominant kernel (k_seed2, SMEM seeding): algorithmic bytes = 32 B per Occ block fetched + 16 B per
-        # prefix-interval table entry looked up + the read bases; one launch covers one chunk of reads
+        # Rooflines.  The stage that takes longest is the banded extension (k_extend_wave, packed 16-bit anti-diagonal wavefront): an
+        # integer recurrence bound by the ALU pipe, reported as `roofline`.  The seeding stage (FM-index gathers) is the HBM-side
+        # kernel the metric names, reported as `roofline_hbm`: algorithmic bytes = 32 B per Occ block fetched + 32 B per prefix-chain
+        # entry + 48 B per text-path request (one suffix-array sector or two text sectors) + the read bases.
         seed_s = stage["ms_seed"] / 1000.0 / args.steps
+        ext_s = stage["ms_extend"] / 1000.0 / args.steps
         occ_per_step = stats["occ_blocks"]
-        tab_per_step = stats.get("tab_lookups_lo", 0) + stats.get("tab_lookups_hi", 0)
+        chain_ent = stats.get("tab_lookups_hi", 0)
+        text_req = stats.get("tab_lookups_lo", 0)
         chunk = min(int(os.environ.get("B200_CHUNK", 1 << 21)), n_per)
         n_seed_launches = max(1, len(chunk_plan(n_per, chunk)))
-        alg_bytes = occ_per_step * 32 + tab_per_step * 16 + n_per * L
+        alg_bytes = occ_per_step * 32 + chain_ent * 32 + text_req * 48 + n_per * L
         achieved = alg_bytes / seed_s / 1e9 if seed_s > 0 else 0.0
         tpr, tsrc = seed_traffic_per_read()
+        int_pk, int_src = int_peak()
+        int_pk /= 1e9
+        ext_ach = stats["sw_cells"] * WAVE_INSTR_PER_CELL / ext_s / 1e9 if ext_s > 0 else 0.0
         line = {
             "metric": "150bp reads/sec (seed+chain+SW end-to-end)", "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True,
@@ -502,21 +509,29 @@ def main():
             "e2e": {"value": n_per * world * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "seeding stage: k_seed2 (SMEM passes) + k_seed3 (bwt_seed_strategy1), one pair of launches per chunk", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+            "roofline": {"bound": "int-alu", "kernel": "k_extend_wave<4> (ksw_extend2 as a packed s16x2 anti-diagonal wavefront), one launch per chunk; the longest stage of the step",
+                         "achieved": ext_ach, "peak": int_pk, "unit": "G thread-instr/s", "frac": ext_ach / int_pk, "traffic": None, "peak_source": int_src,
+                         "launches_per_step": n_seed_launches, "kernel_ms_per_launch": 1000.0 * ext_s / n_seed_launches, "kernel_ms": 1000.0 * ext_s,
+                         "cells_per_launch": stats["sw_cells"] / n_seed_launches, "gcups": stats["sw_cells"] / ext_s / 1e9 if ext_s > 0 else 0.0,
+                         "instr_per_cell": WAVE_INSTR_PER_CELL,
+                         "note": "algorithmic work = band cells of the reference's ksw_extend2 (bwa/ksw.c:416-515) x the SASS instructions of one wavefront step per cell; "
+                                 "the gap to 1 is pipeline fill / drain of the 8-row blocks, row commits and lanes whose group finished its block early (19 of 32 lanes per instruction)"},
+            "roofline_hbm": {"bound": "hbm", "kernel": "seeding stage: k_seed2 (SMEM passes: prefix-chain table + Occ blocks + text path) + k_seed3 (bwt_seed_strategy1), one pair of launches per chunk",
+                         "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                          "frac": achieved / peaks.get("hbm_gbs", 6650.0), "traffic": (tpr * n_per / n_seed_launches if tpr else None), "peak_source": how,
                          "traffic_source": tsrc, "algorithmic_bytes_per_launch": alg_bytes / n_seed_launches,
                          "launches_per_step": n_seed_launches, "kernel_ms_per_launch": 1000.0 * seed_s / n_seed_launches,
                          "algorithmic_bytes_per_read": alg_bytes / n_per, "kernel_ms": 1000.0 * seed_s,
-                         "gathers_per_read": {"occ_blocks_32B": occ_per_step / n_per, "table_entries_16B": tab_per_step / n_per},
-                         "note": "dependent random gathers; round 1 fetched 1391 Occ blocks per read (44.7 KB), the prefix-interval tables cut the algorithmic bytes to ~17 KB per read "
-                                 "and the kernel time by 29 %, so achieved GB/s of ALGORITHMIC bytes falls while the kernel gets faster.  DRAM traffic per read is 3.8x the algorithmic bytes: "
-                                 "the L2 fills whole 128-byte lines (profiles/r02_seed_traffic.json); the measured ceiling of random 32-B gathers on this part is 38.4 G/s (scripts/microbench/gather_bw.cu), "
-                                 "the kernel issues ~30 G/s at 31 % occupancy (shared-memory work lists, 5 blocks per SM) and is bound by latency and by lanes of one warp being in different phases of the search"},
+                         "gathers_per_read": {"occ_blocks_32B": occ_per_step / n_per, "chain_entries_32B": chain_ent / n_per, "text_path_requests_48B": text_req / n_per},
+                         "note": "dependent random gathers.  Round 1 fetched 1391 Occ blocks per read (44.7 KB); the prefix-chain table (one 32-byte entry answers a forward prefix or a whole backward row) "
+                                 "and the text path (size-one intervals are followed through the text) leave ~240 gathers / ~8 KB per read, so the ALGORITHMIC GB/s falls while the stage got 3.5x faster: "
+                                 "the kernel is no longer bound by HBM but by dependent-gather latency and instruction issue (ncu: issue slots 55 % busy, 9 of 32 lanes per instruction, DRAM 25 % of peak, "
+                                 "every L2 miss fills a 128-byte line: profiles/r02_ncu_full_seed2_mask_v0.txt)"},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_s_timed_region": wall_s, "mapped_fraction": mapped, "hits_per_step": n_hits_dev,
             "index_build_s": t_index, "index_bcast_s": t_bcast, "spill_reads_per_step": stats["n_overflow"],
             "sw_cells_per_step": stats["sw_cells"], "occ_blocks_per_read": occ_per_step / n_per,
-            "seed_table_lookups_per_read": {"levels_le_10": stats.get("tab_lookups_lo", 0) / n_per, "levels_11_to_K": stats.get("tab_lookups_hi", 0) / n_per},
+            "seed_gathers_per_read": {"occ_blocks": occ_per_step / n_per, "chain_entries": chain_ent / n_per, "text_path_requests": text_req / n_per},
         }
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line

@@ -241,8 +241,8 @@ typedef struct b200_stage_stats {
     uint64_t n_ext, n_global; /* ksw_extend2 / ksw_global2 calls           */
     uint64_t n_overflow;      /* reads re-run with spill buffers           */
     int n_launches;
-    uint64_t tab_lookups_lo;  /* prefix-interval table lookups (16 B each), levels <= 10 (21 MB, L2 resident) */
-    uint64_t tab_lookups_hi;  /* ... levels 11..K (HBM gathers)             */
+    uint64_t tab_lookups_lo;  /* seeding, text path: suffix-array / text sector requests (one or two 32-B sectors each) */
+    uint64_t tab_lookups_hi;  /* seeding: prefix-chain table entries fetched (32 B each, HBM gathers) */
     uint64_t ext_fallback;    /* reads whose extensions were re-run by the row-synchronous kernel */
     uint64_t n_failed;        /* reads beyond every working-set limit: reported without hits (b200_last_error says so) */
 } b200_stage_stats_t;

@@ -61,7 +61,7 @@ struct KArgs {
 };
 
 template <int STAGE>
-__global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
+__device__ __forceinline__ void stage_body(const KArgs &A)
 {
     u8 *scr = A.scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.scratch_stride;
     const i64 n_work = A.n_work_dev ? (i64)*A.n_work_dev : A.n_work;
@@ -79,6 +79,12 @@ __global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A)
     }
     flush_counters(ctr, A.ctrs);
 }
+template <int STAGE>
+__global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A) { stage_body<STAGE>(A); }
+// the same with a register cap that lets MINB blocks of 128 threads share an SM: the thread-per-read chain / finalize stages
+// wait on dependent scratch accesses (issue slots 13-15 % busy), more resident warps hide more of that latency
+template <int STAGE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_stage_occ(const __grid_constant__ KArgs A) { stage_body<STAGE>(A); }
 
 // ---------------------------------------------------------------------------------------
 // Seeding, main pass: the single-extension-site machine of seed2.cuh.
@@ -606,6 +612,21 @@ static void launch_stage(Engine &E, KArgs &A, int grid, int tpb = 128)
     k_stage<STAGE><<<grid, tpb, 0, E.st>>>(A);
     CU_CHECK(cudaGetLastError());
 }
+static double scratch_budget_bytes();
+template <int STAGE, int MINB>
+static void launch_stage_occ(Engine &E, KArgs &A, size_t stride)
+{
+    int per = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage_occ<STAGE, MINB>, 128, 0));
+    if (per < 1) per = 1;
+    int grid = E.sms * per;
+    i64 fit = (i64)(scratch_budget_bytes() / (double)(stride * 128));
+    if (fit < 1) fit = 1;
+    if (grid > fit) grid = (int)fit;
+    CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
+    k_stage_occ<STAGE, MINB><<<grid, 128, 0, E.st>>>(A);
+    CU_CHECK(cudaGetLastError());
+}
 
 // Main-pass seeding with k_seed2: usable for batches of short reads on indexes below 2^36 symbols.
 static const int SEED2_CAP = 16;          // long work-list entries per read in shared memory (a power of two: ring)
@@ -754,6 +775,8 @@ static void run_stages(Engine &E, KArgs A, int spill, float *ms4)
         for (int i = 0; i < 4; ++i) if (g[i] > fit) g[i] = (int)fit;
     }
     int gmax = std::max(std::max(g[0], g[1]), std::max(g[2], g[3]));
+    static const int occ1 = getenv("B200_STAGE1_MINB") ? atoi(getenv("B200_STAGE1_MINB")) : 0, occ3 = getenv("B200_STAGE3_MINB") ? atoi(getenv("B200_STAGE3_MINB")) : 0;
+    if (!spill && (occ1 || occ3)) gmax = std::max(gmax, (int)std::min<i64>((i64)E.sms * 16, (i64)(scratch_budget_bytes() / (double)(stride * tpb))));
     DevBuf &S = spill ? E.spill_scratch : E.scratch;
     S.reserve(stride * (size_t)gmax * tpb);
     A.scratch = S.as<u8>(); A.scratch_stride = stride;
@@ -762,7 +785,11 @@ static void run_stages(Engine &E, KArgs A, int spill, float *ms4)
     if (!spill && seed2_usable(A)) launch_seed2(E, A, g[0]);
     else launch_stage<0>(E, A, g[0], tpb);
     CU_CHECK(cudaEventRecord(ev[1], E.st));
-    launch_stage<1>(E, A, g[1], tpb); CU_CHECK(cudaEventRecord(ev[2], E.st));
+    if (!spill && occ1 == 12) launch_stage_occ<1, 12>(E, A, stride);
+    else if (!spill && occ1 == 10) launch_stage_occ<1, 10>(E, A, stride);
+    else if (!spill && occ1 == 16) launch_stage_occ<1, 16>(E, A, stride);
+    else launch_stage<1>(E, A, g[1], tpb);
+    CU_CHECK(cudaEventRecord(ev[2], E.st));
     {
         const int G = 8;
         static int reg_ok = getenv("B200_EXTEND_SMEM") ? 0 : 1;
@@ -829,7 +856,11 @@ static void run_stages(Engine &E, KArgs A, int spill, float *ms4)
         } else launch_stage<2>(E, A, g[2], tpb);
     }
     CU_CHECK(cudaEventRecord(ev[3], E.st));
-    { KArgs At = A; At.caps = tc; launch_stage<3>(E, At, g[3], tpb); }
+    { KArgs At = A; At.caps = tc;
+      if (!spill && occ3 == 8) launch_stage_occ<3, 8>(E, At, stride);
+      else if (!spill && occ3 == 10) launch_stage_occ<3, 10>(E, At, stride);
+      else if (!spill && occ3 == 12) launch_stage_occ<3, 12>(E, At, stride);
+      else launch_stage<3>(E, At, g[3], tpb); }
     if (A.B.dp_jobs) {
         const int G = 8;
         size_t smem = (size_t)(128 / G) * findp_smem_bytes(A.caps.maxlen);
