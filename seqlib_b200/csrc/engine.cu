@@ -691,7 +691,7 @@ static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
 }
 
 // Prefix-chain table of an index (seed2.cuh): built once, on the first batch that can use it.
-// K = min(B200_SEED_TAB_K (default 15), floor(log4(seq_len)), what a third of the free HBM holds); 34 GB at K = 15
+// K = min(B200_SEED_TAB_K (default 15), floor(log4(seq_len)), what half of the free HBM holds); 34 GB at K = 15
 // (+ 5.7 GB of builder scratch, freed).  A batch whose options the table cannot serve (min_seed_len <= K, thresholds > 255)
 // runs on the Occ blocks alone.
 static SeedTab seed_tables(Engine &E, const b200_index *idx, const Opt &opt)
@@ -704,7 +704,7 @@ static SeedTab seed_tables(Engine &E, const b200_index *idx, const Opt &opt)
         while (K > 0 && (1ull << (2 * K)) > idx->seq_len) --K;
         size_t free_b = 0, total_b = 0;
         CU_CHECK(cudaMemGetInfo(&free_b, &total_b));
-        while (K > 0 && ((1ull << (2 * K)) * sizeof(ChainEnt) + seedtab_entries(K - 1) * sizeof(PIntv)) > (free_b + dev_pool().pooled) / 3) --K;
+        while (K > 0 && ((1ull << (2 * K)) * sizeof(ChainEnt) + seedtab_entries(K - 1) * sizeof(PIntv)) > (free_b + dev_pool().pooled) / 2) --K;
         if (idx->seq_len >= (1ull << 36) || K < 4) K = 0;
         if (K > 0) {
             void *p = nullptr, *lev = nullptr;
@@ -1057,12 +1057,15 @@ extern "C" {
 
 static int check_reads(const b200_mem_opt_t *opt, i64 n, const int64_t *off, int *maxlen_out)
 {
-    int maxlen = 1;
+    // branch-free min / max so that the compiler vectorises the scan (10^7 offsets per call on the end-to-end path)
+    i64 mn = 0, mx = 1;
     for (i64 i = 0; i < n; ++i) {
-        i64 l = off[i + 1] - off[i];
-        if (l < 0 || l > (1 << 20)) return fail(B200_ERR_ARG, "bad read length");
-        if (l > maxlen) maxlen = (int)l;
+        const i64 l = off[i + 1] - off[i];
+        mn = l < mn ? l : mn;
+        mx = l > mx ? l : mx;
     }
+    if (mn < 0 || mx > (1 << 20)) return fail(B200_ERR_ARG, "bad read length");
+    const int maxlen = (int)mx;
     // reads long enough for mem_flt_chained_seeds (bwa/bwamem.c:624-641, > ~730 bp) are handled in stage_chain (seedsw.cuh)
     (void)opt;
     *maxlen_out = maxlen;
@@ -1091,8 +1094,12 @@ int b200_batch_create(const b200_index_t *idx, const b200_mem_opt_t *opt, int64_
         if (!ids) { myids.resize(n); for (i64 i = 0; i < n; ++i) myids[i] = lrand48(); ids = myids.data(); }
         b->d_seq.reserve(total + 64); b->d_off.reserve((n + 1) * 8); b->d_ids.reserve(n * 8 + 8);
         b->total_bytes = total;
-        if (g_lazy_upload) { b->lazy = true; b->lazy_src = seqs + base; b->lazy_ascii.reserve(total + 64); }
-        else {
+        if (g_lazy_upload) {
+            b->lazy = true; b->lazy_src = seqs + base; b->lazy_ascii.reserve(total + 64);
+            // the first chunk's bases start travelling now, behind the offsets / ids / log table set-up below
+            const i64 first = off[std::min<i64>(n, chunk_reads())] - base;
+            if (first > 0) { CU_CHECK(cudaMemcpyAsync(b->lazy_ascii.p, b->lazy_src, first, cudaMemcpyHostToDevice, E.st_up)); b->uploaded = first; }
+        } else {
             E.seq_ascii.reserve(total + 64);
             CU_CHECK(cudaMemcpyAsync(E.seq_ascii.p, seqs + base, total, cudaMemcpyHostToDevice, E.st));
         }
