@@ -55,9 +55,10 @@ HD GenCigarOut gen_cigar2(const DevIndex &ix, const Opt &opt, int w_, int l_quer
     ctr.ref_bytes += (unsigned long long)((rlen + 3) >> 2);
     // reverse strand: both sequences are walked backwards so that gaps are left-aligned (bwa/bwa.c:163-168)
     bool rev = rb >= l_pac;
-    BytesSeq qs; TextSeq ts; ts.ix = &ix;
-    if (rev) { qs.p = query + l_query - 1; qs.step = -1; ts.pos = re - 1; ts.step = -1; }
-    else { qs.p = query; qs.step = 1; ts.pos = rb; ts.step = 1; }
+    BytesSeq qs;
+    TextSeqC ts(&ix, rev ? re - 1 : rb, rev ? -1 : 1);        // the current 32-base text word stays in registers
+    if (rev) { qs.p = query + l_query - 1; qs.step = -1; }
+    else { qs.p = query; qs.step = 1; }
     R.ok = true;
     if (l_query == rlen && w_ == 0) {
         if (cigar) { if (cap_cigar < 1) { R.overflow = true; return R; } cigar[0] = (u32)l_query << 4; R.n_cigar = 1; }

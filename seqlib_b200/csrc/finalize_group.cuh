@@ -1,7 +1,7 @@
 // finalize_group.cuh -- the gapped part of mem_reg2aln (bwa/bwamem.c:1145-1156: up to three bwa_gen_cigar2 calls with
 // a doubling band) for hits that need a real global alignment, G lanes per hit (device only).
 // stage_finalize (one thread per read) resolves every hit whose alignment is provably ungapped inline and queues the
-// rest as DpJob records; k_finalize_dp drains that queue: DP rows by the group (global2_group), traceback + NM/MD +
+// rest as DpJob records; k_finalize_dp drains that queue: DP rows and traceback by the group (global2_group, traceback_group), NM/MD +
 // clipping by lane 0, then the CIGAR/MD are appended to the pools and the hit record is completed.
 #pragma once
 #include "pipeline.cuh"
@@ -12,26 +12,43 @@ namespace b200 {
 __host__ __device__ inline size_t findp_smem_bytes(int maxlen) { return (size_t)(maxlen + 2) * 8 + (size_t)((maxlen + 4) & ~3); }
 __host__ __device__ inline size_t findp_scratch_bytes(const Caps &c) { return (size_t)c.z + 8 + sizeof(u32) * (size_t)c.cigar + (size_t)c.md + 64; }
 
-// traceback of ksw_global2 (bwa/ksw.c:620-637) by one lane
-__device__ inline int traceback_(const u8 *z, int n_col, int qlen, int tlen, int w, u32 *cigar, int cap_cigar)
+// traceback of ksw_global2 (bwa/ksw.c:620-637), cooperative: the walk is one dependent load per step, and it mostly runs along a
+// diagonal.  The lanes of the group fetch the next G cells of the current diagonal at once; every lane then replays the same steps
+// on the shuffled bytes (uniform control flow) until the path leaves the diagonal, where the group refetches.  Lane 0 writes the
+// CIGAR words.  Returns the number of words (group-uniform), -1 on overflow.
+template <int G>
+__device__ inline int traceback_group(const GroupCtx<G> &g, const u8 *z, int n_col, int qlen, int tlen, int w, u32 *cigar, int cap_cigar)
 {
     int n = 0, which = 0, i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
     bool ovf = false;
+    u32 last = 0;                 // the CIGAR word being accumulated (kept in registers by every lane, stored by lane 0)
 #define PUSH_OP(op_, len_) do { \
-    if (n == 0 || (int)(cigar[n - 1] & 0xf) != (op_)) { if (n < cap_cigar) cigar[n++] = (u32)(len_) << 4 | (op_); else ovf = true; } \
-    else cigar[n - 1] += (u32)(len_) << 4; } while (0)
-    while (i >= 0 && k >= 0) {
-        which = z[(i64)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
-        if (which == 0) { PUSH_OP(0, 1); --i; --k; }
-        else if (which == 1) { PUSH_OP(2, 1); --i; }
-        else { PUSH_OP(1, 1); --k; }
-        if (ovf) return -1;
+    if (n == 0 || (int)(last & 0xf) != (op_)) { \
+        if (n > 0 && g.gl == 0) cigar[n - 1] = last; \
+        if (n < cap_cigar) { last = (u32)(len_) << 4 | (op_); ++n; } else ovf = true; } \
+    else last += (u32)(len_) << 4; } while (0)
+    while (i >= 0 && k >= 0 && !ovf) {
+        const int ti = i - g.gl, tk = k - g.gl;
+        int zz = 0;
+        if (ti >= 0 && tk >= 0) zz = z[(i64)ti * n_col + (tk - (ti > w ? ti - w : 0))];
+        for (int t = 0; t < G; ++t) {
+            if (i < 0 || k < 0) break;
+            const int zt = g.bcast(zz, t);
+            which = zt >> (which << 1) & 3;
+            if (which == 0) { PUSH_OP(0, 1); --i; --k; }
+            else if (which == 1) { PUSH_OP(2, 1); --i; break; }
+            else { PUSH_OP(1, 1); --k; break; }
+            if (ovf) break;
+        }
     }
-    if (i >= 0) PUSH_OP(2, i + 1);
+    if (!ovf && i >= 0) PUSH_OP(2, i + 1);
     if (!ovf && k >= 0) PUSH_OP(1, k + 1);
 #undef PUSH_OP
     if (ovf) return -1;
-    for (i = 0; i < n >> 1; ++i) swap_(cigar[i], cigar[n - 1 - i]);
+    if (g.gl == 0) {
+        if (n > 0) cigar[n - 1] = last;
+        for (i = 0; i < n >> 1; ++i) swap_(cigar[i], cigar[n - 1 - i]);
+    }
     return n;
 }
 
@@ -48,8 +65,7 @@ __device__ GenCigarOut gen_cigar2_group(const GroupCtx<G> &g, const DevIndex &ix
     i64 rlen = re - rb;
     bool rev = rb >= l_pac;
     BytesSeq qs; qs.p = q; qs.step = 1;
-    TextSeq ts; ts.ix = &ix;
-    if (rev) { ts.pos = re - 1; ts.step = -1; } else { ts.pos = rb; ts.step = 1; }
+    TextSeqC ts(&ix, rev ? re - 1 : rb, rev ? -1 : 1);        // the current 32-base text word stays in registers
     R.ok = true;
     int nc = 0;
     if (l_query == rlen && w_ == 0) {
@@ -76,8 +92,8 @@ __device__ GenCigarOut gen_cigar2_group(const GroupCtx<G> &g, const DevIndex &ix
         unsigned long long cells = 0;
         R.score = global2_group(g, l_query, qs, (int)rlen, ts, smat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, w, H, E, z, &cells);
         if (g.gl == 0) { ctr.sw_cells += cells; ctr.n_global++; }
-        if (g.gl == 0) nc = traceback_(z, n_col, l_query, (int)rlen, w, cigar, cap_cigar);
-        nc = __shfl_sync(g.mask, nc, 0, G);
+        g.sync();                      // the direction bytes of all lanes are visible
+        nc = traceback_group<G>(g, z, n_col, l_query, (int)rlen, w, cigar, cap_cigar);
         if (nc < 0) { R.overflow = true; return R; }
     }
     R.n_cigar = nc;
