@@ -150,7 +150,7 @@ __global__ void k_pack_reads(const u8 *__restrict__ seq, const i64 *__restrict__
     if (n_base || (w == 0 && len > (i64)qw * 16)) atomicOr(bad + r, 1u);
 }
 
-template <int CAP, int MINB>
+template <int CAP, int MINB, int PHASED>
 __global__ void __launch_bounds__(128, MINB) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride)
 {
     // The SMEM passes (bwt_smem1a from every start, re-seeding of long SMEMs).  Tried and dropped (round 2): L2 eviction-policy
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(128, MINB) k_seed2(const __grid_constant__ KAr
     CtrLocal ctr;
     i64 rid = -1;
     bool done = false;
+    int phase = 0;
     for (;;) {
         if (m.mode == 0 && !done) {
             if (rid >= 0) {                                     // record the read that just finished
@@ -193,7 +194,17 @@ __global__ void __launch_bounds__(128, MINB) k_seed2(const __grid_constant__ KAr
             }
         }
         if (__all_sync(0xffffffffu, done)) break;
-        if (m.mode != 0) {
+        bool go = m.mode != 0;
+        if (PHASED) {
+            // the lanes of a warp take turns by class: forward sweeps (chain entry, a few Occ steps, text path) or backward sweeps
+            // (rows).  A lane of the other class waits, so the lanes that run are in the same few code paths at the same time
+            // (107 -> 95 ms per 10 M reads).  Finer turns -- always the kind of step most lanes wait for, six kinds -- are slower
+            // (112 ms): every turn costs a gather latency, and fewer lanes share it.
+            const int cls = m.mode == 0 ? -1 : (m.mode == m.M_BWD || m.mode == m.M_BTX) ? 1 : 0;
+            if (__ballot_sync(0xffffffffu, cls == phase) == 0) phase ^= 1;
+            go = cls == phase;
+        }
+        if (go) {
             u64 a, o, s, na = 0, no = 0, ns = 0; int c; u32 key; const void *ga, *gb; ChainView cv;
             const int kind = m.request(A.ix, a, o, s, c, key, ga, gb);
             if (kind >= 0) {
@@ -636,16 +647,16 @@ static bool seed2_usable(const KArgs &A)
 {
     return seed2_enabled() && !A.order && A.caps.maxlen <= 255 && A.ix.seq_len < (1ull << 36) && A.B.pool.cap[POOL_INTV] >= A.B.n_reads * (i64)SEED2_STRIDE;
 }
-template <int CAP, int MINB>
+template <int CAP, int MINB, int PHASED = 0>
 static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
 {
     size_t smem = (size_t)128 * (CAP * 12 + (qw + 1) * 4);
-    CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP, MINB, PHASED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     int per = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP, MINB>, 128, smem));
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP, MINB, PHASED>, 128, smem));
     if (per < 1) per = 1;
     { static const int occ = getenv("B200_OCC_SEED") ? atoi(getenv("B200_OCC_SEED")) : 0; if (occ > 0 && occ < per) per = occ; }
-    k_seed2<CAP, MINB><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
+    k_seed2<CAP, MINB, PHASED><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
     CU_CHECK(cudaGetLastError());
     // then the third pass
     size_t smem3 = (size_t)128 * (qw + 1) * 4;
@@ -666,8 +677,10 @@ static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
     static int cap_sel = getenv("B200_SEED_CAP") ? atoi(getenv("B200_SEED_CAP")) : SEED2_CAP;
     CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
     static int minb = getenv("B200_SEED_MINB") ? atoi(getenv("B200_SEED_MINB")) : 6;
+    static int phased = getenv("B200_SEED_PHASED") ? atoi(getenv("B200_SEED_PHASED")) : 1;
     if (cap_sel == 8) launch_seed2_cap<8, 6>(E, A, qw);
     else if (cap_sel == 32) launch_seed2_cap<32, 5>(E, A, qw);
+    else if (minb == 6 && phased) launch_seed2_cap<SEED2_CAP, 6, 1>(E, A, qw);
     else if (minb == 6) launch_seed2_cap<SEED2_CAP, 6>(E, A, qw);
     else launch_seed2_cap<SEED2_CAP, 5>(E, A, qw);
     CU_CHECK(cudaGetLastError());

@@ -408,12 +408,17 @@ struct SeedMachine {
     // The next gather.  Returns its kind: 0 = an extension through the Occ blocks (coordinate a, other coordinate o, size s,
     // base c); 1 = the chain entry of the K-mer `key` -- the start of a forward sweep, the jump of a third-pass start, or the
     // short entries of a backward row; 2 = the sectors at ga / gb (text path); -1 = the read finished meanwhile.
-    HD int request(const DevIndex &ix, u64 &a, u64 &o, u64 &s, int &c, u32 &key, const void *&ga, const void *&gb)
+    // the gather-free part of the next step: rows that begin with the tracked entry
+    HD void pre(const DevIndex &ix)
     {
         while (mode == M_BWD && j == 0 && tracked) {
             tracked_top();
             if (mode > M_BTX) settle(ix);
         }
+    }
+    HD int request(const DevIndex &ix, u64 &a, u64 &o, u64 &s, int &c, u32 &key, const void *&ga, const void *&gb)
+    {
+        pre(ix);
         if (mode == M_DONE) return -1;
         key = 0u; a = 1; o = 1; s = 0; c = 0; ga = gb = ix.occ;
         if (mode == M_BWD) {
