@@ -9,7 +9,7 @@ for v in "${VS[@]}"; do
 import json
 try:
     d=json.loads(open("gpurun_out/${TAG}_$i.json").read().strip().splitlines()[-1])
-    print("RESULT [$v] value %.2f M e2e %.2f M" % (d["value"]/1e6, d["e2e"]["value"]/1e6), {k: round(x,1) for k,x in d["stage_ms_per_step"].items()}, "truth", d["parity"]["truth_within_8bp"], "hits", d["hits_per_step"])
+    print("RESULT [$v] value %.2f M e2e %.2f M" % (d["value"]/1e6, d["e2e"]["value"]/1e6), {k: round(x,1) for k,x in d["stage_ms_per_step"].items()}, "truth", d["parity"]["truth_within_8bp"], "hits", d["hits_per_step"], "spill", d.get("spill_reads_per_step"))
 except Exception as e:
     print("RESULT [$v] failed", e)
 PY

@@ -678,7 +678,7 @@ static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
     CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
     static int minb = getenv("B200_SEED_MINB") ? atoi(getenv("B200_SEED_MINB")) : 6;
     static int phased = getenv("B200_SEED_PHASED") ? atoi(getenv("B200_SEED_PHASED")) : 1;
-    if (cap_sel == 8) launch_seed2_cap<8, 6>(E, A, qw);
+    if (cap_sel == 8) launch_seed2_cap<8, 6, 1>(E, A, qw);
     else if (cap_sel == 32) launch_seed2_cap<32, 5>(E, A, qw);
     else if (minb == 6 && phased) launch_seed2_cap<SEED2_CAP, 6, 1>(E, A, qw);
     else if (minb == 6) launch_seed2_cap<SEED2_CAP, 6>(E, A, qw);
