@@ -111,6 +111,39 @@ def test_stage_functions_on_cpu_vs_golden(name, small, seed_v2, tab_k, text, mon
                 assert np.array_equal(txt[pos:pos + en - st], q), (t, pos, st, en)
 
 
+SEED_OPTION_SETS = [dict(min_seed_len=12), dict(min_seed_len=8), dict(min_seed_len=27, split_factor=1.1), dict(split_width=3),
+                    dict(split_width=40, split_factor=1.0), dict(max_mem_intv=0), dict(max_mem_intv=6), dict(max_mem_intv=120),
+                    dict(split_width=300), dict(max_mem_intv=1000, min_seed_len=15)]
+
+
+@pytest.mark.parametrize("over", SEED_OPTION_SETS)
+def test_seeding_machine_options_on_cpu_vs_reference(over, monkeypatch):
+    """The seeding options reach the machine's thresholds (min_intv of the re-seeding pass = split_width + 1 at most, max_mem_intv of
+    the third pass, the report filter min_seed_len) and decide whether the chain table may be used at all (min_seed_len > K,
+    thresholds <= 255): interval lists and hits of the host build (table K = 8, text path) equal the live reference's."""
+    from oracle import pyref
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import simlib
+    monkeypatch.setenv("HOSTSIM_SEED_V2", "16")
+    monkeypatch.setenv("HOSTSIM_SEED_TAB_K", "8")
+    monkeypatch.setenv("HOSTSIM_SEED_TEXT", "1")
+    sidx, tidx = _sim_index_for_tiny()
+    reads = cases.read_lines(goldenlib.path("sim1_5k.txt"))[:1200] + cases.read_lines(goldenlib.path("bcr_2k.txt"))[:600]
+    opt = pyref.default_opt()
+    for k, v in over.items():
+        setattr(opt, k, v)
+    ids = cases.ids_for(len(reads))
+    exp, _ = pyref.align(tidx, reads, opt, ids)
+    eoff, eintv = pyref.collect_intv(tidx, reads, opt)
+    got = simlib.align(sidx, reads, opt, ids, False)
+    assert parity.compare_results(got, exp) == []
+    assert np.array_equal(got.intv_off, eoff)
+    assert np.array_equal(got.intv["x2"], eintv["x2"]) and np.array_equal(got.intv["info"], eintv["info"])
+    flagged = (got.intv["x0"] >> np.uint64(63)) != 0
+    assert np.array_equal(got.intv["x0"][~flagged], eintv["x0"][~flagged])
+
+
 def test_long_reads_seed_sw_filter_on_cpu_vs_reference(monkeypatch):
     """Contig-like queries (0.8-4 kb) activate mem_flt_chained_seeds / mem_seed_sw -> ksw_i16 (bwa/bwamem.c:597-641): the host
     build of the stage functions (seedsw.cuh replays the striped kernel) gives the reference's hits, CIGARs and MAPQs; with

@@ -331,3 +331,27 @@ def test_coordinates_beyond_2_32_vs_live_reference(capi):
     exp, _ = pyref.align(ridx, (r[:m * 150], off[:m + 1]), opt, ids[:m], n_threads=os.cpu_count() or 1)
     bad, msgs = parity.compare_prefix(got, exp, m)
     assert bad == 0, msgs
+
+
+@pytest.mark.parametrize("over", [dict(min_seed_len=12), dict(min_seed_len=8), dict(min_seed_len=27, split_factor=1.1), dict(split_width=3),
+                                  dict(split_width=40, split_factor=1.0), dict(max_mem_intv=0), dict(max_mem_intv=120),
+                                  dict(split_width=300), dict(max_mem_intv=1000, min_seed_len=15)])
+def test_seeding_options_vs_live_reference(capi, over):
+    """Seeding options decide the thresholds of the seeding machine and whether its chain table may be used (seed2.cuh): hits, and
+    the interval lists of the debug entry point, equal the live reference's for every set."""
+    from oracle import pyref
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    idx = capi.Index.load(goldenlib.path("tiny", "tiny.fa"))
+    tidx = pyref.RefIndex.load(goldenlib.path("tiny", "tiny.fa"))
+    reads = cases.read_lines(goldenlib.path("sim1_5k.txt"))[:2500] + cases.read_lines(goldenlib.path("bcr_2k.txt"))[:1000]
+    opt, ropt = capi.default_opt(), pyref.default_opt()
+    for k, v in over.items():
+        setattr(opt, k, v); setattr(ropt, k, v)
+    ids = cases.ids_for(len(reads))
+    exp, _ = pyref.align(tidx, reads, ropt, ids, n_threads=os.cpu_count() or 1)
+    got = capi.align(idx, reads, opt, ids)
+    assert parity.compare_results(got, exp) == []
+    eoff, eintv = pyref.collect_intv(tidx, reads, ropt)
+    ioff, intv = capi.collect_intv(idx, reads, opt)
+    assert np.array_equal(ioff, eoff) and np.array_equal(intv, eintv)
