@@ -465,7 +465,7 @@ def main():
     capi.results_free(h)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)            # the same K steps as the device-resident leg
     for _ in range(e2e_steps):
         h = capi.align_raw(idx, seqs_p, off_p, opt, ids_p)
         capi.results_free(h)
@@ -506,11 +506,13 @@ def main():
                        "reads_per_gpu_per_step": n_per, "read_len": L, "ref_len": args.ref_len,
                        "parallelism": "reads sharded x%d, index replicated (one NCCL broadcast)" % world,
                        "l2": "inputs larger than L2 (index %.1f GB, reads %.2f GB per GPU)" % (idx.blob_bytes() / 1e9, n_per * L / 1e9)},
-            "e2e": {"value": n_per * world * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": n_per * world * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "int-alu", "kernel": "k_extend_wave<4> (ksw_extend2 as a packed s16x2 anti-diagonal wavefront), one launch per chunk; the longest stage of the step",
-                         "achieved": ext_ach, "peak": int_pk, "unit": "G thread-instr/s", "frac": ext_ach / int_pk, "traffic": None, "peak_source": int_src,
+                         "achieved": ext_ach, "peak": int_pk, "unit": "G thread-instr/s", "frac": ext_ach / int_pk,
+                         "traffic": 1.591e9 * (n_per / n_seed_launches) / 1e6, "traffic_source": "profiles/r02_ncu_full_extend_wave_v2.txt: dram read 1.185 GB + write 0.406 GB per 10^6 reads (ncu --set full)",
+                         "peak_source": int_src,
                          "launches_per_step": n_seed_launches, "kernel_ms_per_launch": 1000.0 * ext_s / n_seed_launches, "kernel_ms": 1000.0 * ext_s,
                          "cells_per_launch": stats["sw_cells"] / n_seed_launches, "gcups": stats["sw_cells"] / ext_s / 1e9 if ext_s > 0 else 0.0,
                          "instr_per_cell": WAVE_INSTR_PER_CELL,
