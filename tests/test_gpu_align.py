@@ -355,3 +355,41 @@ def test_seeding_options_vs_live_reference(capi, over):
     eoff, eintv = pyref.collect_intv(tidx, reads, ropt)
     ioff, intv = capi.collect_intv(idx, reads, opt)
     assert np.array_equal(ioff, eoff) and np.array_equal(intv, eintv)
+
+
+def test_reference_with_ambiguous_bases_keeps_off_the_text_path(capi):
+    """SeqLib's ConstructIndex randomises N bases twice (src/BWAIndex.cpp:102-125): the BWT is built over another text than the
+    one bns_get_seq returns.  The engine's proof BWT[k] == text[SA[k]-1] fails for such an index, the seeding machine keeps to the
+    Occ blocks and the chain table (no text-path requests), and the hits equal the live reference's, also around the N runs."""
+    from oracle import pyref
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.Generator(np.random.PCG64(77))
+    L = 200_000
+    ref = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)].copy()
+    for p, ln in ((20_000, 60), (90_000, 400), (150_000, 7)):
+        ref[p:p + ln] = ord("N")
+    seq = ref.tobytes().decode()
+    _libc().srand48(3)
+    idx = capi.Index.construct(["c1"], [seq])
+    pyref.srand48(3)
+    ridx = pyref.RefIndex.construct(["c1"], [seq])
+    starts = np.concatenate([rng.integers(0, L - 150, 2500), np.array([19_900, 19_960, 89_950, 90_300, 149_900, 149_990])])
+    reads = []
+    for s in starts:
+        r = ref[s:s + 150].copy()
+        m = rng.random(150) < 0.01
+        r[m] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(m.sum()))]
+        reads.append(r.tobytes().decode())
+    ids = cases.ids_for(len(reads))
+    opt = capi.default_opt()
+    got = capi.align(idx, reads, opt, ids)
+    st = capi.last_stats()
+    exp, _ = pyref.align(ridx, reads, pyref.default_opt(), ids, n_threads=os.cpu_count() or 1)
+    assert parity.compare_results(got, exp) == []
+    assert st["tab_lookups_lo"] == 0 and st["tab_lookups_hi"] > 0
+    # the same sequence without N: the text is the BWT's text and the text path is taken
+    clean = seq.replace("N", "A")
+    idx2 = capi.Index.construct(["c1"], [clean])
+    capi.align(idx2, reads[:500], opt, ids[:500])
+    assert capi.last_stats()["tab_lookups_lo"] > 0
