@@ -10,7 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "seqlib_b200", "libseqlib_b200.so")
 OUT = os.path.join(ROOT, "profiles")
 KERNELS = {
-    "seed2": r"k_seed2ILi24",
+    "seed2": r"k_seed2ILi16ELi6ELi1",
+    "seed3": r"k_seed3",
+    "chain_build": r"k_chain_build",
     "extend_wave": r"k_extend_waveILi(4|8)",
     "ext_wave_batch": r"k_ext_waveILi4",
     "extend_group": r"k_extend_groupILi8ELb1",
