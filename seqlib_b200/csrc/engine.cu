@@ -42,10 +42,20 @@ __device__ __forceinline__ void flush_counters(const CtrLocal &c, DevCounters *g
 }
 
 // a warp claims 32 consecutive work items
-__device__ __forceinline__ i64 claim(unsigned long long *counter)
+// How many work items a warp takes at a time: all `full` slots of the warp when there is enough work, fewer for small batches, so
+// that the items spread over the warps of the grid instead of filling a few warps whose lanes then serialise on each other's
+// divergent paths (a 1 024-read call is bound by the latency of ONE read's dependent chain, not by throughput).
+__device__ __forceinline__ int warp_share(i64 n_work, int full)
+{
+    const i64 warps = (i64)gridDim.x * (blockDim.x >> 5);
+    const i64 w = (n_work + warps - 1) / warps;
+    return (int)(w < 1 ? 1 : w > full ? full : w);
+}
+// a warp claims `width` consecutive work items; lanes >= width get an index beyond n_work semantics via the caller's check
+__device__ __forceinline__ i64 claim(unsigned long long *counter, int width)
 {
     unsigned long long base = 0;
-    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, 32ull);
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, (unsigned long long)width);
     base = __shfl_sync(0xffffffffu, base, 0);
     return (i64)base + (threadIdx.x & 31);
 }
@@ -66,10 +76,11 @@ __device__ __forceinline__ void stage_body(const KArgs &A)
     u8 *scr = A.scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * A.scratch_stride;
     const i64 n_work = A.n_work_dev ? (i64)*A.n_work_dev : A.n_work;
     CtrLocal ctr;
+    const int width = warp_share(n_work, 32);
     for (;;) {
-        i64 w = claim(A.work_ctr);
+        i64 w = claim(A.work_ctr, width);
         if (w - (threadIdx.x & 31) >= n_work) break;
-        if (w < n_work) {
+        if ((int)(threadIdx.x & 31) < width && w < n_work) {
             i64 rid = A.order ? A.order[w] : w;
             if (STAGE == 0) stage_seed_t<true>(A.ix, A.opt, A.caps, A.B, rid, scr, ctr);
             else if (STAGE == 1) stage_chain(A.ix, A.opt, A.caps, A.B, rid, scr, ctr, A.log_tab, A.n_log);
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(128, MINB) k_seed2(const __grid_constant__ KAr
     m.mode = 0; m.ovf = 0;
     CtrLocal ctr;
     i64 rid = -1;
-    bool done = false;
+    bool done = (int)(threadIdx.x & 31) >= warp_share(A.n_work, 32);
     int phase = 0;
     for (;;) {
         if (m.mode == 0 && !done) {
@@ -234,7 +245,7 @@ __global__ void __launch_bounds__(128, 8) k_seed3(const __grid_constant__ KArgs 
     m.mode = 0; m.ovf = 0;
     CtrLocal ctr;
     i64 rid = -1;
-    bool done = false;
+    bool done = (int)(threadIdx.x & 31) >= warp_share(A.n_work, 32);
     for (;;) {
         if (m.mode == 0 && !done) {
             if (rid >= 0) {
@@ -354,14 +365,15 @@ __global__ void __launch_bounds__(128, REG ? 4 : 3) k_extend_group(const __grid_
     u8 *smem = REG ? smem_raw : smem_raw + (size_t)gib * group_smem_bytes(A.caps.maxlen);
     u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
     const i64 n_work = A.n_work_dev ? (i64)*A.n_work_dev : A.n_work;
+    const int share = warp_share(n_work, 32 / G);
     CtrLocal ctr;
     for (;;) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)(32 / G));
+        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)share);
         base = __shfl_sync(0xffffffffu, base, 0);
         if ((i64)base >= n_work) break;
         i64 w = (i64)base + lane / G;
-        if (w < n_work) {
+        if (lane / G < share && w < n_work) {
             i64 rid = A.order ? A.order[w] : w;
             stage_extend_group<G, REG>(g, A.ix, A.opt, A.caps, A.B, rid, scr, smem, smat, ctr);
         }
@@ -385,14 +397,15 @@ __global__ void __launch_bounds__(128, 6) k_extend_wave(const __grid_constant__ 
     g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     u8 *smem = smem_raw + (size_t)gib * ((((size_t)WAVE_WORDS(A.caps.maxlen, G) * 4) + 15) & ~(size_t)15);
     u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
+    const int share = warp_share(A.n_work, 32 / G);
     CtrLocal ctr;
     for (;;) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)(32 / G));
+        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)share);
         base = __shfl_sync(0xffffffffu, base, 0);
         if ((i64)base >= A.n_work) break;
         i64 w = (i64)base + lane / G;
-        if (w < A.n_work) {
+        if (lane / G < share && w < A.n_work) {
             i64 rid = A.order ? A.order[w] : w;
             stage_extend_group<G, 2>(g, A.ix, A.opt, A.caps, A.B, rid, scr, smem, nullptr, ctr);
         }
@@ -417,14 +430,15 @@ __global__ void __launch_bounds__(128) k_finalize_dp(const __grid_constant__ KAr
     u8 *smem = smem_raw + (size_t)gib * findp_smem_bytes(A.caps.maxlen);
     u8 *scr = A.scratch + (size_t)(blockIdx.x * (128 / G) + gib) * A.scratch_stride;
     const i64 n_jobs = (i64)*A.B.n_dp_jobs < A.B.cap_dp_jobs ? (i64)*A.B.n_dp_jobs : A.B.cap_dp_jobs;
+    const int share = warp_share(n_jobs, 32 / G);
     CtrLocal ctr;
     for (;;) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)(32 / G));
+        if (lane == 0) base = atomicAdd(A.work_ctr, (unsigned long long)share);
         base = __shfl_sync(0xffffffffu, base, 0);
         if ((i64)base >= n_jobs) break;
         i64 w = (i64)base + lane / G;
-        if (w < n_jobs) finalize_dp_job<G>(g, A.ix, A.opt, A.caps, A.B, A.B.dp_jobs[w], scr, smem, smat, ctr);
+        if (lane / G < share && w < n_jobs) finalize_dp_job<G>(g, A.ix, A.opt, A.caps, A.B, A.B.dp_jobs[w], scr, smem, smat, ctr);
         __syncwarp();
     }
     flush_counters(ctr, A.ctrs);
