@@ -90,8 +90,9 @@ __device__ __forceinline__ void stage_body(const KArgs &A)
     }
     flush_counters(ctr, A.ctrs);
 }
+// (stages 1 and 3 are latency bound on their scratch slots: five blocks per SM is the measured optimum, more thrash the caches, fewer hide less)
 template <int STAGE>
-__global__ void __launch_bounds__(128) k_stage(const __grid_constant__ KArgs A) { stage_body<STAGE>(A); }
+__global__ void __launch_bounds__(128, (STAGE == 1 || STAGE == 3) ? 5 : 4) k_stage(const __grid_constant__ KArgs A) { stage_body<STAGE>(A); }
 // the same with a register cap that lets MINB blocks of 128 threads share an SM: the thread-per-read chain / finalize stages
 // wait on dependent scratch accesses (issue slots 13-15 % busy), more resident warps hide more of that latency
 template <int STAGE, int MINB>
@@ -619,6 +620,7 @@ static int stage_grid(int sms)
     int per = 0;
     CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_stage<STAGE>, 128, 0));
     if (per < 1) per = 1;
+    if ((STAGE == 1 || STAGE == 3) && per > 5) per = 5;
     return sms * per;
 }
 
