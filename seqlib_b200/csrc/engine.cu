@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(128, 6) k_extend_wave(const __grid_constant__ 
 
 // gapped CIGARs: G lanes per queued hit (see finalize_group.cuh)
 template <int G>
-__global__ void __launch_bounds__(128) k_finalize_dp(const __grid_constant__ KArgs A)
+__global__ void __launch_bounds__(128, 6) k_finalize_dp(const __grid_constant__ KArgs A)
 {
     extern __shared__ __align__(16) u8 smem_raw[];
     __shared__ i8 smat[32];
