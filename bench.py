@@ -97,7 +97,18 @@ def measured_peaks():
 
 def chunk_plan(n, ch):
     """The chunk sizes b200_batch_run uses (csrc/engine.cu): a quarter-size first chunk, full chunks, a tapering tail."""
-    if os.environ.get("B200_CHUNK_TAPER", "0") == "0":
+    taper = os.environ.get("B200_CHUNK_TAPER", "0")
+    if taper == "2" and n > 3 * ch:
+        first, last = (ch * 3 // 4) & ~1023, (ch // 2) & ~1023
+        mid_total = n - first - last
+        k = max(1, (mid_total * 4 + ch * 5 - 1) // (ch * 5))
+        mid = ((mid_total + k - 1) // k + 1023) & ~1023
+        plan, rem = [first], n - first
+        while rem > last:
+            t = min(mid, rem - last); plan.append(t); rem -= t
+        plan.append(rem)
+        return plan
+    if taper in ("0", "2"):
         return [min(ch, n - i) for i in range(0, n, ch)]
     plan, rem, q = [], n, max(ch // 4, 1024)
     if rem > ch:

@@ -1160,7 +1160,17 @@ int b200_batch_run(b200_batch_t *b, int *n_launches)
             i64 rem = b->n;
             const i64 q = std::max<i64>(CH / 4, 1024);
             static const int taper = getenv("B200_CHUNK_TAPER") ? atoi(getenv("B200_CHUNK_TAPER")) : 0;   // measured: every extra chunk costs ~3 ms of kernel tails, more than the shorter head / tail copies save
-            if (!taper) { while (rem > 0) { i64 t = std::min(CH, rem); plan.push_back(t); rem -= t; } }
+            if (taper == 2 && rem > 3 * CH) {
+                // same number of chunks, but a 3/4 first chunk (its upload is the only one no kernel hides) and a half-size last one
+                // (its result copy is the only one no kernel hides); the middle chunks share the rest
+                const i64 first = (CH * 3 / 4) & ~(i64)1023, last = (CH / 2) & ~(i64)1023, mid_total = rem - first - last;
+                const i64 k = std::max<i64>(1, (mid_total * 4 + CH * 5 - 1) / (CH * 5));
+                const i64 mid = ((mid_total + k - 1) / k + 1023) & ~(i64)1023;
+                plan.push_back(first); rem -= first;
+                while (rem > last) { i64 t = std::min(mid, rem - last); plan.push_back(t); rem -= t; }
+                plan.push_back(rem); rem = 0;
+            }
+            if (!taper || taper == 2) { while (rem > 0) { i64 t = std::min(CH, rem); plan.push_back(t); rem -= t; } }
             if (rem > CH) { plan.push_back(q); rem -= q; }
             while (rem > CH + CH / 2) { plan.push_back(CH); rem -= CH; }
             while (rem > q) { i64 t = std::max(q, (rem / 2 + 1023) & ~(i64)1023); if (t > rem) t = rem; plan.push_back(t); rem -= t; }
