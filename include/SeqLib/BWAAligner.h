@@ -48,7 +48,7 @@ namespace detail {
 // Test seam (not part of the reference's API): the record assembly of BWAAligner::alignSequence, src/BWAAligner.cpp:111-248,
 // applied to regions that are already computed.  tests/test_cpu_wrapper.py checks it against oracle/oracle_wrap.cpp.
 void RecordsFromRegions(const std::string &seq, const std::string &name, const b200_results_view_t &v, int64_t read, bool hardclip,
-                        double keepSecFrac, int maxSecondary, BamRecordPtrVector &out);
+                        double keepSecFrac, int maxSecondary, BamRecordPtrVector &out, bool batch_packing = false);
 }
 
 } // namespace SeqLib

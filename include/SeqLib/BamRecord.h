@@ -41,6 +41,8 @@ typedef struct bam1_t {
 } bam1_t;
 }
 
+#define BAM_USER_OWNS_STRUCT 1
+#define BAM_USER_OWNS_DATA 2
 #define BAM_FPAIRED 1
 #define BAM_FUNMAP 4
 #define BAM_FREVERSE 16
@@ -121,6 +123,9 @@ class BamRecord {
 
 public:
     BamRecord();                                   ///< allocates an empty bam1_t (SeqLib/BamRecord.cpp:99-106)
+    /// wraps a record somebody else owns (htslib's BAM_USER_OWNS_STRUCT / BAM_USER_OWNS_DATA in bam1_t::mempolicy): the batch path
+    /// of BWAAligner packs the records of a batch into a few large blocks that live as long as any of their records
+    explicit BamRecord(std::shared_ptr<bam1_t> p) : b(std::move(p)) {}
     bool isEmpty() const { return !b || b->data == nullptr; }
     std::string Qname() const;
     int32_t ChrID() const { return b ? b->core.tid : -1; }
@@ -142,6 +147,7 @@ public:
     bool GetIntTag(const std::string &tag, int32_t &t) const;
     bool GetZTag(const std::string &tag, std::string &s) const;
     const bam1_t *raw() const { return b.get(); }
+    void Own();                                    ///< makes the record own its memory (a private copy) if it does not; the tag setters call it
     friend std::ostream &operator<<(std::ostream &out, const BamRecord &r);
 
     std::shared_ptr<bam1_t> b;                     ///< the record (public in the reference too, SeqLib/BamRecord.h:248)

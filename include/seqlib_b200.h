@@ -199,6 +199,13 @@ int b200_mem_align_batch(const b200_index_t *idx, const b200_mem_opt_t *opt,
 int b200_results_view(const b200_results_t *res, b200_results_view_t *view);
 void b200_results_free(b200_results_t *res);
 
+/* Page-locked host memory from the library's pool (cudaHostAlloc, recycled across calls): reads handed to b200_mem_align_batch
+ * in such a buffer travel by DMA straight from it instead of through the driver's staging copies (a third of the call's time for
+ * pageable buffers).  The drop-in BWAAligner::alignSequences flattens its std::string reads into one (src/BWAAligner.cpp has no
+ * analogue: the reference aligns in place on the host). */
+int b200_host_alloc(size_t bytes, void **out);
+void b200_host_free(void *p);
+
 /* Device-resident form used by bench.py's "value" leg: the reads are
  * uploaded once, each call runs all kernels and leaves results on the
  * device.  n_launches (optional) receives the number of kernel launches. */

@@ -17,6 +17,7 @@
 #include <string>
 #include <algorithm>
 #include <mutex>
+#include <unordered_map>
 #include <time.h>
 #include "engine.cuh"
 #include "extend_group.cuh"
@@ -1317,6 +1318,34 @@ int b200_results_view(const b200_results_t *res, b200_results_view_t *v)
 }
 
 void b200_results_free(b200_results_t *res) { delete res; }
+
+namespace { std::mutex g_host_mu; std::unordered_map<void *, PinBuf> g_host_bufs; }
+int b200_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(B200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    try {
+        engine();                                   // a device context must exist before cudaHostAlloc
+        PinBuf b = pin_pool().get(bytes);
+        std::lock_guard<std::mutex> g(g_host_mu);
+        g_host_bufs[b.p] = b;
+        *out = b.p;
+    } catch (const std::bad_alloc &) { return fail(B200_ERR_NOMEM, "pinned host allocation failed"); }
+    catch (const std::exception &e) { return fail(B200_ERR_CUDA, e.what()); }
+    return B200_OK;
+}
+void b200_host_free(void *p)
+{
+    if (!p) return;
+    PinBuf b;
+    {
+        std::lock_guard<std::mutex> g(g_host_mu);
+        auto it = g_host_bufs.find(p);
+        if (it == g_host_bufs.end()) return;
+        b = it->second; g_host_bufs.erase(it);
+    }
+    pin_pool().put(b);
+}
 
 int b200_last_stats(b200_stage_stats_t *out)
 {

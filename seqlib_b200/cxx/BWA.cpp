@@ -10,6 +10,7 @@
 #include <functional>
 #include <memory>
 #include <thread>
+#include <vector>
 #include <exception>
 #include <algorithm>
 #include "SeqLib/BWAIndex.h"
@@ -120,8 +121,30 @@ bool aln_sort(const HitRef &a, const HitRef &b)
 }
 
 // Turns the hits of one read into BamRecords (src/BWAAligner.cpp:111-248).
+// Batch packing: the bam1_t structs and data blocks of many records in a few large blocks (one arena per packing thread).  A record
+// points into its arena through an aliasing shared_ptr, so the arena lives as long as any of its records and a record costs no
+// allocation of its own; bam1_t::mempolicy says so, and BamRecord::Own() gives a record private memory before its data could grow.
+struct RecordArena {
+    std::vector<void *> blocks;
+    uint8_t *cur = nullptr; size_t left = 0;
+    void *alloc(size_t n)
+    {
+        n = (n + 15) & ~(size_t)15;
+        if (n > left) {
+            size_t sz = std::max<size_t>(n, (size_t)1 << 20);
+            void *p = std::malloc(sz);
+            if (!p) throw std::bad_alloc();
+            blocks.push_back(p); cur = (uint8_t *)p; left = sz;
+        }
+        void *r = cur; cur += n; left -= n;
+        return r;
+    }
+    ~RecordArena() { for (void *p : blocks) std::free(p); }
+};
+
 void emit_records(const std::string &seq, const std::string &name, const b200_results_view_t &v, int64_t read, bool hardclip,
-                  double keepSecFrac, int maxSecondary, bool primary_first, BamRecordPtrVector &out)
+                  double keepSecFrac, int maxSecondary, bool primary_first, BamRecordPtrVector &out,
+                  const std::shared_ptr<RecordArena> &arena = std::shared_ptr<RecordArena>())
 {
     int64_t b0 = v.hit_off[read], b1 = v.hit_off[read + 1];
     int n_regs = (int)(b1 - b0);
@@ -148,7 +171,13 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
         bool tooMany = isSec && (int(i) > maxSecondary);                 // Q2: rank, not a secondary counter
         if (tooLow || tooMany) continue;
         if (!isSec) primaryScore = h.score;                             // Q3
-        auto rec = std::make_shared<BamRecord>();
+        std::shared_ptr<BamRecord> rec;
+        if (arena) {
+            bam1_t *nb = (bam1_t *)arena->alloc(sizeof(bam1_t));
+            std::memset(nb, 0, sizeof(bam1_t));
+            nb->mempolicy = BAM_USER_OWNS_STRUCT | BAM_USER_OWNS_DATA;
+            rec = std::make_shared<BamRecord>(std::shared_ptr<bam1_t>(arena, nb));
+        } else rec = std::make_shared<BamRecord>();
         bam1_t *b = rec->b.get();
         b->core.tid = h.rid; b->core.pos = h.pos; b->core.qual = (uint8_t)h.mapq; b->core.flag = (uint16_t)h.flag;
         b->core.n_cigar = (uint32_t)h.n_cigar; b->core.mtid = -1; b->core.mpos = -1; b->core.isize = 0;
@@ -173,7 +202,7 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
         {   // room for the three integer tags appended below (3 x 7 bytes), rounded like bam_aux_append's kroundup32 would
             // leave it after the third append: one allocation instead of four
             size_t m = (size_t)b->l_data + 21; --m; m |= m >> 1; m |= m >> 2; m |= m >> 4; m |= m >> 8; m |= m >> 16; ++m;
-            b->data = (uint8_t *)std::malloc(m);
+            b->data = arena ? (uint8_t *)arena->alloc(m) : (uint8_t *)std::malloc(m);
             if (!b->data) throw std::bad_alloc();
             b->m_data = (uint32_t)m;
         }
@@ -214,9 +243,13 @@ void emit_records(const std::string &seq, const std::string &name, const b200_re
         }
         // Q4: the reference sets qual[0] = 0xff and leaves the rest uninitialised; here the whole string is "absent"
         if (sl) std::memset(bam_get_qual(b), 0xff, sl);
-        rec->AddIntTag("NA", n_regs);
-        rec->AddIntTag("NM", h.NM);
-        rec->AddIntTag("AS", h.score);                                   // Q5: no XA tag is ever produced
+        {   // the three integer tags, as bam_aux_append would write them; the room was allocated above (Q5: no XA tag is ever produced)
+            const int32_t vals[3] = {n_regs, h.NM, h.score};
+            static const char tags[3][3] = {"NA", "NM", "AS"};
+            uint8_t *t = b->data + b->l_data;
+            for (int k = 0; k < 3; ++k, t += 7) { t[0] = (uint8_t)tags[k][0]; t[1] = (uint8_t)tags[k][1]; t[2] = 'i'; std::memcpy(t + 3, &vals[k], 4); }
+            b->l_data += 21;
+        }
         out.push_back(rec);
     }
 }
@@ -227,9 +260,11 @@ namespace detail {
 // test seam: the record assembly of alignSequence on regions that are already computed (tests/cxx/wraptest.cpp feeds it the
 // reference's own regions and compares the records with oracle/oracle_wrap.cpp)
 void RecordsFromRegions(const std::string &seq, const std::string &name, const b200_results_view_t &v, int64_t read, bool hardclip,
-                        double keepSecFrac, int maxSecondary, BamRecordPtrVector &out)
+                        double keepSecFrac, int maxSecondary, BamRecordPtrVector &out, bool batch_packing)
 {
-    emit_records(seq, name, v, read, hardclip, keepSecFrac, maxSecondary, false, out);
+    // batch_packing: the arena packing of alignSequences instead of the per-record allocation of alignSequence
+    if (batch_packing) emit_records(seq, name, v, read, hardclip, keepSecFrac, maxSecondary, false, out, std::make_shared<RecordArena>());
+    else emit_records(seq, name, v, read, hardclip, keepSecFrac, maxSecondary, false, out);
 }
 } // namespace detail
 
@@ -275,12 +310,29 @@ void BWAAligner::alignSequences(const UnalignedSequenceVector &reads, std::vecto
     out.clear();
     out.resize(n);
     if (index_->IsEmpty() || reads.empty()) return;
-    std::vector<int64_t> off(n + 1, 0), ids(n);
+    // offsets, tie-break ids and the flattened bases live in page-locked memory of the library's pool: the call below then moves
+    // them by DMA instead of through the driver's staging copies of pageable memory
+    // (small batches keep to the heap: page-locking costs more than it saves there)
+    struct HostBuf {
+        void *p = nullptr; bool pinned;
+        HostBuf(size_t bytes, bool pin) : pinned(pin)
+        {
+            if (!pin) { p = std::malloc(bytes ? bytes : 1); if (!p) throw std::bad_alloc(); }
+            else if (b200_host_alloc(bytes ? bytes : 1, &p) != B200_OK) throw std::runtime_error(std::string("BWAAligner::alignSequences: ") + b200_last_error());
+        }
+        ~HostBuf() { if (pinned) b200_host_free(p); else std::free(p); }
+        HostBuf(const HostBuf &) = delete; HostBuf &operator=(const HostBuf &) = delete;
+    };
+    const bool pin = n >= 4096;
+    HostBuf off_b((n + 1) * sizeof(int64_t), pin), ids_b(n * sizeof(int64_t), pin);
+    int64_t *off = (int64_t *)off_b.p, *ids = (int64_t *)ids_b.p;
+    off[0] = 0;
     for (size_t i = 0; i < n; ++i) { off[i + 1] = off[i] + (int64_t)reads[i].Seq.size(); ids[i] = lrand48(); }
-    std::unique_ptr<char[]> all(new char[(size_t)off.back() + 1]);
-    on_threads([&](unsigned t) { for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) std::memcpy(all.get() + off[i], reads[i].Seq.data(), reads[i].Seq.size()); });
+    HostBuf all_b((size_t)off[n] + 1, pin);
+    char *all = (char *)all_b.p;
+    on_threads([&](unsigned t) { for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i) std::memcpy(all + off[i], reads[i].Seq.data(), reads[i].Seq.size()); });
     b200_results_t *res = nullptr;
-    int rc = b200_mem_align_batch(index_->handle(), &opt_, (int64_t)n, all.get(), off.data(), ids.data(), &res);
+    int rc = b200_mem_align_batch(index_->handle(), &opt_, (int64_t)n, all, off, ids, &res);
     if (rc != B200_OK) throw std::runtime_error(std::string("BWAAligner::alignSequences: ") + b200_last_error());
     b200_results_view_t v;
     b200_results_view(res, &v);
@@ -288,8 +340,9 @@ void BWAAligner::alignSequences(const UnalignedSequenceVector &reads, std::vecto
     std::vector<std::exception_ptr> errs(nt);
     auto work = [&](unsigned t) {
         try {
+            auto arena = std::make_shared<RecordArena>();
             for (size_t i = n * t / nt, e = n * (t + 1) / nt; i < e; ++i)
-                emit_records(reads[i].Seq, reads[i].Name, v, (int64_t)i, hardclip, keepSecFrac, maxSecondary, false, out[i]);
+                emit_records(reads[i].Seq, reads[i].Name, v, (int64_t)i, hardclip, keepSecFrac, maxSecondary, false, out[i], arena);
         } catch (...) { errs[t] = std::current_exception(); }
     };
     on_threads(work);

@@ -107,15 +107,36 @@ std::string BamRecord::CigarString() const { std::ostringstream ss; ss << GetCig
 
 int32_t BamRecord::PositionEnd() const { return b ? (int32_t)b->core.pos + GetCigar().NumReferenceConsumed() : -1; }
 
+// A record packed into a batch block (mempolicy says the struct and the data are not its own) becomes an ordinary malloc'ed bam1_t
+// before anything may reallocate its data.
+void BamRecord::Own()
+{
+    if (!b || !(b->mempolicy & (BAM_USER_OWNS_STRUCT | BAM_USER_OWNS_DATA))) return;
+    bam1_t *n = (bam1_t *)calloc(1, sizeof(bam1_t));
+    if (!n) throw std::bad_alloc();
+    *n = *b;
+    n->mempolicy = 0;
+    n->data = nullptr;
+    if (b->data) {
+        n->m_data = b->m_data ? b->m_data : (uint32_t)b->l_data;
+        n->data = (uint8_t *)malloc(n->m_data ? n->m_data : 1);
+        if (!n->data) { free(n); throw std::bad_alloc(); }
+        memcpy(n->data, b->data, (size_t)b->l_data);
+    }
+    b = std::shared_ptr<bam1_t>(n, Bam1Free());
+}
+
 void BamRecord::AddIntTag(const std::string &tag, int32_t val)
 {
     if (tag.size() < 2) return;
+    Own();
     aux_append(b.get(), tag.data(), 'i', 4, (const uint8_t *)&val);
 }
 
 void BamRecord::AddZTag(std::string tag, std::string val)
 {
     if (tag.size() < 2 || val.empty()) return;
+    Own();
     aux_append(b.get(), tag.data(), 'Z', (int)val.size() + 1, (const uint8_t *)val.c_str());
 }
 

@@ -19,6 +19,22 @@ extern "C" int64_t wraptest_records(const char *seq_, int l_seq, const char *nam
     try {
         SeqLib::detail::RecordsFromRegions(std::string(seq_, (size_t)l_seq), std::string(name_), v, 0, hardclip != 0, keepSecFrac, maxSecondary, recs);
     } catch (const std::out_of_range &) { if (n_rec) *n_rec = -1; return -1; }
+    {   // the batch path's arena packing must make the same records, and a record must survive getting memory of its own
+        SeqLib::BamRecordPtrVector recs2;
+        SeqLib::detail::RecordsFromRegions(std::string(seq_, (size_t)l_seq), std::string(name_), v, 0, hardclip != 0, keepSecFrac, maxSecondary, recs2, true);
+        if (recs2.size() != recs.size()) { if (n_rec) *n_rec = -2; return -2; }
+        for (size_t i = 0; i < recs.size(); ++i) {
+            const bam1_t *a = recs[i]->b.get(), *c = recs2[i]->b.get();
+            if (memcmp(&a->core, &c->core, sizeof(a->core)) || a->l_data != c->l_data || memcmp(a->data, c->data, (size_t)a->l_data) ||
+                !(c->mempolicy & BAM_USER_OWNS_DATA) || a->mempolicy) { if (n_rec) *n_rec = -2; return -2; }
+            std::vector<uint8_t> before(c->data, c->data + c->l_data);
+            recs2[i]->AddZTag("BC", "xyz");
+            const bam1_t *d = recs2[i]->b.get();
+            std::string got;
+            if (d->mempolicy || d->l_data != (int)before.size() + 7 || memcmp(d->data, before.data(), before.size()) ||
+                !recs2[i]->GetZTag("BC", got) || got != "xyz") { if (n_rec) *n_rec = -3; return -3; }
+        }
+    }
     std::vector<uint8_t> o;
     for (auto &r : recs) {
         const bam1_t *b = r->b.get();
