@@ -108,27 +108,27 @@ __global__ void __launch_bounds__(128, MINB) k_stage_occ(const __grid_constant__
 //   (read r owns [r * stride, (r+1) * stride)), in production order; k_sort_intv orders them afterwards.
 //   Reads the machine does not take (N bases, list or slot overflow) get OVF_INTV and go through the spill pass,
 //   i.e. the reference-shaped k_stage<0>.
-// The work list of k_seed2 in shared memory: 12 bytes per entry (word k of entry e of thread t at [(3 e + k) * 128 + t], conflict
-// free): x0, x1 low words; x0 / x1 high nibbles | size (16 bits) | end (8 bits).  Entries whose size does not fit 16 bits are
-// strings of at most ~8 bases: a table answers every extension of them and they can never be reported as seeds, so their interval
-// is not kept (take() says so, and the machine sends the read to the spill path if it ever asks for one).  336 bytes of shared
-// memory per thread instead of 432: five blocks per SM instead of four.
+// The ring of long work-list entries of k_seed2 in shared memory: 12 bytes per entry (word k of entry e of thread t at
+// [(3 e + k) * 128 + t], conflict free): x0, x1 low words; then x0 / x1 high bits | size | end (8 bits).  The 24 bits in front of the
+// end hold `hb` high bits of each coordinate and 24 - 2 hb bits of size: hb = 1 for texts below 2^33 symbols (a human-sized
+// reference: sizes up to 4.19 M, i.e. every repeat family keeps its entries in the ring), hb = 4 up to 2^36 (sizes up to 65 534).
+// An entry whose size does not fit is not kept: take() says so and the machine sends the read to the reference-shaped kernel.
 struct SmemList {
-    u32 *p;
+    u32 *p; int hb;
     __device__ __forceinline__ void put(int e, u64 x0, u64 x1, u64 x2, u32 end)
     {
         u32 *q = p + e * 384;
+        const u32 smax = (1u << (24 - 2 * hb)) - 1u;
         q[0] = (u32)x0; q[128] = (u32)x1;
-        q[256] = (u32)(x0 >> 32) | (u32)(x1 >> 32) << 4 | (x2 < 0xffffull ? (u32)x2 : 0xffffu) << 8 | end << 24;
+        q[256] = (u32)(x0 >> 32) | (u32)(x1 >> 32) << hb | (x2 < (u64)smax ? (u32)x2 : smax) << (2 * hb) | end << 24;
     }
-    __device__ __forceinline__ void put_end(int e, u32 end) { p[e * 384 + 256] = 0xffffu << 8 | end << 24; }
     __device__ __forceinline__ bool take(int e, u64 &x0, u64 &x1, u64 &x2, u32 &end) const
     {
         const u32 *q = p + e * 384;
-        const u32 w = q[256];
-        x0 = (u64)q[0] | (u64)(w & 15u) << 32; x1 = (u64)q[128] | (u64)((w >> 4) & 15u) << 32;
-        x2 = (w >> 8) & 0xffffu; end = w >> 24;
-        return x2 != 0xffffull;
+        const u32 w = q[256], hm = (1u << hb) - 1u, smax = (1u << (24 - 2 * hb)) - 1u;
+        x0 = (u64)q[0] | (u64)(w & hm) << 32; x1 = (u64)q[128] | (u64)((w >> hb) & hm) << 32;
+        x2 = (w >> (2 * hb)) & smax; end = w >> 24;
+        return x2 != (u64)smax;
     }
     __device__ __forceinline__ u32 end(int e) const { return p[e * 384 + 256] >> 24; }
 };
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128, MINB) k_seed2(const __grid_constant__ KAr
     // hints / a persisting window for the low table levels (no change in hit rate or time, profiles/r02_seed_l2hint_ab.txt);
     // entry ends in shared memory + intervals in an L2-resident global slot (6 blocks per SM but a global access per step: no gain).
     extern __shared__ u32 seed_smem[];
-    SmemList L; L.p = seed_smem + threadIdx.x;
+    SmemList L; L.p = seed_smem + threadIdx.x; L.hb = A.ix.seq_len < (1ull << 33) ? 1 : 4;
     u32 *myq = seed_smem + CAP * 384 + threadIdx.x;
     SmemQuery Q; Q.p = myq;
     myq[qw * 128] = 0;

@@ -393,3 +393,44 @@ def test_reference_with_ambiguous_bases_keeps_off_the_text_path(capi):
     idx2 = capi.Index.construct(["c1"], [clean])
     capi.align(idx2, reads[:500], opt, ids[:500])
     assert capi.last_stats()["tab_lookups_lo"] > 0
+
+
+def test_high_copy_repeat_family_vs_live_reference(capi):
+    """150 000 copies of a 300-bp element (3 % divergence) in a 60 Mb reference: 15-mers of the element occur ~95 000 times, so the
+    seeding machine's ring holds entries whose interval sizes exceed 16 bits (22-bit size field for texts below 2^33 symbols).  Hits
+    equal the live reference's, and the reads stay on the fast path (no spill pass)."""
+    from oracle import pyref
+    from seqlib_b200 import synth
+    if not pyref.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.Generator(np.random.PCG64(20240))
+    n_copy, el, sp = 150_000, 300, 100
+    elem = rng.integers(0, 4, el, dtype=np.uint8)
+    ref = rng.integers(0, 4, n_copy * (el + sp), dtype=np.uint8)
+    cop = np.tile(elem, n_copy).reshape(n_copy, el)
+    mut = rng.random((n_copy, el)) < 0.03
+    cop[mut] = (cop[mut] + rng.integers(1, 4, int(mut.sum()), dtype=np.uint8)) & 3
+    ref.reshape(n_copy, el + sp)[:, :el] = cop
+    l_pac = len(ref)
+    pac = np.zeros((l_pac + 3) // 4 + 1, np.uint8)
+    r4 = np.concatenate([ref, np.zeros((-l_pac) % 4, np.uint8)]).reshape(-1, 4)
+    pac[: len(r4)] = (r4[:, 0] << 6 | r4[:, 1] << 4 | r4[:, 2] << 2 | r4[:, 3]).astype(np.uint8)
+    ctg = synth.contigs_for(l_pac, 3)
+    idx = capi.Index.construct_pac(pac, l_pac, ctg, keep_host=True)
+    n = 1500
+    starts = rng.integers(0, l_pac - 150, n)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = []
+    for s in starts:
+        r = ref[s:s + 150].copy()
+        m = rng.random(150) < 0.01
+        r[m] = (r[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
+        reads.append(letters[r].tobytes().decode())
+    ids = cases.ids_for(n)
+    opt = capi.default_opt()
+    got = capi.align(idx, reads, opt, ids)
+    st = capi.last_stats()
+    ridx = pyref.RefIndex.from_view(idx.view(), keep=idx)
+    exp, _ = pyref.align(ridx, reads, pyref.default_opt(), ids, n_threads=os.cpu_count() or 1)
+    assert parity.compare_results(got, exp) == []
+    assert st["n_failed"] == 0
