@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(128, MINB) k_stage_occ(const __grid_constant__
 // end hold `hb` high bits of each coordinate and 24 - 2 hb bits of size: hb = 1 for texts below 2^33 symbols (a human-sized
 // reference: sizes up to 4.19 M, i.e. every repeat family keeps its entries in the ring), hb = 4 up to 2^36 (sizes up to 65 534).
 // An entry whose size does not fit is not kept: take() says so and the machine sends the read to the reference-shaped kernel.
+template <int hb>
 struct SmemList {
-    u32 *p; int hb;
+    u32 *p;
     __device__ __forceinline__ void put(int e, u64 x0, u64 x1, u64 x2, u32 end)
     {
         u32 *q = p + e * 384;
@@ -163,18 +164,18 @@ __global__ void k_pack_reads(const u8 *__restrict__ seq, const i64 *__restrict__
     if (n_base || (w == 0 && len > (i64)qw * 16)) atomicOr(bad + r, 1u);
 }
 
-template <int CAP, int MINB, int PHASED>
+template <int CAP, int MINB, int PHASED, int HB>
 __global__ void __launch_bounds__(128, MINB) k_seed2(const __grid_constant__ KArgs A, const u32 *__restrict__ packed, int qw, const u32 *__restrict__ bad, int stride)
 {
     // The SMEM passes (bwt_smem1a from every start, re-seeding of long SMEMs).  Tried and dropped (round 2): L2 eviction-policy
     // hints / a persisting window for the low table levels (no change in hit rate or time, profiles/r02_seed_l2hint_ab.txt);
     // entry ends in shared memory + intervals in an L2-resident global slot (6 blocks per SM but a global access per step: no gain).
     extern __shared__ u32 seed_smem[];
-    SmemList L; L.p = seed_smem + threadIdx.x; L.hb = A.ix.seq_len < (1ull << 33) ? 1 : 4;
+    SmemList<HB> L; L.p = seed_smem + threadIdx.x;
     u32 *myq = seed_smem + CAP * 384 + threadIdx.x;
     SmemQuery Q; Q.p = myq;
     myq[qw * 128] = 0;
-    SeedMachine<SmemList, SmemQuery> m;
+    SeedMachine<SmemList<HB>, SmemQuery> m;
     m.mode = 0; m.ovf = 0;
     CtrLocal ctr;
     i64 rid = -1;
@@ -664,16 +665,16 @@ static bool seed2_usable(const KArgs &A)
 {
     return seed2_enabled() && !A.order && A.caps.maxlen <= 255 && A.ix.seq_len < (1ull << 36) && A.B.pool.cap[POOL_INTV] >= A.B.n_reads * (i64)SEED2_STRIDE;
 }
-template <int CAP, int MINB, int PHASED = 0>
-static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
+template <int CAP, int MINB, int PHASED, int HB>
+static void launch_seed2_hb(Engine &E, KArgs &A, int qw)
 {
     size_t smem = (size_t)128 * (CAP * 12 + (qw + 1) * 4);
-    CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP, MINB, PHASED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CU_CHECK(cudaFuncSetAttribute(k_seed2<CAP, MINB, PHASED, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     int per = 0;
-    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP, MINB, PHASED>, 128, smem));
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seed2<CAP, MINB, PHASED, HB>, 128, smem));
     if (per < 1) per = 1;
     { static const int occ = getenv("B200_OCC_SEED") ? atoi(getenv("B200_OCC_SEED")) : 0; if (occ > 0 && occ < per) per = occ; }
-    k_seed2<CAP, MINB, PHASED><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
+    k_seed2<CAP, MINB, PHASED, HB><<<E.sms * per, 128, smem, E.st>>>(A, E.packed.as<u32>(), qw, E.seedflag.as<u32>(), SEED2_STRIDE);
     CU_CHECK(cudaGetLastError());
     // then the third pass
     size_t smem3 = (size_t)128 * (qw + 1) * 4;
@@ -682,6 +683,12 @@ static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
     if (per3 < 1) per3 = 1;
     CU_CHECK(cudaMemsetAsync(A.work_ctr, 0, 8, E.st));
     k_seed3<<<E.sms * per3, 128, smem3, E.st>>>(A, E.packed.as<u32>(), qw, SEED2_STRIDE);
+}
+template <int CAP, int MINB, int PHASED = 0>
+static void launch_seed2_cap(Engine &E, KArgs &A, int qw)
+{
+    if (A.ix.seq_len < (1ull << 33)) launch_seed2_hb<CAP, MINB, PHASED, 1>(E, A, qw);
+    else launch_seed2_hb<CAP, MINB, PHASED, 4>(E, A, qw);
 }
 static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
 {
@@ -696,10 +703,9 @@ static void launch_seed2(Engine &E, KArgs &A, int grid0 = 0)
     static int minb = getenv("B200_SEED_MINB") ? atoi(getenv("B200_SEED_MINB")) : 6;
     static int phased = getenv("B200_SEED_PHASED") ? atoi(getenv("B200_SEED_PHASED")) : 1;
     if (cap_sel == 8) launch_seed2_cap<8, 6, 1>(E, A, qw);
-    else if (cap_sel == 32) launch_seed2_cap<32, 5>(E, A, qw);
     else if (minb == 6 && phased) launch_seed2_cap<SEED2_CAP, 6, 1>(E, A, qw);
     else if (minb == 6) launch_seed2_cap<SEED2_CAP, 6>(E, A, qw);
-    else launch_seed2_cap<SEED2_CAP, 5>(E, A, qw);
+    else launch_seed2_cap<SEED2_CAP, 6>(E, A, qw);
     CU_CHECK(cudaGetLastError());
     k_sort_intv<<<(unsigned)((n + 127) / 128), 128, 0, E.st>>>(A.B.rec, A.B.ovf, n, A.B.pool.intv);
     CU_CHECK(cudaGetLastError());

@@ -38,7 +38,10 @@ inline Caps default_caps(int maxlen, bool tiny = false)
     Caps c;
     c.maxlen = maxlen;
     if (tiny) { c.intv = 6; c.wchains = 3; c.wseeds = 6; c.seeds = 4; c.regs = 2; c.cigar = 3; c.md = 6; c.z = 1024; }
-    else { c.intv = 64; c.wchains = 64; c.wseeds = 160; c.seeds = 96; c.regs = 24; c.cigar = 24; c.md = 96; c.z = (i64)maxlen * 256; }
+    // main-pass slots: sized so that reads inside interspersed repeats (hundreds of seeds, dozens of chains and regions) stay in the main
+    // pass -- on a reference with a 10 % / 12 %-divergence repeat family 3.8 % of the reads overflowed slots a quarter this size and the
+    // spill pass took 80 % of the time (scripts/repeat_probe.py); untouched slot space costs nothing but address range
+    else { c.intv = 64; c.wchains = 256; c.wseeds = 640; c.seeds = 384; c.regs = 96; c.cigar = 24; c.md = 96; c.z = (i64)maxlen * 256; }
     return c;
 }
 
