@@ -67,7 +67,7 @@ struct KArgs {
     u8 *scratch; size_t scratch_stride;
     unsigned long long *work_ctr; DevCounters *ctrs;
     const double *log_tab; int n_log;
-    SeedTab tab;                            // prefix-interval tables of the index (seed2.cuh); K == 0: none
+    SeedTab tab;                            // prefix-chain table of the index + text-path permission (seed2.cuh); K == 0: no table
     const unsigned long long *n_work_dev;   // when set: the number of work items lives on the device (retry lists)
 };
 
@@ -100,9 +100,9 @@ template <int STAGE, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_stage_occ(const __grid_constant__ KArgs A) { stage_body<STAGE>(A); }
 
 // ---------------------------------------------------------------------------------------
-// Seeding, main pass: the single-extension-site machine of seed2.cuh.
-//   shared memory per block: CAP packed intervals per thread (entry e of thread t at [e * 128 + t], 16 B each, so a
-//   warp's access is four conflict-free 128-byte wavefronts) + the read as 2-bit words (word w of thread t at [w * 128 + t]).
+// Seeding, main pass: the single-gather-site machine of seed2.cuh.
+//   shared memory per block: a ring of CAP packed long entries per thread (12 B each, see SmemList) + the read as 2-bit words (word w of
+//   thread t at [w * 128 + t]); the short entries of a sweep are a bit mask in a register.
 //   A lane whose read is finished records it and claims the next one by itself, so the 32 lanes stay inside the one
 //   loop and reach the Occ gathers together.  Intervals go straight to the read's fixed slot of the interval pool
 //   (read r owns [r * stride, (r+1) * stride)), in production order; k_sort_intv orders them afterwards.
@@ -234,7 +234,6 @@ __global__ void __launch_bounds__(128, MINB) k_seed2(const __grid_constant__ KAr
 // work list, 48 bytes of shared memory per thread -- occupancy and convergence that the mixed kernel cannot have.
 struct NoList {
     __device__ __forceinline__ void put(int, u64, u64, u64, u32) {}
-    __device__ __forceinline__ void put_end(int, u32) {}
     __device__ __forceinline__ bool take(int, u64 &, u64 &, u64 &, u32 &) const { return false; }
     __device__ __forceinline__ u32 end(int) const { return 0; }
 };

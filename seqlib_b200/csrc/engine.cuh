@@ -123,7 +123,7 @@ struct b200_index {
     // device image
     void *d_blob = nullptr; b200::i64 blob_bytes = 0; bool owns_blob = false;
     b200::DevIndex dev;
-    // prefix-interval tables of the seeding kernel (seed2.cuh): derived from the image, built on first use, never part of the blob
+    // prefix-chain table of the seeding kernel (seed2.cuh) and the verdict of the text proof: derived from the image, built on first use, never part of the blob
     mutable void *d_seedtab = nullptr; mutable int seedtab_K = -1, seed_text_ok = 0; mutable std::mutex seedtab_mu;
     ~b200_index();
 };

@@ -1,17 +1,15 @@
-// seed2.cuh -- mem_collect_intv (bwa/bwamem.c:140-188) shaped for the GPU: one extension site.
+// seed2.cuh -- mem_collect_intv (bwa/bwamem.c:140-188) shaped for the GPU: one gather site.
 //
 // seed.cuh states SMEM seeding as the reference does (bwt_smem1a / bwt_seed_strategy1, bwa/bwt.c:289-379): nested
 // loops with bwt_extend in three places, two work lists of 32-byte intervals per read in scratch memory.  Profiled on
 // a B200 that shape is bound by instruction issue (a third of the lanes active) and by scratch traffic, not by the
-// Occ gathers.  Here the same computation is a small machine that yields every extension:
+// Occ gathers.  Here the same computation is a small machine that yields every memory access it depends on:
 //
-//     request(a, o, s, c)  ->  extend_lean  ->  consume(na, no, ns)
+//     request(...)  ->  gather (two 256-bit loads)  ->  consume / consume_chain / consume_aux
 //
-// so a warp has ONE place where the two dependent 32-byte Occ gathers and the popcounts happen, reached by all lanes
-// together.  The work list is a single array of 16-byte packed intervals (coordinates < 2^36, end < 2^16) that the
-// forward sweep fills from the top down -- it is born reversed, as the reference wants it after its in-place
-// reversal -- and that the backward sweep compacts in place (row i+1 never has more survivors than row i read so
-// far).  The caller keeps that list in shared memory.  SMEMs shorter than min_seed_len are dropped when they are
+// so a warp has ONE place where the dependent gathers happen, reached by all lanes together.  The work list of a
+// bwt_smem1a call is a bit mask (strings shorter than K bases) plus a small ring of packed intervals in the caller's
+// shared memory (see SeedMachine).  SMEMs shorter than min_seed_len are dropped when they are
 // produced (the reference drops them after each bwt_smem1 call; the "is this SMEM contained in the previous one"
 // test uses the unfiltered start, kept in a register).  Intervals leave in production order; the final order is
 // the sort by (start, end), done by the caller -- equal keys mean the same substring and therefore identical
@@ -596,8 +594,7 @@ struct SeedMachine {
 struct ArrayList {
     PIntv *p;
     HD void put(int e, u64 x0, u64 x1, u64 x2, u32 end) { p[e] = pintv_pack(x0, x1, x2, end); }
-    HD void put_end(int e, u32 end) { p[e] = pintv_pack(0, 0, 0, end); }          // x0 == 0: no interval (every interval starts at >= 1)
-    HD bool take(int e, u64 &x0, u64 &x1, u64 &x2, u32 &end) const { pintv_unpack(p[e], x0, x1, x2, end); return x0 != 0; }
+    HD bool take(int e, u64 &x0, u64 &x1, u64 &x2, u32 &end) const { pintv_unpack(p[e], x0, x1, x2, end); return true; }
     HD u32 end(int e) const { return p[e].w3 >> 16; }
 };
 struct ByteQuery {
