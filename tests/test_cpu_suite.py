@@ -369,3 +369,23 @@ def test_compare_prefix_detects_changes():
     g3.hits = g3.hits.copy(); g3.hits["mapq"][7] += 1
     bad, msgs = parity.compare_prefix(g3, gold, n)
     assert bad == 1 and "mapq" in msgs[0]
+
+
+def test_aligner_half_fails_loudly_without_a_device():
+    """No CPU fallback in the product: without a CUDA device the aligner entry points (index construction, batch alignment, the
+    ksw batch, page-locked host memory) return B200_ERR_CUDA / B200_ERR_NOMEM instead of computing anything on the host."""
+    import ctypes as C
+    from seqlib_b200 import capi
+    if not os.path.exists(capi.SO_PATH):
+        pytest.skip("libseqlib_b200.so not built")
+    L = capi.lib()
+    if L.b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.B200Error):
+        capi.Index.construct(["c"], ["ACGTACGTTTGACCAGT" * 20])
+    L.b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.b200_host_alloc.restype = C.c_int
+    p = C.c_void_p()
+    assert L.b200_host_alloc(1 << 20, C.byref(p)) != 0 and not p.value
+    L.b200_host_free.argtypes = [C.c_void_p]
+    L.b200_host_free(None)                      # harmless
